@@ -1,0 +1,84 @@
+"""In-tree builds of the native libraries (no JIT cache: the .so files travel with the repo).
+
+libctts_front.so  plain C host front end (gcc)
+libctts_gpu.so    C-ABI + hand-written sm_100a kernels (nvcc, -fmad=false: the
+                  reference is built without FMA contraction and discrete
+                  decisions flip on 1-ulp differences)
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+INCLUDE = os.path.join(ROOT, "include")
+CSRC = os.path.join(PKG_DIR, "csrc")
+
+FRONT_SO = os.path.join(PKG_DIR, "libctts_front.so")
+GPU_SO = os.path.join(PKG_DIR, "libctts_gpu.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _newer(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _headers() -> list[str]:
+    return [os.path.join(INCLUDE, h) for h in os.listdir(INCLUDE) if h.endswith(".h")]
+
+
+def build_front(force: bool = False) -> str:
+    src = os.path.join(CSRC, "front", "ctts_front.c")
+    deps = [src] + _headers()
+    if not force and _newer(FRONT_SO, deps):
+        return FRONT_SO
+    cc = shutil.which("gcc") or "cc"
+    cmd = [cc, "-O2", "-std=c99", "-ffp-contract=off", "-Wall", "-Wextra", "-fPIC", "-shared",
+           "-I", INCLUDE, "-o", FRONT_SO, src, "-lm"]
+    subprocess.run(cmd, check=True)
+    return FRONT_SO
+
+
+def gpu_sources() -> list[str]:
+    d = os.path.join(CSRC, "gpu")
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith((".cu", ".c")))
+
+
+def build_gpu(force: bool = False, verbose: bool = False) -> str:
+    d = os.path.join(CSRC, "gpu")
+    srcs = gpu_sources()
+    deps = srcs + _headers() + [os.path.join(d, f) for f in os.listdir(d) if f.endswith((".cuh", ".h"))]
+    if not force and _newer(GPU_SO, deps):
+        return GPU_SO
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cus = [s for s in srcs if s.endswith(".cu")]
+    cs = [s for s in srcs if s.endswith(".c")]
+    objs = []
+    # the host tables use libm cosf/sinf with C promotion rules: compile them as C
+    cc = shutil.which("gcc") or "cc"
+    for s in cs:
+        o = s[:-2] + ".o"
+        subprocess.run([cc, "-O2", "-std=c99", "-ffp-contract=off", "-fPIC", "-I", INCLUDE, "-c", s, "-o", o],
+                       check=True)
+        objs.append(o)
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-I", INCLUDE, "-I", d, "-o", GPU_SO] + cus + objs + ["-lcudart"]
+    subprocess.run(cmd, check=True)
+    return GPU_SO
+
+
+def build_oracle() -> None:
+    """Builds the TEST oracle (oracle/libctts_oracle.so, and oracle/_ref when the reference tree exists)."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], check=True,
+                   stdout=subprocess.DEVNULL)

@@ -1,0 +1,109 @@
+/*
+ * ctts_gpu.h -- C-ABI of the B200 (sm_100a) batched audio-assembly back end.
+ *
+ * Exported by libctts_gpu.so.  Plain pointers and sizes only.  This is the
+ * boundary the reference does not have: it replaces every sample-touching
+ * statement of `ctts_synthesize` (ctts.c:3689-3921) -- unit gather
+ * (get_unit_samples :1557), normalize_rms :1709, smooth_pitch_boundary :1979,
+ * match_boundary_energy :1730, buffer_append_crossfade :3279,
+ * buffer_append_silence :3361, apply_fade_out :3028, remove_silence_regions
+ * :1634, apply_phrase_intonation :2736, time_stretch :3490 -- for a whole batch
+ * of utterances described by a CSR plan (ctts_plan.h) that the unchanged host
+ * front end emits.
+ *
+ * Conventions follow the reference API (ctts.h:175-346): 0 on success,
+ * negative CTTS_ERR_* on failure (plus CTTS_GPU_ERR_* below); caller-owned
+ * output buffers (no hidden malloc per utterance); one context per GPU; a
+ * context is used by one host thread at a time.  There is NO CPU fallback:
+ * without a CUDA device every entry point fails with CTTS_GPU_ERR_CUDA.
+ */
+#ifndef CTTS_GPU_H
+#define CTTS_GPU_H
+
+#include "ctts_plan.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTTS_GPU_OK 0
+#define CTTS_GPU_ERR_INVALID_ARG (-1)    /* == CTTS_ERR_INVALID_ARG */
+#define CTTS_GPU_ERR_INVALID_FORMAT (-5) /* == CTTS_ERR_INVALID_FORMAT (voice.db) */
+#define CTTS_GPU_ERR_OUT_OF_MEMORY (-6)  /* == CTTS_ERR_OUT_OF_MEMORY */
+#define CTTS_GPU_ERR_VERSION (-8)        /* == CTTS_ERR_VERSION */
+#define CTTS_GPU_ERR_CUDA (-100)         /* CUDA runtime error, see ctts_gpu_last_error */
+#define CTTS_GPU_ERR_BOUNDS (-101)       /* an output slot is smaller than its upper bound */
+#define CTTS_GPU_ERR_DEVICE (-102)       /* a kernel reported an internal capacity error */
+
+typedef struct ctts_gpu_ctx ctts_gpu_ctx;
+typedef struct ctts_gpu_plan ctts_gpu_plan;
+
+/* Replaces ctts_init (ctts.c:1117) for the back end: parses the same voice.db
+ * bytes (header ctts.h:84-98, index :101-111), re-packs the PCM pool so every
+ * unit starts 16-byte aligned, uploads it with the fade LUTs (ctts.c:60-73)
+ * and Hann windows (ctts.c:1624, :2198), all computed on the host with libm. */
+int ctts_gpu_init(ctts_gpu_ctx** out, const void* voice_db, size_t db_size, int device_ordinal);
+/* Replaces ctts_free (ctts.c:1167). */
+void ctts_gpu_free(ctts_gpu_ctx* ctx);
+/* Kernels and copies are issued on `cuda_stream` (a cudaStream_t); NULL
+ * restores the context's own stream. */
+int ctts_gpu_set_stream(ctts_gpu_ctx* ctx, void* cuda_stream);
+const char* ctts_gpu_last_error(const ctts_gpu_ctx* ctx);
+
+/* Upper bound, per utterance, of the samples ctts_gpu_synth_batch may write
+ * (sum of unit lengths and silences; for speed != 1.0f the WSOLA bound
+ * num_frames*synthesis_hop + 512 of ctts.c:3515-3517). */
+int ctts_gpu_plan_bounds(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, uint64_t* out_bound);
+
+/* THE drop-in entry point: replaces the sample half of N calls of
+ * ctts_synthesize (ctts.c:3623).  Host buffers in, host buffers out,
+ * synchronous on return.  Utterance u's PCM is written to
+ * pcm_out[out_offsets[u] .. out_offsets[u] + out_counts[u]); out_offsets has
+ * n_utts+1 entries, each a multiple of 8 samples, and
+ * out_offsets[u+1]-out_offsets[u] must be >= ctts_gpu_plan_bounds()[u]. */
+int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan,
+                         const ctts_assembly_params* params, int16_t* pcm_out,
+                         const uint64_t* out_offsets, uint32_t* out_counts);
+
+/* ---- resident-plan path: upload once, run many times, PCM stays in HBM ---- */
+
+/* Uploads the plan, derives the per-utterance tasks and output layout
+ * (slots sized by the bounds, 16-byte aligned) and allocates workspace.
+ * `out_offsets` may be NULL (packed slots chosen by the library). */
+int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan,
+                         const ctts_assembly_params* params, const uint64_t* out_offsets,
+                         ctts_gpu_plan** out);
+void ctts_gpu_plan_destroy(ctts_gpu_plan* plan);
+/* total samples spanned by the output slots, and the slot offsets (n_utts+1) */
+uint64_t ctts_gpu_plan_out_samples(const ctts_gpu_plan* plan);
+int ctts_gpu_plan_out_offsets(const ctts_gpu_plan* plan, uint64_t* offsets);
+/* Enqueue the kernels for the whole batch on the context stream (asynchronous).
+ * d_pcm_out: device buffer of >= ctts_gpu_plan_out_samples() int16, or NULL to
+ * use a buffer owned by the plan. */
+int ctts_gpu_plan_run(ctts_gpu_ctx* ctx, ctts_gpu_plan* plan, int16_t* d_pcm_out);
+/* Waits for the stream, then copies counts (and checks device error flags). */
+int ctts_gpu_plan_read_counts(ctts_gpu_ctx* ctx, ctts_gpu_plan* plan, uint32_t* out_counts);
+/* Device -> host copy of the plan-owned PCM buffer range [first, first+n). */
+int ctts_gpu_plan_read_pcm(ctts_gpu_ctx* ctx, ctts_gpu_plan* plan, int16_t* dst, uint64_t first,
+                           uint64_t n);
+/* Debug / tests: pre-stretch buffer of utterance u (only for speed != 1.0f utterances). */
+int ctts_gpu_plan_read_pre(ctts_gpu_ctx* ctx, ctts_gpu_plan* plan, uint32_t u, int16_t* dst,
+                           uint64_t cap, uint64_t* n);
+
+typedef struct ctts_gpu_run_info {
+    uint32_t kernel_launches;    /* kernels enqueued by one ctts_gpu_plan_run */
+    uint32_t n_stretch;          /* utterances that go through WSOLA */
+    uint64_t gather_samples;     /* sum of unit lengths over the batch (PCM pool reads) */
+    uint64_t bound_samples;      /* sum of output upper bounds */
+    uint32_t smem_bytes;         /* dynamic shared memory of the assembly kernel */
+    uint32_t window_samples;     /* shared-memory window capacity per CTA */
+    uint32_t halo_samples;
+    uint32_t threads;
+} ctts_gpu_run_info;
+int ctts_gpu_plan_info(const ctts_gpu_plan* plan, ctts_gpu_run_info* info);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CTTS_GPU_H */

@@ -76,9 +76,3 @@ def build_gpu(force: bool = False, verbose: bool = False) -> str:
         ["-I", INCLUDE, "-I", d, "-o", GPU_SO] + cus + objs + ["-lcudart"]
     subprocess.run(cmd, check=True)
     return GPU_SO
-
-
-def build_oracle() -> None:
-    """Builds the TEST oracle (oracle/libctts_oracle.so, and oracle/_ref when the reference tree exists)."""
-    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], check=True,
-                   stdout=subprocess.DEVNULL)

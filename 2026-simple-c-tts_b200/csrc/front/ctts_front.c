@@ -1070,6 +1070,14 @@ void ctts_front_params(const ctts_front* f, ctts_assembly_params* out) {
     out->remove_dc_offset = f->cfg.remove_dc_offset ? 1u : 0u;
 }
 
+int ctts_front_word_end_op(const ctts_front* f, int type_id, int word_index, int total_words,
+                           ctts_plan_op* out) {
+    if (!f || !out || type_id < 0 || type_id > (int)PT_LISTING) return CTTS_FRONT_ERR_INVALID_ARG;
+    contour c = phrase_contour((phrase_type)type_id, f->cfg.max_pitch_change);
+    word_end_op(&c, word_index, total_words, f->cfg.max_pitch_change, f->cfg.remove_word_silence, out);
+    return CTTS_FRONT_OK;
+}
+
 int ctts_front_plan_batch(ctts_front* f, const char* const* texts, const float* speeds,
                           uint32_t n, ctts_batch_plan* out, uint32_t* stats) {
     if (!f || !out || (n && !texts)) return CTTS_FRONT_ERR_INVALID_ARG;

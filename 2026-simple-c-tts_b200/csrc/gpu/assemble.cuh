@@ -558,8 +558,8 @@ __device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t utt, 
 // collects the (at most two) 256-sample frames that cover it, in frame order;
 // the int16 overlap-add wraps exactly as the reference's `+=` does.  In place,
 // tile by tile, with the 256 originals behind the tile carried in shared memory.
-// Reads the reference performs past the end of its heap copy yield 0 here (see
-// oracle/ctts_oracle.h).
+// Reads the reference performs past the end of its heap copy (undefined
+// behaviour there, DESIGN.md "Reference UB") yield 0 here.
 __device__ void pitch_contour(const Smem& sm, int16_t* x, uint32_t n, float f0, float f1) {
     if (n < 100 || fabsf(f0 - f1) < 0.01f) return;
     if (n < PITCH_FRAME) return;  // no frame fits: every sample keeps its original value

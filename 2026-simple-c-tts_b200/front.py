@@ -118,6 +118,7 @@ def lib() -> C.CDLL:
         L.ctts_front_plan_batch.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
                                             C.c_uint32, C.POINTER(CBatchPlan), C.POINTER(C.c_uint32)]
         L.ctts_front_plan_free.argtypes = [C.POINTER(CBatchPlan)]
+        L.ctts_front_word_end_op.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ctts_front_plan_bounds.argtypes = [C.c_void_p, C.POINTER(CBatchPlan), C.c_void_p,
                                              C.c_void_p, C.c_void_p]
         _lib = L
@@ -195,6 +196,14 @@ class Front:
             lib().ctts_front_plan_free(C.byref(cp))
         st = stats[:2 * n].reshape(n, 2)
         return BatchPlan(begin, speed, ops, st[:, 0].copy(), st[:, 1].copy())
+
+    def word_end_op(self, phrase_type: int, word_index: int, total_words: int) -> np.ndarray:
+        """The WORD_END op for (phrase type, word index, word count): scalar half of apply_phrase_intonation."""
+        op = np.zeros(1, dtype=OP_DTYPE)
+        rc = lib().ctts_front_word_end_op(self._h, phrase_type, word_index, total_words, op.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"ctts_front_word_end_op failed: {rc}")
+        return op
 
     def bounds(self, plan: BatchPlan):
         """(pre, out, region) host upper bounds per utterance, see ctts_front_plan_bounds."""

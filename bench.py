@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 CTTS back end (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+One "step" is one pass of the audio-assembly hot path over one batch of
+synthetic utterances (default: BASELINE.json configs[2], 4096 sentences of ~200
+characters at speed 1.0 on the seeded synthetic voice).  Prints ONE JSON line.
+
+value      audio-seconds synthesised per second, plan and voice resident in HBM,
+           timed with CUDA events on the launching stream, max over ranks.
+e2e        the same through the drop-in C-ABI call ctts_gpu_synth_batch() with
+           host buffers (plan H2D and PCM D2H inside the timed region).
+roofline   algorithmic bytes of the assembly kernel / its duration / measured HBM peak.
+cpu_baseline  the unmodified reference (oracle/_ref/ctts_ref_bench, N processes) on a
+           bounded sample of the same workload, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SAMPLE_RATE = 22050
+METRIC = "audio_seconds_per_second"
+UNIT = "audio-s/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--utts", type=int, default=4096, help="utterances per GPU (weak scaling)")
+    ap.add_argument("--workload", default="speed1", choices=["speed1", "mixed"],
+                    help="speed1 = BASELINE configs[2]; mixed = configs[3] (speeds 0.5-2.0, WSOLA)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args, rank: int):
+    """Synthetic batch for one rank: texts, speeds."""
+    pkg = importlib.import_module("2026-simple-c-tts_b200")
+    texts = pkg.corpus.batch(args.utts, seed=1234 + 7919 * rank, target_chars=200)
+    if args.workload == "mixed":
+        speeds = pkg.corpus.mixed_speeds(args.utts, seed=99 + rank)
+    else:
+        speeds = np.ones(args.utts, dtype=np.float32)
+    return texts, speeds
+
+
+def workload_name(args) -> str:
+    if args.workload == "mixed":
+        return f"BASELINE configs[3]: {args.utts} synthetic sentences (~200 chars) per GPU at mixed speeds 0.5-2.0 (WSOLA)"
+    return f"BASELINE configs[2]: {args.utts} synthetic Portuguese sentences (~200 chars) per GPU at speed 1.0"
+
+
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch from the committed ncu capture, if any (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        self.tmp.close()
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(smax))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def run_reference_cpu(texts, speeds, db_bytes: bytes, n_sample: int, procs: int):
+    """Times oracle/_ref/ctts_ref_bench (the unmodified reference, N processes) on texts[:n_sample]."""
+    import harness as H
+    if not os.path.exists(H.REF_BENCH):
+        raise RuntimeError("oracle/_ref/ctts_ref_bench is missing (built from /root/reference by oracle/Makefile)")
+    with tempfile.TemporaryDirectory() as d:
+        dbp = os.path.join(d, "voice.db")
+        with open(dbp, "wb") as f:
+            f.write(db_bytes)
+        tsv = os.path.join(d, "texts.tsv")
+        with open(tsv, "w", encoding="utf-8") as f:
+            for t, s in zip(texts[:n_sample], speeds[:n_sample]):
+                f.write(f"{float(s):.3f}\t{t}\n")
+        r = subprocess.run([H.REF_BENCH, dbp, H.SHIPPED_YAML, H.NORM_CSV, tsv, str(procs)],
+                           capture_output=True, text=True, timeout=1800)
+        if r.returncode != 0:
+            raise RuntimeError(f"ctts_ref_bench failed: {r.stderr[-400:]}")
+        res = json.loads(r.stdout.strip().splitlines()[-1])
+    return res
+
+
+def cpu_sample_size(n_utts: int, cores: int, mixed: bool) -> int:
+    # ~30 ms/utt/core at speed 1.0, ~0.3 s/utt/core through WSOLA; aim at 10-20 s of wall time
+    per_core = 40 if mixed else 400
+    return int(max(1, min(n_utts, cores * per_core)))
+
+
+def main() -> int:
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation on the host cores; rank 0 alone runs it
+        if rank != 0:
+            return 0
+        import harness as H
+        texts, speeds = workload(args, 0)
+        db = H.synthetic_db()
+        n_sample = cpu_sample_size(args.utts, cores, args.workload == "mixed")
+        for _ in range(max(args.warmup, 0) and 1):
+            run_reference_cpu(texts, speeds, db, min(n_sample, cores), cores)
+        secs, samples = 0.0, 0
+        for _ in range(args.steps):
+            r = run_reference_cpu(texts, speeds, db, n_sample, cores)
+            secs += r["seconds"]
+            samples += r["samples"]
+        value = samples / SAMPLE_RATE / secs
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "voice": "seeded synthetic voice.db (1787 units)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": f"first {n_sample} utterances of the workload per step, {cores} processes of the unmodified reference (oracle/_ref/ctts_ref_bench)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the back end has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import harness as H
+    pkg = importlib.import_module("2026-simple-c-tts_b200")
+    gpu = importlib.import_module("2026-simple-c-tts_b200.gpu")
+
+    db = H.synthetic_db()
+    cfg = H.shipped_config()
+    fr = pkg.front.Front(db, cfg, H.NORM_CSV)
+    prm = fr.params()
+    texts, speeds = workload(args, rank)
+    t0 = time.time()
+    plan = fr.plan(texts, speeds)
+    plan_s = time.time() - t0
+
+    g = gpu.GpuSynth(db, local_rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    g.set_stream(stream.cuda_stream)
+    rp = g.create_plan(plan, prm)
+    info = rp.info()
+    out_samples = rp.out_samples
+    d_out = torch.empty(max(out_samples, 8), dtype=torch.int16, device=f"cuda:{local_rank}")
+
+    def sync_all():
+        torch.cuda.synchronize(local_rank)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(local_rank)
+
+    for _ in range(args.warmup):
+        rp.run(d_out.data_ptr())
+    counts = rp.counts()
+    audio_s = float(counts.astype(np.int64).sum()) / SAMPLE_RATE
+    n_out = int(counts.astype(np.int64).sum())
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sync_all()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with torch.cuda.stream(stream):
+        evs[0].record(stream)
+        for k in range(args.steps):
+            rp.run(d_out.data_ptr())
+            evs[k + 1].record(stream)
+    sync_all()
+    clocks = sampler.stop() if sampler else None
+    step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    total_ms = evs[0].elapsed_time(evs[args.steps])
+    rp.counts()  # surfaces device error flags
+
+    # ---- e2e through the drop-in call, host buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        offsets = rp.out_offsets()
+        host_out = torch.empty(max(out_samples, 8), dtype=torch.int16).pin_memory()
+        host_np = host_out.numpy()
+        e2e_steps = max(1, min(args.e2e_steps, args.steps))
+        g.synth_batch(plan, prm, host_np, offsets)  # warm-up (allocates the device buffer once)
+        sync_all()
+        te = time.perf_counter()
+        for _ in range(e2e_steps):
+            _, _, c2 = g.synth_batch(plan, prm, host_np, offsets)
+        torch.cuda.synchronize(local_rank)
+        e2e_s = (time.perf_counter() - te) / e2e_steps
+        h2d = int(plan.ops.nbytes + plan.utt_op_begin.nbytes + plan.speed.nbytes)
+        d2h = int(out_samples * 2 + 8 * plan.n_utts)
+        e2e = {"seconds_per_step": e2e_s, "h2d": h2d, "d2h": d2h, "steps": e2e_steps,
+               "audio_s": float(c2.astype(np.int64).sum()) / SAMPLE_RATE}
+
+    # ---- reduce over ranks: time = max, work = sum
+    t_rank = torch.tensor([total_ms, audio_s, e2e["seconds_per_step"] if e2e else 0.0,
+                           e2e["audio_s"] if e2e else 0.0], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        mx = t_rank.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t_rank.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms_all, audio_all = float(mx[0]), float(sm[1])
+        e2e_s_all, e2e_audio_all = float(mx[2]), float(sm[3])
+    else:
+        total_ms_all, audio_all = total_ms, audio_s
+        e2e_s_all, e2e_audio_all = (e2e["seconds_per_step"], e2e["audio_s"]) if e2e else (0.0, 0.0)
+
+    if rank == 0:
+        ms_per_step = total_ms_all / args.steps
+        value = audio_all / (ms_per_step / 1e3)
+        peak, peak_src = peak_hbm()
+        # algorithmic bytes of one launch of the assembly kernel:
+        # 2 B per gathered unit sample + 2 B per output sample + 32 B per plan op
+        alg_bytes = 2 * int(info.gather_samples) + 2 * n_out + int(plan.ops.nbytes)
+        kern_ms = float(np.mean(step_ms))
+        achieved = alg_bytes / (kern_ms / 1e3) / 1e9
+        dominant = "assemble_kernel" if args.workload == "speed1" else "wsola_search_kernel"
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16/f32", "data": "synthetic",
+            "config": {
+                "workload": workload_name(args),
+                "voice": "seeded synthetic voice.db (1787 units, 9.2 M samples), shipped config values",
+                "audio_seconds_per_gpu_step": audio_s, "plan_ops": int(plan.ops.shape[0]),
+                "l2": "output per step (%.2f GB) exceeds the 126 MB L2; the 18 MB voice pool is L2-resident by design" % (2 * n_out / 1e9),
+                "front_end_plan_seconds": plan_s,
+                "window_samples": int(info.window_samples), "smem_bytes": int(info.smem_bytes),
+            },
+            "gpu_launches": int(info.kernel_launches) * args.steps,
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(dominant), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
+                "note": "step = one assemble_kernel launch (+16 KB memset)" if args.workload == "speed1"
+                        else "step = assemble + wsola_search + wsola_ola; the stretch stage is FP32-issue bound, HBM fraction reported as the metric demands",
+            },
+        }
+        if e2e:
+            line["e2e"] = {"value": e2e_audio_all / e2e_s_all, "unit": UNIT,
+                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                           "steps": e2e["steps"], "ms_per_step": 1e3 * e2e_s_all,
+                           "call": "ctts_gpu_synth_batch (pinned host PCM buffer)"}
+        if not args.no_cpu_baseline:
+            try:
+                n_sample = cpu_sample_size(args.utts, cores, args.workload == "mixed")
+                r = run_reference_cpu(texts, speeds, db, n_sample, cores)
+                line["cpu_baseline"] = {
+                    "value": r["samples"] / SAMPLE_RATE / r["seconds"], "unit": UNIT, "cores": cores,
+                    "kind": "reference",
+                    "sample": f"first {n_sample} utterances of the same workload, {cores} processes of the unmodified reference (oracle/_ref/ctts_ref_bench), {r['seconds']:.1f} s",
+                }
+            except Exception as e:  # the GPU number stands on its own
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

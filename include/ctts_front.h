@@ -87,6 +87,13 @@ int ctts_front_plan_batch(ctts_front* f, const char* const* texts, const float* 
                           uint32_t n, ctts_batch_plan* out, uint32_t* stats);
 void ctts_front_plan_free(ctts_batch_plan* plan);
 
+/* The WORD_END op the walk emits for word `word_index` of `total_words` in a
+ * phrase of the given type (0 declarative, 1 interrogative, 2 exclamatory,
+ * 3 continuation, 4 listing: PhraseType, ctts.c:2526): the scalar half of
+ * apply_phrase_intonation (ctts.c:2740-2855).  Exposed for tests and tools. */
+int ctts_front_word_end_op(const ctts_front* f, int phrase_type, int word_index, int total_words,
+                           ctts_plan_op* out);
+
 /* Host-known upper bounds on sample counts of utterance u of a plan:
  * pre[u]  >= samples in the assembly buffer before time stretching
  *            (sum of unit lengths + silences; crossfades and trimming only shrink it),

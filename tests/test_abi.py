@@ -1,0 +1,55 @@
+"""The drop-in boundary: the shared libraries load and export every symbol the headers declare."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+
+def _declared(header: str) -> list[str]:
+    text = open(header).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ctts_(?:gpu|front)_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_gpu_library_exports_header_symbols(H):
+    gpu = H.importlib.import_module("2026-simple-c-tts_b200.gpu")
+    L = gpu.lib()
+    names = _declared(os.path.join(H.ROOT, "include", "ctts_gpu.h"))
+    assert "ctts_gpu_synth_batch" in names and "ctts_gpu_init" in names and len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_front_library_exports_header_symbols(H):
+    L = H.front.lib()
+    names = _declared(os.path.join(H.ROOT, "include", "ctts_front.h"))
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_plan_op_abi_is_32_bytes(H):
+    assert H.front.OP_DTYPE.itemsize == 32
+    assert C.sizeof(H.front.AssemblyParams) == 32
+    assert C.sizeof(H.front.Config) == 21 * 4
+
+
+def test_no_cpu_fallback_without_device(H, small_db):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    gpu = H.importlib.import_module("2026-simple-c-tts_b200.gpu")
+    with pytest.raises(gpu.GpuError):
+        gpu.GpuSynth(small_db, 0)
+
+
+def test_product_does_not_import_the_oracle(H):
+    # only tests/, smoke() and bench.py's baseline legs may touch oracle/
+    pkg_dir = os.path.join(H.ROOT, "2026-simple-c-tts_b200")
+    for root, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".c", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f), errors="replace").read()
+                for needle in ("libctts_oracle", "libctts_ref", "ctts_oracle", "oracle/", "ctts_ref_bench"):
+                    assert needle not in src, (f, needle)

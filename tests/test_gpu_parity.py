@@ -1,0 +1,229 @@
+"""Parity tests proper: the CUDA path through the C-ABI against the oracle (bit-exact), the
+committed reference vectors, and size-independent properties at full batch size.
+
+Run on a B200 with:  python -m pytest tests -m gpu
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(H):
+    return H.importlib.import_module("2026-simple-c-tts_b200.gpu")
+
+
+@pytest.fixture(scope="module")
+def synth_small(gpu, small_db):
+    return gpu.GpuSynth(small_db, 0)
+
+
+def _assert_same(got, want, what=""):
+    assert len(got) == len(want), f"{what}: length {len(got)} != {len(want)}"
+    if not np.array_equal(got, want):
+        d = np.nonzero(got != want)[0]
+        raise AssertionError(f"{what}: {len(d)} of {len(want)} samples differ, first at {d[:5]}, "
+                             f"max |d| {np.abs(got.astype(int) - want.astype(int)).max()}")
+
+
+def _check_plan(H, synth, oracle, prm, plan, what=""):
+    outs = synth.synth_list(plan, prm)
+    for u in range(plan.n_utts):
+        want, _ = oracle.synth(prm, plan.utt_ops(u), float(plan.speed[u]))
+        _assert_same(outs[u], want, f"{what} utt {u} speed {float(plan.speed[u])}")
+    return outs
+
+
+def test_config1_and_2_ola_mundo(H, synth_small, oracle_small, front_small, golden):
+    """BASELINE configs[0] and [1]: 'olá mundo' at 1.0 and at 1.5 (WSOLA), GPU vs oracle (±0)
+    and vs the PCM the compiled reference produced (±1 LSB as north_star states; observed ±0)."""
+    prm = front_small.params()
+    plan = front_small.plan(["olá mundo", "olá mundo"], [1.0, 1.5])
+    outs = _check_plan(H, synth_small, oracle_small, prm, plan, "olá mundo")
+    for k, got in enumerate(outs):
+        want = golden[f"e2e_pcm_{k}"]
+        assert len(got) == len(want)
+        assert np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 1   # tolerance: ±1 int16 LSB
+
+
+def test_golden_reference_pcm(H, synth_small, oracle_small, front_small, golden):
+    texts = [str(t) for t in golden["e2e_texts"]]
+    speeds = [float(s) for s in golden["e2e_speeds"]]
+    prm = front_small.params()
+    plan = front_small.plan(texts, speeds)
+    outs = synth_small.synth_list(plan, prm)
+    for k, got in enumerate(outs):
+        want = golden[f"e2e_pcm_{k}"]
+        assert len(got) == len(want), texts[k]
+        _, st = oracle_small.synth(prm, plan.utt_ops(k), 1.0)
+        if speeds[k] == 1.0:
+            ok = ~H.ub_mask(st, len(got))        # samples the reference computed from out-of-bounds reads
+            assert np.abs(got[ok].astype(np.int32) - want[ok].astype(np.int32)).max(initial=0) <= 1
+            assert np.array_equal(got[ok], want[ok])
+        elif st.ub_spans == 0:
+            assert np.array_equal(got, want), texts[k]
+
+
+def test_batch_speed1_bit_exact(H, synth_small, oracle_small, front_small):
+    texts = H.corpus.batch(64, seed=42)
+    prm = front_small.params()
+    plan = front_small.plan(texts)
+    _check_plan(H, synth_small, oracle_small, prm, plan, "batch64")
+
+
+def test_mixed_speeds_bit_exact(H, synth_small, oracle_small, front_small):
+    texts = H.corpus.batch(14, seed=43, target_chars=120)
+    speeds = [0.5, 0.6, 0.75, 0.9, 0.995, 1.0, 1.005, 1.1, 1.3, 1.5, 1.7, 2.0, 3.0, 0.2]
+    prm = front_small.params()
+    plan = front_small.plan(texts, speeds)
+    _check_plan(H, synth_small, oracle_small, prm, plan, "mixed")
+
+
+def test_edge_cases(H, synth_small, oracle_small, front_small):
+    texts = ["", " ", "   ", ".", "?!", "a", "@#$", "a-a-a", "...a...", "a,a;a:a.a!a?", "1", "21?", "100 000",
+             "á" * 40, "ai " * 30, "(a) [e] \"i\" 'o' `u`", "a\tb\nc\rd", "Dr. Sr. km etc.",
+             "casa-casa-casa-casa-casa-casa-casa-casa-casa-casa-casa-casa"]
+    prm = front_small.params()
+    for sp in (1.0, 1.5):
+        plan = front_small.plan(texts, [sp] * len(texts))
+        _check_plan(H, synth_small, oracle_small, prm, plan, f"edge@{sp}")
+
+
+def test_huge_region_uses_hbm_window(H, synth_small, oracle_small, front_small):
+    # one "word" far longer than the shared-memory window: commas do not reset the word mark
+    text = ",".join(["casa"] * 60)
+    prm = front_small.params()
+    plan = front_small.plan([text, "olá mundo", text + " fim"], [1.0, 1.0, 1.25])
+    pre, _, region = front_small.bounds(plan)
+    assert region[0] > 200000
+    _check_plan(H, synth_small, oracle_small, prm, plan, "huge")
+
+
+def test_other_configs(H, gpu, small_db):
+    """Compiled-in defaults (crossfade 20 ms, pause 120 ms, ...) and switches off."""
+    F = H.front
+    texts = H.corpus.batch(10, seed=44, target_chars=100)
+    orc = H.Oracle(small_db)
+    g = gpu.GpuSynth(small_db, 0)
+    for variant in range(4):
+        cfg = F.load_config(None)
+        if variant == 1:
+            cfg.remove_dc_offset = 0
+        if variant == 2:
+            cfg.remove_word_silence = 0
+            cfg.crossfade_ms = 0.0
+        if variant == 3:
+            cfg.crossfade_ms = 150.0
+            cfg.crossfade_vowel_ms = 200.0
+            cfg.word_pause_ms = 0.0
+            cfg.fade_in_ms = 0.0
+            cfg.fade_out_ms = 10.0
+            cfg.min_silence_ms = 5.0
+            cfg.silence_threshold = 0.2
+            cfg.max_pitch_change = 0.3
+        fr = F.Front(small_db, cfg, H.NORM_CSV)
+        prm = fr.params()
+        plan = fr.plan(texts, [1.0] * 9 + [1.4])
+        _check_plan(H, g, orc, prm, plan, f"config variant {variant}")
+
+
+def test_caller_offsets_and_errors(H, gpu, synth_small, oracle_small, front_small):
+    prm = front_small.params()
+    plan = front_small.plan(H.corpus.batch(3, seed=45, target_chars=60), [1.0, 1.5, 1.0])
+    b = synth_small.bounds(plan).astype(np.int64)
+    # generous, unevenly padded slots
+    off = np.zeros(4, np.uint64)
+    off[1] = ((b[0] + 7) // 8) * 8 + 64
+    off[2] = off[1] + ((b[1] + 7) // 8) * 8 + 8
+    off[3] = off[2] + ((b[2] + 7) // 8) * 8 + 800
+    pcm = np.full(int(off[3]), 12345, np.int16)
+    _, _, cnt = synth_small.synth_batch(plan, prm, pcm, off)
+    for u in range(3):
+        want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(plan.speed[u]))
+        _assert_same(pcm[int(off[u]):int(off[u]) + int(cnt[u])], want, f"offsets utt {u}")
+        assert cnt[u] <= b[u]
+    # a slot smaller than its bound is refused, not overrun
+    bad = off.copy()
+    bad[1] = 8
+    with pytest.raises(gpu.GpuError) as e:
+        synth_small.synth_batch(plan, prm, pcm, bad)
+    assert str(gpu.ERR_BOUNDS) in str(e.value)
+    mis = off.copy()
+    mis[1] += 3
+    with pytest.raises(gpu.GpuError):
+        synth_small.synth_batch(plan, prm, pcm, mis)
+    # an op naming a unit that does not exist is an invalid plan
+    broken = front_small.plan(["a"])
+    broken.ops["a"][broken.ops["kind"] == H.front.OP_UNIT] = 10 ** 6
+    with pytest.raises(gpu.GpuError):
+        synth_small.synth_batch(broken, prm)
+
+
+def test_resident_plan_is_idempotent(H, synth_small, oracle_small, front_small):
+    prm = front_small.params()
+    plan = front_small.plan(H.corpus.batch(12, seed=46, target_chars=80), [1.0] * 8 + [0.8, 1.2, 1.6, 2.0])
+    rp = synth_small.create_plan(plan, prm)
+    rp.run()
+    a = rp.utterances()
+    rp.run()
+    rp.run()
+    b = rp.utterances()
+    for u in range(plan.n_utts):
+        assert np.array_equal(a[u], b[u])
+        want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(plan.speed[u]))
+        _assert_same(b[u], want, f"resident utt {u}")
+    info = rp.info()
+    assert info.kernel_launches == 3 and info.n_stretch == 4 and info.threads == 512
+    # pre-stretch buffer of a stretched utterance equals the oracle's
+    _, _, pre = oracle_small.synth(prm, plan.utt_ops(9), 1.2, want_pre=True)
+    _assert_same(rp.read_pre(9, len(pre) + 16), pre, "pre-stretch")
+
+
+def test_full_voice_sample_against_oracle(H, gpu):
+    """The bench voice (1787 units) and corpus: 48 utterances bit-exact, both speeds."""
+    db = H.synthetic_db()
+    fr = H.front.Front(db, H.shipped_config(), H.NORM_CSV)
+    prm = fr.params()
+    orc = H.Oracle(db)
+    g = gpu.GpuSynth(db, 0)
+    texts = H.corpus.batch(48, seed=1234)
+    plan = fr.plan(texts, [1.0] * 40 + list(H.corpus.mixed_speeds(8, seed=3)))
+    _check_plan(H, g, orc, prm, plan, "full voice")
+
+
+def test_full_batch_properties(H, gpu):
+    """BASELINE configs[2] at full size (4096 utterances): properties that do not need the oracle on
+    every utterance -- counts within bounds, idempotence, independence of batch composition (an
+    utterance synthesised alone equals the same utterance inside the batch), and a sampled oracle check."""
+    db = H.synthetic_db()
+    fr = H.front.Front(db, H.shipped_config(), H.NORM_CSV)
+    prm = fr.params()
+    g = gpu.GpuSynth(db, 0)
+    texts = H.corpus.batch(4096, seed=1234)
+    plan = fr.plan(texts)
+    rp = g.create_plan(plan, prm)
+    rp.run()
+    cnt = rp.counts().astype(np.int64)
+    off = rp.out_offsets().astype(np.int64)
+    bounds = g.bounds(plan).astype(np.int64)
+    assert (cnt <= bounds).all() and (cnt > 0).all()
+    pcm1 = rp.read_pcm(0, rp.out_samples)
+    digest1 = [hashlib.sha1(pcm1[off[u]:off[u] + cnt[u]].tobytes()).digest() for u in range(0, 4096, 64)]
+    rp.run()
+    cnt2 = rp.counts().astype(np.int64)
+    assert np.array_equal(cnt, cnt2)
+    pcm2 = rp.read_pcm(0, rp.out_samples)
+    digest2 = [hashlib.sha1(pcm2[off[u]:off[u] + cnt[u]].tobytes()).digest() for u in range(0, 4096, 64)]
+    assert digest1 == digest2
+    orc = H.Oracle(db)
+    rng = np.random.default_rng(1)
+    pick = sorted(rng.choice(4096, 24, replace=False).tolist())
+    solo = g.synth_list(plan.select(pick), prm)
+    for k, u in enumerate(pick):
+        inside = pcm1[off[u]:off[u] + cnt[u]]
+        _assert_same(solo[k], inside, f"utt {u} alone vs in batch")
+        want, _ = orc.synth(prm, plan.utt_ops(u), 1.0)
+        _assert_same(inside, want, f"utt {u} vs oracle")

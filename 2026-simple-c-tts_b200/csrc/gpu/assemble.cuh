@@ -97,7 +97,7 @@ struct Smem {
     int16_t* ustage;
     uint32_t* scratch;
     float* hann256;
-    int16_t* carry;              // 256 samples
+    float* nrm2;                 // hann256[i+128] + hann256[i], 128 entries
     unsigned long long* red;     // 2 * ASM_THREADS/32 entries
 };
 
@@ -174,73 +174,135 @@ __device__ void region_switch(State& s, const Smem& sm, const AsmArgs& A, uint32
 
 // ---------------------------------------------------------------- pitch
 
-// estimate_pitch (ctts.c:1899) for two signals of the same length at once:
-// threads 0..255 take the lags of `a` (buffer tail), 256..511 those of `b`
-// (unit head).  Each lag is one thread's sequential float loop, exactly the
-// reference's accumulation order; the argmax keeps the smallest lag on ties
-// (the reference scans lags upward with a strict >).
+// estimate_pitch (ctts.c:1899) for two signals of the same length at once (the
+// buffer tail `a` and the unit head `b`).
+//
+// The reference evaluates, for each lag in 55..275, three sequential float sums
+// over i < 220: corr += s[i]*s[i+lag], e1 += s[i]^2, e2 += s[i+lag]^2.  The sums
+// must keep that order, so the parallel axis is the lag.  Each of 2 x 64 threads
+// owns FOUR consecutive lags and walks i in steps of 4 with one 16-byte load of
+// x = s[i..i+3] (broadcast) and one of the 4 new y = s[i+lag0+3 .. i+lag0+6]; the
+// 7-value sliding window of y (and of y*y, computed once per value) feeds the 16
+// (lag, i) pairs of the step: 3.4 instructions per pair instead of 8.5 for the
+// one-lag-per-thread loop.  e1 does not depend on the lag: one thread per signal
+// computes it concurrently.  The argmax keeps the smallest lag on ties (the
+// reference scans lags upward with a strict >).
+constexpr int PITCH_Y_WORDS = 576;  // y staging per signal (index + 2 keeps the 16-byte loads aligned)
+constexpr int PITCH_X_WORDS = 224;
+constexpr int PITCH_SCRATCH_WORDS = 2 * PITCH_Y_WORDS + 2 * PITCH_X_WORDS + 8;
+
 __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int16_t* b, uint32_t n,
                                     float* pa, float* pb) {
-    static_assert(ASM_THREADS == 512, "lag mapping assumes 2 x 256 threads");
+    static_assert(ASM_THREADS >= 192, "needs 128 lag threads + 2 energy threads");
+    static_assert((CTTS_PLAN_SAMPLE_RATE / 400) % 4 == 3, "y staging offset assumes min lag = 3 (mod 4)");
     *pa = 0.0f;
     *pb = 0.0f;
     if (n < 200) return;
     const int tid = threadIdx.x;
-    uint32_t lo = CTTS_PLAN_SAMPLE_RATE / 400, hi = CTTS_PLAN_SAMPLE_RATE / 80;
+    const uint32_t lo = CTTS_PLAN_SAMPLE_RATE / 400;
+    uint32_t hi = CTTS_PLAN_SAMPLE_RATE / 80;
     if (hi > n / 2) hi = n / 2;
     uint32_t len = CTTS_PLAN_SAMPLE_RATE / 100;
     if (len > n - hi) len = n - hi;
-    float* fa = reinterpret_cast<float*>(sm.scratch);
-    float* fb = fa + 512;
-    uint32_t need = len + hi;  // <= 495
-    for (uint32_t i = tid; i < need; i += ASM_THREADS) {
-        fa[i] = (float)a[i];
-        fb[i] = (float)b[i];
+    float* ya = reinterpret_cast<float*>(sm.scratch);
+    float* yb = ya + PITCH_Y_WORDS;
+    float* xa = yb + PITCH_Y_WORDS;
+    float* xb = xa + PITCH_X_WORDS;
+    float* e1s = xb + PITCH_X_WORDS;  // [2]
+    const uint32_t need = len + hi;   // <= 495
+    for (uint32_t i = tid; i < PITCH_Y_WORDS; i += ASM_THREADS) {
+        bool in = i >= 2 && i - 2 < need;
+        ya[i] = in ? (float)a[i - 2] : 0.0f;
+        yb[i] = in ? (float)b[i - 2] : 0.0f;
+    }
+    for (uint32_t i = tid; i < PITCH_X_WORDS; i += ASM_THREADS) {
+        bool in = i < len;
+        xa[i] = in ? (float)a[i] : 0.0f;
+        xb[i] = in ? (float)b[i] : 0.0f;
     }
     __syncthreads();
-    const int half = tid >> 8;
-    const uint32_t lag = lo + (uint32_t)(tid & 255);
-    const float* f = half ? fb : fa;
-    unsigned long long key = 0ull;
-    if (lag <= hi) {
-        float c = 0.0f, e1 = 0.0f, e2 = 0.0f;
-        const float* g = f + lag;
-#pragma unroll 4
-        for (uint32_t i = 0; i < len; i++) {
-            float x = f[i], y = g[i];
-            c += x * y;
-            e1 += x * x;
-            e2 += y * y;
+
+    float c[4] = {0.0f, 0.0f, 0.0f, 0.0f}, e2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const int sig = (tid >> 6) & 1;
+    const uint32_t lag0 = lo + 4u * (uint32_t)(tid & 63);
+    if (tid < 128 && lag0 <= hi) {
+        const float* x = sig ? xb : xa;
+        const float* y = (sig ? yb : ya) + 2 + lag0;  // y[j] = s[lag0 + j]
+        float w0 = y[0], w1 = y[1], w2 = y[2];
+        float q0 = w0 * w0, q1 = w1 * w1, q2 = w2 * w2;
+        const uint32_t len4 = len & ~3u;
+        for (uint32_t i = 0; i < len4; i += 4) {
+            const float4 xv = *reinterpret_cast<const float4*>(x + i);
+            const float4 yn = *reinterpret_cast<const float4*>(y + i + 3);
+            const float w3 = yn.x, w4 = yn.y, w5 = yn.z, w6 = yn.w;
+            const float q3 = w3 * w3, q4 = w4 * w4, q5 = w5 * w5, q6 = w6 * w6;
+            c[0] += xv.x * w0; c[1] += xv.x * w1; c[2] += xv.x * w2; c[3] += xv.x * w3;
+            e2[0] += q0; e2[1] += q1; e2[2] += q2; e2[3] += q3;
+            c[0] += xv.y * w1; c[1] += xv.y * w2; c[2] += xv.y * w3; c[3] += xv.y * w4;
+            e2[0] += q1; e2[1] += q2; e2[2] += q3; e2[3] += q4;
+            c[0] += xv.z * w2; c[1] += xv.z * w3; c[2] += xv.z * w4; c[3] += xv.z * w5;
+            e2[0] += q2; e2[1] += q3; e2[2] += q4; e2[3] += q5;
+            c[0] += xv.w * w3; c[1] += xv.w * w4; c[2] += xv.w * w5; c[3] += xv.w * w6;
+            e2[0] += q3; e2[1] += q4; e2[2] += q5; e2[3] += q6;
+            w0 = w4; w1 = w5; w2 = w6;
+            q0 = q4; q1 = q5; q2 = q6;
         }
-        float nrm = sqrtf(e1 * e2);
-        if (nrm > 0) c /= nrm;
-        if (c > 0.0f) key = ((unsigned long long)__float_as_uint(c) << 32) | (0xffffffffu - lag);
-    }
-    // max per half
+        for (uint32_t i = len4; i < len; i++) {
+            const float xs = x[i];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-        key = other > key ? other : key;
+            for (int k = 0; k < 4; k++) {
+                const float ys = y[i + k];
+                c[k] += xs * ys;
+                e2[k] += ys * ys;
+            }
+        }
+    } else if (tid == 128 || tid == 160) {
+        const float* x = tid == 160 ? xb : xa;
+        float e1 = 0.0f;
+        for (uint32_t i = 0; i < len; i++) e1 += x[i] * x[i];
+        e1s[tid == 160 ? 1 : 0] = e1;
     }
-    if (lane_id() == 0) sm.red[warp_id()] = key;
     __syncthreads();
-    unsigned long long ka = 0ull, kb = 0ull;
+    unsigned long long key = 0ull;
+    if (tid < 128 && lag0 <= hi) {
+        const float e1 = e1s[sig];
+        float best = 0.0f;
+        uint32_t best_lag = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        unsigned long long x = sm.red[k], y = sm.red[8 + k];
-        ka = x > ka ? x : ka;
-        kb = y > kb ? y : kb;
+        for (int k = 0; k < 4; k++) {
+            if (lag0 + k > hi) break;
+            float v = c[k];
+            float nrm = sqrtf(e1 * e2[k]);
+            if (nrm > 0) v /= nrm;
+            if (v > best) {
+                best = v;
+                best_lag = lag0 + k;
+            }
+        }
+        if (best_lag) key = ((unsigned long long)__float_as_uint(best) << 32) | (0xffffffffu - best_lag);
     }
+    // max per signal: warps 0-1 hold signal a, warps 2-3 signal b
+    if (tid < 128) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+        }
+        if (lane_id() == 0) sm.red[warp_id()] = key;
+    }
+    __syncthreads();
+    const unsigned long long ka = sm.red[0] > sm.red[1] ? sm.red[0] : sm.red[1];
+    const unsigned long long kb = sm.red[2] > sm.red[3] ? sm.red[2] : sm.red[3];
     __syncthreads();
     {
-        float c = __uint_as_float((uint32_t)(ka >> 32));
+        float v = __uint_as_float((uint32_t)(ka >> 32));
         uint32_t l = 0xffffffffu - (uint32_t)(ka & 0xffffffffu);
-        if (ka != 0ull && c > 0.3f && l > 0) *pa = (float)CTTS_PLAN_SAMPLE_RATE / (float)l;
+        if (ka != 0ull && v > 0.3f && l > 0) *pa = (float)CTTS_PLAN_SAMPLE_RATE / (float)l;
     }
     {
-        float c = __uint_as_float((uint32_t)(kb >> 32));
+        float v = __uint_as_float((uint32_t)(kb >> 32));
         uint32_t l = 0xffffffffu - (uint32_t)(kb & 0xffffffffu);
-        if (kb != 0ull && c > 0.3f && l > 0) *pb = (float)CTTS_PLAN_SAMPLE_RATE / (float)l;
+        if (kb != 0ull && v > 0.3f && l > 0) *pb = (float)CTTS_PLAN_SAMPLE_RATE / (float)l;
     }
 }
 
@@ -296,22 +358,22 @@ __device__ void match_energy(const State& s, const Smem& sm, int16_t* us, uint32
     if (len > s.count) len = s.count;
     if (len > n) len = n;
     const int16_t* tail = s.w + (s.count - len);
-    unsigned long long sp = 0, sn = 0;
+    long long sp = 0, sn = 0;
     for (uint32_t i = tid; i < len; i += ASM_THREADS) {
         int p = tail[i], q = us[i];
-        sp += (unsigned long long)(p * p);
-        sn += (unsigned long long)(q * q);
+        sp += (long long)p * p;
+        sn += (long long)q * q;
     }
-    sp = block_allreduce<ASM_THREADS>(sp, OpAddU64(), sm.red);
-    sn = block_allreduce<ASM_THREADS>(sn, OpAddU64(), sm.red);
+    block_allreduce_add2<ASM_THREADS>(sp, sn, reinterpret_cast<long long*>(sm.red));
     float pr = (float)sqrt((double)sp / (double)len);
     float nr = (float)sqrt((double)sn / (double)len);
     if (pr < 1.0f || nr < 1.0f) return;
     float ratio = pr / nr;
     if (ratio > 2.0f) ratio = 2.0f;
     if (ratio < 0.5f) ratio = 0.5f;
+    const float flen = (float)len;
     for (uint32_t i = tid; i < len; i += ASM_THREADS) {
-        float t = (float)i / (float)len;
+        float t = (float)i / flen;
         float g = ratio * (1.0f - t) + 1.0f * t;
         us[i] = f2s(clamp16f((float)us[i] * g));
     }
@@ -319,6 +381,28 @@ __device__ void match_energy(const State& s, const Smem& sm, int16_t* us, uint32
 }
 
 // ---------------------------------------------------------------- unit op
+
+// the two crossfade gains at t share the table position (fast_fade_out / fast_fade_in, ctts.c:76-92)
+__device__ __forceinline__ void crossfade_gains(const DevTables& tab, float t, float* pg, float* ng) {
+    float x = t * (float)(LUT_N - 1);
+    int k = (int)x;
+    if (k >= LUT_N - 1) {
+        *pg = __ldg(tab.fade_out + LUT_N - 1);
+        *ng = __ldg(tab.fade_in + LUT_N - 1);
+    } else if (k < 0) {
+        *pg = __ldg(tab.fade_out);
+        *ng = __ldg(tab.fade_in);
+    } else {
+        float fr = x - (float)k, om = 1.0f - fr;
+        *pg = __ldg(tab.fade_out + k) * om + __ldg(tab.fade_out + k + 1) * fr;
+        *ng = __ldg(tab.fade_in + k) * om + __ldg(tab.fade_in + k + 1) * fr;
+    }
+}
+
+__device__ __forceinline__ int sub_dc(int v, int dc) {
+    // clamp(v - dc) to int16 (remove_dc_offset, ctts.c:1577-1581)
+    return max(__viaddmin_s32(v, -dc, 32767), -32768);
+}
 
 // ctts.c:3785-3846: gather -> normalize_rms -> [smooth, match] -> buffer_append_crossfade
 __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_plan_op& op) {
@@ -331,9 +415,13 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
     int16_t* us = sm.ustage;
     const uint32_t xf = op.b;
     const bool boundary = (op.flags & CTTS_UNIT_AFTER_BOUNDARY) != 0;
+    const bool join = !boundary && s.count > 0;
+    const bool remove_dc = A.prm.remove_dc_offset != 0;
+    // samples [0, head) may still be rewritten by smooth_pitch / match_energy
+    const uint32_t head = join ? (xf < n ? xf : n) : 0u;
 
     // gather with 16-byte loads (pool is zero-padded to 8 samples per unit) + sum of squares
-    unsigned long long ss = 0;
+    long long ss = 0;
     const uint32_t nvec = (n + 7) >> 3;
     for (uint32_t v = tid; v < nvec; v += ASM_THREADS) {
         int4 q = __ldg(reinterpret_cast<const int4*>(src) + v);
@@ -342,39 +430,50 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             int x = e[k];
-            ss += (unsigned long long)(x * x);
+            ss += (long long)x * x;
         }
     }
-    ss = block_allreduce<ASM_THREADS>(ss, OpAddU64(), sm.red);
-    // normalize_rms, ctts.c:1709 (double sum of squares == integer sum, exactly)
+    ss = block_allreduce<ASM_THREADS>(ss, OpAddI64(), reinterpret_cast<long long*>(sm.red));
+    // normalize_rms, ctts.c:1709 (double sum of squares == integer sum, exactly); the DC sum of
+    // everything past `head` is taken on the way (integer, order-free)
+    int dsum = 0;
+    bool scale = false;
+    float g = 1.0f;
     if (A.prm.target_rms > 0) {
         float rms = (float)sqrt((double)ss / (double)n);
         if (!(rms < 1.0f)) {
-            float g = A.prm.target_rms / rms;
+            g = A.prm.target_rms / rms;
             if (g > 3.0f) g = 3.0f;
             if (g < 0.1f) g = 0.1f;
-            for (uint32_t v = tid; v < nvec; v += ASM_THREADS) {
-                int4 q = *(reinterpret_cast<int4*>(us) + v);
-                int16_t* e = reinterpret_cast<int16_t*>(&q);
-#pragma unroll
-                for (int k = 0; k < 8; k++) e[k] = f2s(clamp16f((float)e[k] * g));
-                *(reinterpret_cast<int4*>(us) + v) = q;
-            }
+            scale = true;
         }
+    }
+    for (uint32_t v = tid; v < nvec; v += ASM_THREADS) {
+        int4 q = *(reinterpret_cast<int4*>(us) + v);
+        int16_t* e = reinterpret_cast<int16_t*>(&q);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int y = e[k];
+            if (scale) {
+                y = (int)f2s(clamp16f((float)y * g));
+                e[k] = (int16_t)y;
+            }
+            if (v * 8 + k >= head) dsum += y;   // padding past n is zero
+        }
+        if (scale) *(reinterpret_cast<int4*>(us) + v) = q;
     }
     __syncthreads();
 
-    if (!boundary && s.count > 0) {
+    if (join) {
         smooth_pitch(s, sm, us, n, xf);
         match_energy(s, sm, us, n, xf);
     }
 
     // buffer_append_crossfade, ctts.c:3279
     int dc = 0;
-    if (A.prm.remove_dc_offset) {
-        long long sum = 0;
-        for (uint32_t i = tid; i < n; i += ASM_THREADS) sum += us[i];
-        sum = block_allreduce<ASM_THREADS>(sum, OpAddI64(), reinterpret_cast<long long*>(sm.red));
+    if (remove_dc) {
+        for (uint32_t i = tid; i < head; i += ASM_THREADS) dsum += us[i];
+        long long sum = block_allreduce<ASM_THREADS>((long long)dsum, OpAddI64(), reinterpret_cast<long long*>(sm.red));
         dc = (int)(int16_t)(sum / (long long)n);
     }
     const bool fresh = (s.count == 0) || boundary;
@@ -385,35 +484,63 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
         if (a > n) a = n;
     }
     if ((unsigned long long)s.count - s.base + (n - a) > s.cap) { s.err = ERR_WINDOW_OVERFLOW; return; }
-    int16_t* tail = s.w + (s.count - a);
-    uint32_t fin = 0;
-    float inv = 0.0f;
+    int16_t* tail = s.w + (s.count - a);   // unit sample i lands at tail[i]
+
+    // prefix that is not a plain copy: the fade-in (ctts.c:3015) or the crossfade mix (ctts.c:3328-3344)
+    uint32_t pre = 0;
     if (fresh) {
-        fin = A.prm.fade_in_samples < n ? A.prm.fade_in_samples : n;
-        if (fin) inv = 1.0f / (float)fin;
-    } else if (a) {
-        inv = 1.0f / (float)a;
-    }
-    for (uint32_t i = tid; i < n; i += ASM_THREADS) {
-        int v = us[i];
-        if (A.prm.remove_dc_offset) {
-            v -= dc;
-            if (v > 32767) v = 32767;
-            if (v < -32768) v = -32768;
+        pre = A.prm.fade_in_samples < n ? A.prm.fade_in_samples : n;
+        if (pre) {
+            const float inv = 1.0f / (float)pre;
+            for (uint32_t i = tid; i < pre; i += ASM_THREADS) {
+                int v = us[i];
+                if (remove_dc) v = sub_dc(v, dc);
+                tail[i] = f2s((float)v * lut_lerp(A.tab.sine, (float)i * inv));
+            }
         }
-        if (fresh) {
-            if (i < fin) v = f2s((float)v * lut_lerp(A.tab.sine, (float)i * inv));
-        } else if (i < a) {
-            float t = (float)i * inv;
-            float pg = lut_lerp(A.tab.fade_out, t);
-            float ng = lut_lerp(A.tab.fade_in, t);
+    } else if (a) {
+        pre = a;
+        const float inv = 1.0f / (float)a;
+        for (uint32_t i = tid; i < a; i += ASM_THREADS) {
+            int v = us[i];
+            if (remove_dc) v = sub_dc(v, dc);
+            float pg, ng;
+            crossfade_gains(A.tab, (float)i * inv, &pg, &ng);
             int p = tail[i];
             int mix = (int)((float)p * pg + (float)v * ng);
-            if (mix > 32767) mix = 32767;
-            else if (mix < -32768) mix = -32768;
-            v = mix;
+            tail[i] = (int16_t)max(min(mix, 32767), -32768);
         }
-        tail[i] = (int16_t)v;
+    }
+    // the rest: DC removal + copy, 8 samples per thread from the aligned staging buffer
+    {
+        const uint32_t v0 = pre >> 3;
+        for (uint32_t v = v0 + tid; v < nvec; v += ASM_THREADS) {
+            int4 q = *(reinterpret_cast<const int4*>(us) + v);
+            const int16_t* e = reinterpret_cast<const int16_t*>(&q);
+            const uint32_t i0 = v << 3;
+            int y[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) y[k] = remove_dc ? sub_dc((int)e[k], dc) : (int)e[k];
+            if (i0 >= pre && i0 + 8 <= n) {
+                int16_t* d = tail + i0;
+                if ((reinterpret_cast<uintptr_t>(d) & 3) == 0) {
+                    uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) d32[k] = (uint32_t)(y[2 * k] & 0xffff) | ((uint32_t)y[2 * k + 1] << 16);
+                } else {
+                    d[0] = (int16_t)y[0];
+                    uint32_t* d32 = reinterpret_cast<uint32_t*>(d + 1);
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+                        d32[k] = (uint32_t)(y[2 * k + 1] & 0xffff) | ((uint32_t)y[2 * k + 2] << 16);
+                    d[7] = (int16_t)y[7];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (i0 + k >= pre && i0 + k < n) tail[i0 + k] = (int16_t)y[k];
+            }
+        }
     }
     s.count += n - a;
     __syncthreads();
@@ -557,72 +684,136 @@ __device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t utt, 
 // apply_smooth_pitch_contour, ctts.c:2206, in gather form: every output sample
 // collects the (at most two) 256-sample frames that cover it, in frame order;
 // the int16 overlap-add wraps exactly as the reference's `+=` does.  In place,
-// tile by tile, with the 256 originals behind the tile carried in shared memory.
-// Reads the reference performs past the end of its heap copy (undefined
-// behaviour there, DESIGN.md "Reference UB") yield 0 here.
-__device__ void pitch_contour(const Smem& sm, int16_t* x, uint32_t n, float f0, float f1) {
-    if (n < 100 || fabsf(f0 - f1) < 0.01f) return;
-    if (n < PITCH_FRAME) return;  // no frame fits: every sample keeps its original value
+// tile by tile: the originals a tile needs ([t0-256, t1+288)) are staged in
+// shared scratch (zero past the end of the segment: reads the reference performs
+// past the end of its heap copy -- undefined behaviour there, DESIGN.md
+// "Reference UB" -- yield 0 here), per-frame pitch factors come from a table, and
+// the norm of an interior sample is the precomputed hann[i+128] + hann[i].
+// When `energy` is set the linear energy ramp of apply_phrase_intonation
+// (ctts.c:2857-2864) over the whole word (index ebase + j, denominator eden) is
+// applied to each sample as it is written.  Returns false if nothing was done.
+constexpr uint32_t CONTOUR_TILE = ASM_THREADS * CONTOUR_KPT;
+constexpr uint32_t CONTOUR_STAGE = CONTOUR_TILE + 576;       // samples (256 behind, 288 ahead, 8 phase, pad)
+constexpr uint32_t CONTOUR_PF_MAX = 1024;                    // frames with a tabulated pitch factor
+constexpr uint32_t CONTOUR_SCRATCH_WORDS = CONTOUR_STAGE / 2 + CONTOUR_PF_MAX;
+
+__device__ bool pitch_contour(const Smem& sm, int16_t* x, uint32_t n, float f0, float f1, bool energy,
+                              float e0, float de, float eden, uint32_t ebase) {
+    if (n < 100 || fabsf(f0 - f1) < 0.01f) return false;
+    if (n < PITCH_FRAME) return false;  // no frame fits: every sample keeps its original value
     const int tid = threadIdx.x;
     const uint32_t frames = (n - PITCH_FRAME) / (PITCH_FRAME / 2) + 1;
     const bool degenerate = (n == PITCH_FRAME);  // 1/(n-256) = inf in the reference: NaN indices
     const float inv = 1.0f / (float)(n - PITCH_FRAME);
     const float* hann = sm.hann256;
-    int16_t* carry = sm.carry;
-    constexpr uint32_t TILE = ASM_THREADS * CONTOUR_KPT;
-    for (uint32_t t0 = 0; t0 < n; t0 += TILE) {
-        const uint32_t t1 = min(t0 + TILE, n);
-        int16_t outv[CONTOUR_KPT];
+    const float* nrm2 = sm.nrm2;
+    int16_t* stage = reinterpret_cast<int16_t*>(sm.scratch);
+    float* pft = reinterpret_cast<float*>(sm.scratch + CONTOUR_STAGE / 2);
+    const bool tabulated = frames <= CONTOUR_PF_MAX;
+    if (tabulated) {
+        for (uint32_t k = tid; k < frames; k += ASM_THREADS) {
+            float t = (float)(k << 7) * inv;
+            float st = t * t * (3.0f - 2.0f * t);
+            pft[k] = f0 + (f1 - f0) * st;
+        }
+    }
+    // stage[phase + 256 + u] = x[t0 + u]: same 16-byte phase on both sides
+    const uint32_t phase = (uint32_t)((reinterpret_cast<uintptr_t>(x) >> 1) & 7u);
+    int16_t* sbase = stage + phase + PITCH_FRAME;   // index u relative to the tile start
+    for (uint32_t t0 = 0; t0 < n; t0 += CONTOUR_TILE) {
+        const uint32_t t1 = min(t0 + CONTOUR_TILE, n);
+        // ---- staging: carry the 544 samples that overlap the previous tile, load the new ones
+        if (t0 != 0) {
+            for (uint32_t v = tid; v < 560 / 8 + 1; v += ASM_THREADS) {
+                int4* d = reinterpret_cast<int4*>(stage) + v;
+                *d = *(reinterpret_cast<const int4*>(stage + CONTOUR_TILE) + v);
+            }
+        }
+        __syncthreads();
+        {
+            // u range to load: [u_lo, u_hi) as whole 16-byte vectors of the staging buffer
+            const int u_lo = t0 == 0 ? -(int)phase : (int)(288 + 8 - phase) & ~7;  // first vector not carried
+            const int first_vec = (int)(phase + PITCH_FRAME + u_lo) >> 3;
+            const int last_vec = (int)(CONTOUR_STAGE >> 3);
+            for (int v = first_vec + tid; v < last_vec; v += ASM_THREADS) {
+                const int u0 = (v << 3) - (int)(phase + PITCH_FRAME);   // u of the vector's first sample
+                const long long g0 = (long long)t0 + u0;                // segment index
+                int4 q = make_int4(0, 0, 0, 0);
+                if (g0 >= 0 && g0 + 8 <= (long long)n) {
+                    q = *reinterpret_cast<const int4*>(x + g0);
+                } else {
+                    int16_t* e = reinterpret_cast<int16_t*>(&q);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        long long g = g0 + k;
+                        if (g >= 0 && g < (long long)n) e[k] = x[g];
+                    }
+                }
+                *(reinterpret_cast<int4*>(stage) + v) = q;
+            }
+        }
+        __syncthreads();
+        // ---- outputs of this tile
 #pragma unroll
         for (int r = 0; r < CONTOUR_KPT; r++) {
-            uint32_t j = t0 + (uint32_t)tid + (uint32_t)r * ASM_THREADS;
-            outv[r] = 0;
+            const uint32_t j = t0 + (uint32_t)tid + (uint32_t)r * ASM_THREADS;
             if (j >= t1) continue;
+            const uint32_t k1 = j >> 7;
+            const uint32_t i1 = j & 127u;
+            const bool v1 = k1 < frames;
+            const bool v0 = k1 >= 1 && k1 - 1 < frames;
             int16_t acc = 0;
             float norm = 0.0f;
-            int k1 = (int)(j >> 7);
-#pragma unroll
-            for (int kk = k1 - 1; kk <= k1; kk++) {
-                if (kk < 0 || (uint32_t)kk >= frames) continue;
-                uint32_t pos = (uint32_t)kk << 7;
-                uint32_t i = j - pos;
-                float wv = hann[i];
+            if (v0) {
+                const uint32_t kk = k1 - 1, i = i1 + 128u;
                 float v = 0.0f;
                 if (!degenerate) {
-                    float t = (float)pos * inv;
-                    float st = t * t * (3.0f - 2.0f * t);
-                    float pf = f0 + (f1 - f0) * st;
+                    float pf;
+                    if (tabulated) pf = pft[kk];
+                    else {
+                        float t = (float)(kk << 7) * inv;
+                        pf = f0 + (f1 - f0) * (t * t * (3.0f - 2.0f * t));
+                    }
                     float xs = (float)i * pf;
                     uint32_t k = (uint32_t)(unsigned long long)xs;
                     float fr = xs - (float)k;
-                    uint32_t q = pos + k;
-                    if (k + 1 < PITCH_FRAME) {
-                        int16_t s0 = (q < t0) ? carry[q - (t0 - PITCH_FRAME)] : x[q];
-                        int16_t s1 = (q + 1 < t0) ? carry[q + 1 - (t0 - PITCH_FRAME)] : x[q + 1];
-                        v = (float)s0 * (1.0f - fr) + (float)s1 * fr;
-                    } else if (q < n) {
-                        int16_t s0 = (q < t0) ? carry[q - (t0 - PITCH_FRAME)] : x[q];
-                        v = (float)s0;
-                    }
+                    const int16_t* sp = sbase + ((int)(kk << 7) - (int)t0) + (int)k;
+                    v = (k + 1 < PITCH_FRAME) ? (float)sp[0] * (1.0f - fr) + (float)sp[1] * fr : (float)sp[0];
                 }
-                acc = (int16_t)(acc + f2s(v * wv));
-                norm += wv;
+                acc = f2s(v * hann[i]);
+                norm = hann[i];
             }
-            if (norm > 0.01f) outv[r] = f2s(clamp16f((float)acc / norm));
-            else outv[r] = x[j];
+            if (v1) {
+                const uint32_t kk = k1, i = i1;
+                float v = 0.0f;
+                if (!degenerate) {
+                    float pf;
+                    if (tabulated) pf = pft[kk];
+                    else {
+                        float t = (float)(kk << 7) * inv;
+                        pf = f0 + (f1 - f0) * (t * t * (3.0f - 2.0f * t));
+                    }
+                    float xs = (float)i * pf;
+                    uint32_t k = (uint32_t)(unsigned long long)xs;
+                    float fr = xs - (float)k;
+                    const int16_t* sp = sbase + ((int)(kk << 7) - (int)t0) + (int)k;
+                    v = (k + 1 < PITCH_FRAME) ? (float)sp[0] * (1.0f - fr) + (float)sp[1] * fr : (float)sp[0];
+                }
+                acc = (int16_t)(acc + f2s(v * hann[i]));
+                norm = v0 ? nrm2[i1] : hann[i];
+            }
+            int16_t o;
+            if (norm > 0.01f) o = f2s(clamp16f((float)acc / norm));
+            else o = sbase[(int)(j - t0)];
+            if (energy) {
+                float t = (float)(j + ebase) / eden;
+                o = f2s(clamp16f((float)o * (e0 + de * t)));
+            }
+            x[j] = o;
         }
-        // originals the next tile still needs: [t1-256, t1)
-        int16_t save = 0;
-        if (tid < PITCH_FRAME && t1 >= PITCH_FRAME) save = x[t1 - PITCH_FRAME + tid];
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < CONTOUR_KPT; r++) {
-            uint32_t j = t0 + (uint32_t)tid + (uint32_t)r * ASM_THREADS;
-            if (j < t1) x[j] = outv[r];
-        }
-        if (tid < PITCH_FRAME) carry[tid] = save;
         __syncthreads();
     }
+    return true;
 }
 
 // ctts.c:3693-3713 / :3878-3898: trim then phrase intonation on [word_start, count)
@@ -638,20 +829,28 @@ __device__ void op_word_end(State& s, const Smem& sm, const AsmArgs& A, uint32_t
     int16_t* x = s.w + s.word_start;
     // device half of apply_phrase_intonation, ctts.c:2740, :2774-2790, :2839-2865
     if (!(op.flags & CTTS_WE_INTON) || n < 100) return;
+    const bool energy = (op.flags & CTTS_WE_ENERGY) != 0;
+    const float e0 = op.e0, de = op.e1 - op.e0;
+    const float den = (float)(n - 1);
     bool done = false;
+    // [lo, hi): samples whose energy ramp is still to be applied after the contour
+    uint32_t lo = 0, hi = n;
     if (op.flags & CTTS_WE_CIRCUMFLEX) {
         uint32_t rise = (uint32_t)(unsigned long long)((float)n * 0.6f);
         if (rise > 100 && n - rise > 100) {
-            pitch_contour(sm, x, rise, op.f0, op.f2);
-            pitch_contour(sm, x + rise, n - rise, op.f2, op.f1);
+            bool a = pitch_contour(sm, x, rise, op.f0, op.f2, energy, e0, de, den, 0);
+            bool b = pitch_contour(sm, x + rise, n - rise, op.f2, op.f1, energy, e0, de, den, rise);
+            if (a) lo = rise;
+            if (b) hi = rise;
+            if (a && b) hi = lo = 0;
+            if (!a && b) { lo = 0; hi = rise; }
+            if (a && !b) { lo = rise; hi = n; }
             done = true;
         }
     }
-    if (!done) pitch_contour(sm, x, n, op.f0, op.f1);
-    if (op.flags & CTTS_WE_ENERGY) {
-        const float e0 = op.e0, de = op.e1 - op.e0;
-        const float den = (float)(n - 1);
-        for (uint32_t i = tid; i < n; i += ASM_THREADS) {
+    if (!done && pitch_contour(sm, x, n, op.f0, op.f1, energy, e0, de, den, 0)) lo = hi = 0;
+    if (energy && hi > lo) {
+        for (uint32_t i = lo + tid; i < hi; i += ASM_THREADS) {
             float t = (float)i / den;
             float e = e0 + de * t;
             x[i] = f2s(clamp16f((float)x[i] * e));
@@ -669,11 +868,14 @@ __global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const AsmArgs 
     sm.ustage = sm.win + A.wcap;
     sm.scratch = reinterpret_cast<uint32_t*>(sm.ustage + A.ucap);
     sm.hann256 = reinterpret_cast<float*>(sm.scratch + A.scr_words);
-    sm.carry = reinterpret_cast<int16_t*>(sm.hann256 + PITCH_FRAME);
-    sm.red = reinterpret_cast<unsigned long long*>(sm.carry + PITCH_FRAME);
+    sm.nrm2 = sm.hann256 + PITCH_FRAME;
+    sm.red = reinterpret_cast<unsigned long long*>(sm.nrm2 + PITCH_FRAME / 2);
 
     const int tid = threadIdx.x;
     for (int i = tid; i < PITCH_FRAME; i += ASM_THREADS) sm.hann256[i] = __ldg(A.tab.hann256 + i);
+    // norm of a sample covered by two frames: (0 + w[i+128]) + w[i], the reference's accumulation order
+    for (int i = tid; i < PITCH_FRAME / 2; i += ASM_THREADS)
+        sm.nrm2[i] = __ldg(A.tab.hann256 + i + PITCH_FRAME / 2) + __ldg(A.tab.hann256 + i);
 
     const UttTask task = A.tasks[blockIdx.x];
     State s;

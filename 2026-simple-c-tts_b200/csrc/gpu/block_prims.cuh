@@ -50,6 +50,31 @@ __device__ __forceinline__ V block_allreduce(V v, Op op, V* red) {
     return r;
 }
 
+// Sum of two 64-bit integers per thread in one pass (one barrier pair instead of two).
+// `red` needs 2 * NT/32 entries.
+template <int NT>
+__device__ __forceinline__ void block_allreduce_add2(long long& a, long long& b, long long* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane_id() == 0) {
+        red[warp_id()] = a;
+        red[NT / 32 + warp_id()] = b;
+    }
+    __syncthreads();
+    long long ra = 0, rb = 0;
+#pragma unroll
+    for (int k = 0; k < NT / 32; k++) {
+        ra += red[k];
+        rb += red[NT / 32 + k];
+    }
+    __syncthreads();
+    a = ra;
+    b = rb;
+}
+
 // Exclusive scan of one value per thread in thread order (reverse = suffix scan).
 // Op must be commutative and associative.  Optionally returns the CTA total.
 template <int NT, typename V, typename Op>

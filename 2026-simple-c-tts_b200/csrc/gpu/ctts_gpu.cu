@@ -380,7 +380,8 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
     const uint32_t ucap = (uint32_t)up8(std::max<uint32_t>(max_unit, 8));
     const uint32_t fixed = ucap * 2 + 256 * 4 + 256 * 2 + 2 * (ctts::ASM_THREADS / 32) * 8 + 64;
     auto scr_for = [&](uint32_t wcap) {
-        uint32_t a = 1024, b = ucap / 8 + 8, c = 2 * ((wcap + 31) / 32) + 4;
+        uint32_t a = std::max<uint32_t>(ctts::PITCH_SCRATCH_WORDS, ctts::CONTOUR_SCRATCH_WORDS + 8), b = ucap / 8 + 8,
+                 c = 2 * ((wcap + 31) / 32) + 4;
         return std::max(a, std::max(b, c));
     };
     // budget: two CTAs per SM (1 KB per CTA is reserved by the runtime)

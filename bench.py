@@ -89,19 +89,42 @@ def ncu_traffic(kernel: str):
 
 
 class ClockSampler:
+    """nvidia-smi sampled every 50 ms in the background; mark() brackets the timed region."""
+
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.out = open(self.path, "w")
         self.proc = None
+        self.lo = self.hi = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=self.tmp, stderr=subprocess.DEVNULL)
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=self.out, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def _lines(self) -> int:
+        try:
+            with open(self.path) as f:
+                return sum(1 for _ in f)
+        except OSError:
+            return 0
+
+    def wait_ready(self, timeout: float = 8.0) -> None:
+        t0 = time.time()
+        while self.proc is not None and self._lines() < 2 and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark_begin(self) -> None:
+        self.lo = self._lines()
+
+    def mark_end(self) -> None:
+        time.sleep(0.06)  # let the sample that covers the end of the region land
+        self.hi = self._lines()
 
     def stop(self) -> dict:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -112,14 +135,23 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        self.tmp.flush()
-        self.tmp.seek(0)
+        self.out.close()
+        rows = []
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) >= 7:
+                    rows.append(parts)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        lo = max((self.lo or 0) - 1, 0)
+        hi = min(self.hi if self.hi is not None else len(rows), len(rows))
+        sel = rows[lo:max(hi, lo + 1)] or rows[-1:]
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.tmp:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
-                continue
+        for parts in sel:
             try:
                 sm.append(float(parts[0]))
                 smax.append(float(parts[1]))
@@ -128,11 +160,6 @@ class ClockSampler:
             for name, val in zip(names, parts[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        self.tmp.close()
-        try:
-            os.unlink(self.tmp.name)
-        except OSError:
-            pass
         if sm:
             out["sm_mhz"] = float(np.median(sm))
             out["sm_max_mhz"] = float(max(smax))
@@ -241,14 +268,17 @@ def main() -> int:
             dist.barrier()
         torch.cuda.synchronize(local_rank)
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         rp.run(d_out.data_ptr())
     counts = rp.counts()
     audio_s = float(counts.astype(np.int64).sum()) / SAMPLE_RATE
     n_out = int(counts.astype(np.int64).sum())
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     sync_all()
+    if sampler:
+        sampler.wait_ready()
+        sampler.mark_begin()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with torch.cuda.stream(stream):
         evs[0].record(stream)
@@ -256,6 +286,8 @@ def main() -> int:
             rp.run(d_out.data_ptr())
             evs[k + 1].record(stream)
     sync_all()
+    if sampler:
+        sampler.mark_end()
     clocks = sampler.stop() if sampler else None
     step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     total_ms = evs[0].elapsed_time(evs[args.steps])

@@ -1,18 +1,29 @@
-// assemble.cuh -- the audio-assembly kernel: one CTA executes one utterance's
-// plan ops in order, with CTA-wide parallelism inside every op.
+// assemble.cuh -- the audio-assembly kernel.
 //
-// The reference is a sequential program over a growing buffer in which each
-// join reads the processed tail of what came before (ctts.c:3835-3845), so
-// the parallel axes are: utterances (one CTA each), and samples / lags / words
-// of a bitmask inside an op.  The live tail of the utterance (a "window":
-// the last HALO finished samples plus the region since the last word mark)
-// is kept in shared memory; finished samples are streamed to HBM with 16-byte
-// stores when a region closes.  Regions that cannot fit use the output slot in
-// HBM as the window instead (same code: all ops address the window through an
-// absolute-index generic pointer).
+// Decomposition.  The reference is one sequential program per utterance over a
+// growing buffer (ctts.c:3689-3904).  What one word region (the samples between
+// two word marks) does depends on earlier regions only through
+//   (1) the absolute sample count at its start (the `count/2`, `count` clamps of
+//       ctts.c:1985-1987, :1736, :3319 and the `count == 0` tests), and
+//   (2) rarely, the last few thousand finished samples (an analysis / crossfade /
+//       fade window that reaches back past the word start).
+// So the parallel unit here is the REGION TASK: one CTA assembles one region (or
+// a run of tiny ones) entirely in shared memory, and only at the end -- or at
+// the first op whose decision really needs (1) or (2) -- waits for its
+// predecessor's published inclusive sample count (a decoupled look-back chain,
+// one 64-bit word per task).  The finished region is then streamed to its final
+// position in the utterance's HBM slot with 16-byte stores.  Tasks are handed
+// out through an atomic ticket in region-major order (region r of every
+// utterance before region r+1 of any), so predecessors are normally long
+// finished and the chain wait is a single L2 read; a waiting CTA only ever waits
+// on a smaller ticket, which is held by a running CTA, so the chain cannot
+// deadlock.  Regions too large for the shared window, and regions that need (2),
+// run the same code on the HBM slot itself (the window pointer is generic).
 //
-// Float arithmetic mirrors the reference expression by expression and the
-// file is compiled with -fmad=false: PCM must be bit-exact.
+// Float arithmetic mirrors the reference expression by expression and the file
+// is compiled with -fmad=false: PCM must be bit-exact.  The one place an FMA is
+// used is the pitch pre-filter (estimate_pitch_pair), whose results only select
+// which lags are then evaluated exactly.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -22,10 +33,14 @@
 
 namespace ctts {
 
-constexpr int ASM_THREADS = 512;
+constexpr int ASM_THREADS = 256;
+constexpr int ASM_WARPS = ASM_THREADS / 32;
 constexpr int PITCH_FRAME = 256;  // ctts.c:2194
 constexpr int LUT_N = 1024;       // ctts.c:52
 constexpr int CONTOUR_KPT = 4;    // outputs per thread per contour tile
+
+// private op kind: an op the host proved to be a no-op (plan compile step)
+constexpr uint16_t OP_NOP = 0;
 
 struct DevTables {
     const float* fade_out;  // 1 -> 0 raised cosine
@@ -35,24 +50,28 @@ struct DevTables {
     const float* hann512;
 };
 
-struct UttTask {
-    uint32_t utt;          // index into out_counts / pre_counts / err
+enum { TASK_LAST = 1u, TASK_TO_PRE = 2u, TASK_GLOBAL = 4u };
+
+struct RegionTask {
+    uint32_t utt;       // index into out_counts / pre_counts / err
     uint32_t op_begin;
     uint32_t op_end;
-    uint32_t first_bound;  // upper bound of samples appended before the first MARK
-    unsigned long long dst_off;  // sample offset of this utterance's slot in dst
-    uint32_t dst_cap;      // slot capacity in samples
-    uint32_t to_pre;       // 1: write the pre-stretch buffer (speed != 1), 0: final PCM
+    uint32_t bound;     // upper bound of the samples this task appends
+    int32_t pred;       // task of the same utterance that precedes this one, -1: none
+    uint32_t flags;     // TASK_*
+    uint32_t dst_cap;   // utterance slot capacity in samples
+    uint32_t big;       // slot in the global trim scratch, 0xffffffff: none
+    unsigned long long dst_off;  // sample offset of the utterance slot in dst
 };
 
 struct AsmArgs {
-    const int16_t* pool;        // re-packed PCM pool, every unit 16-byte aligned
+    const int16_t* pool;        // re-packed PCM pool, every unit 16-byte aligned, zero padded to 8
     const uint32_t* unit_off;   // samples, multiple of 8
     const uint32_t* unit_cnt;
     uint32_t n_units;
     DevTables tab;
-    const ctts_plan_op* ops;    // MARK ops carry the next region's bound in .a
-    const UttTask* tasks;
+    const ctts_plan_op* ops;
+    const RegionTask* tasks;    // in ticket order
     uint32_t n_tasks;
     int16_t* dst_final;
     int16_t* dst_pre;
@@ -60,11 +79,13 @@ struct AsmArgs {
     uint32_t* pre_counts;
     uint32_t* err;              // per utterance, 0 = ok
     uint32_t* trim_scratch;     // global fallback for the silence bitmask
-    uint32_t trim_scratch_words;  // per utterance
+    uint32_t trim_scratch_words;  // per slot
+    unsigned long long* chain;  // per task: (epoch << 32) | inclusive sample count
+    uint32_t* ticket;           // zeroed before every launch
+    uint32_t epoch;             // != 0, changes every launch
     ctts_assembly_params prm;
-    uint32_t wcap;   // window capacity (samples, multiple of 8)
-    uint32_t ucap;   // unit staging capacity (samples, multiple of 8)
-    uint32_t halo;   // finished samples kept writable behind the word mark (multiple of 8)
+    uint32_t wcap;       // window capacity (samples, multiple of 8)
+    uint32_t hcap;       // unit-head staging capacity (samples, multiple of 8)
     uint32_t scr_words;  // shared scratch, 32-bit words
 };
 
@@ -93,82 +114,111 @@ __device__ __forceinline__ float lut_lerp(const float* __restrict__ lut, float t
 __device__ __forceinline__ int abs16(int16_t v) { return (int)(int16_t)(v > 0 ? v : -v); }
 
 struct Smem {
-    int16_t* win;
-    int16_t* ustage;
-    uint32_t* scratch;
+    int16_t* win;                // wcap + 16 samples
+    int16_t* hstage;             // hcap samples: the head of the unit being joined
+    uint32_t* scratch;           // scr_words
     float* hann256;
     float* nrm2;                 // hann256[i+128] + hann256[i], 128 entries
-    unsigned long long* red;     // 2 * ASM_THREADS/32 entries
+    unsigned long long* red;     // 2 * ASM_WARPS entries
+    uint32_t* bcast;             // 4 words
 };
 
 // Per-CTA execution state (replicated in every thread; all control flow is CTA-uniform).
+// Sample indices are relative to the first sample of the task; in HBM mode w = dst + base,
+// so negative indices reach the finished samples of earlier tasks.
 struct State {
-    int16_t* w;          // window addressed by ABSOLUTE sample index: w[abs]
-    uint32_t base;       // first absolute index held by the window
-    uint32_t cap;        // window capacity
+    int16_t* w;          // the window: w[i], i in [in_smem ? 0 : -base, cap)
+    uint32_t cap;
     bool in_smem;
-    uint32_t count;      // buf.count
-    uint32_t word_start; // word_start_sample
-    int16_t* dst;        // utterance slot in HBM (dst[abs])
+    bool have_base;
+    uint32_t base;       // absolute sample count at the start of the task (valid iff have_base)
+    uint32_t cnt;        // samples appended by this task so far: buf.count == base + cnt
+    uint32_t word_start; // word_start_sample - base
+    int32_t pred;
+    int16_t* dst;        // utterance slot in HBM
     uint32_t dst_cap;
     uint32_t err;
 };
 
-// ---------------------------------------------------------------- window moves
+// ---------------------------------------------------------------- look-back chain
 
-// dst[a..b) <- w[a..b); a is a multiple of 8 and both sides are 16-byte aligned there.
-__device__ __forceinline__ void flush_range(const State& s, uint32_t a, uint32_t b) {
-    const int tid = threadIdx.x;
-    uint32_t nvec = (b - a) >> 3;
-    const int4* src = reinterpret_cast<const int4*>(s.w + a);
-    int4* d = reinterpret_cast<int4*>(s.dst + a);
-    for (uint32_t i = tid; i < nvec; i += ASM_THREADS) d[i] = src[i];
-    for (uint32_t i = a + (nvec << 3) + tid; i < b; i += ASM_THREADS) s.dst[i] = s.w[i];
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Called at a word mark: decide where the next region lives, stream finished
-// samples to HBM and slide the live tail to the front of the shared window.
-__device__ void region_switch(State& s, const Smem& sm, const AsmArgs& A, uint32_t next_bound) {
-    const int tid = threadIdx.x;
-    uint32_t keep_from = s.count > A.halo ? ((s.count - A.halo) & ~7u) : 0u;
-    if (keep_from < s.base) keep_from = s.base;
-    bool want_smem = (unsigned long long)(s.count - keep_from) + next_bound + 8ull <= A.wcap;
-    __syncthreads();
-    if (s.in_smem) {
-        if (want_smem) {
-            flush_range(s, s.base, keep_from);
-            uint32_t delta = keep_from - s.base;
-            if (delta) {
-                // slide [keep_from, count) down by delta (both multiples of 8)
-                uint32_t n = s.count - keep_from;
-                int16_t* win = sm.win;
-                for (uint32_t c0 = 0; c0 < n; c0 += ASM_THREADS * 8) {
-                    uint32_t i = c0 + tid * 8;
-                    int4 v = make_int4(0, 0, 0, 0);
-                    if (i < n) v = *reinterpret_cast<const int4*>(win + delta + i);
-                    __syncthreads();
-                    if (i < n) *reinterpret_cast<int4*>(win + i) = v;
-                    __syncthreads();
-                }
-                s.base = keep_from;
-                s.w = sm.win - s.base;
-            }
-        } else {
-            flush_range(s, s.base, s.count);
-            s.in_smem = false;
-            s.base = 0;
-            s.cap = s.dst_cap;
-            s.w = s.dst;
+// Block until the predecessor task has published its inclusive count.
+__device__ void need_base(State& s, const Smem& sm, const AsmArgs& A) {
+    if (s.have_base) return;
+    if (threadIdx.x == 0) {
+        const unsigned long long* p = A.chain + s.pred;
+        unsigned long long v;
+        unsigned ns = 20;
+        while ((uint32_t)((v = ld_acquire_u64(p)) >> 32) != A.epoch) {
+            __nanosleep(ns);
+            if (ns < 640) ns *= 2;
         }
-    } else if (want_smem) {
-        // re-enter shared memory: bring the live tail back from HBM
-        uint32_t n = s.count - keep_from;
-        for (uint32_t i = tid; i < n; i += ASM_THREADS) sm.win[i] = s.dst[keep_from + i];
-        s.in_smem = true;
-        s.base = keep_from;
-        s.cap = A.wcap;
-        s.w = sm.win - s.base;
+        sm.bcast[0] = (uint32_t)v;
     }
+    __syncthreads();
+    s.base = sm.bcast[0];
+    s.have_base = true;
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- window moves
+
+// dst[base + a .. base + b) <- win[a..b): the source is 2-byte aligned only (base is arbitrary),
+// the destination is written with 16-byte stores.
+__device__ void flush_window(const State& s, const Smem& sm, uint32_t a, uint32_t b) {
+    const int tid = threadIdx.x;
+    if (b <= a) return;
+    int16_t* d = s.dst + s.base;   // d[i] <-> win[i]
+    const uint32_t phase = (uint32_t)((reinterpret_cast<uintptr_t>(d + a) >> 1) & 7u);
+    uint32_t h = (8u - phase) & 7u;          // scalar head up to the first aligned vector
+    if (h > b - a) h = b - a;
+    if ((uint32_t)tid < h) d[a + tid] = sm.win[a + tid];
+    const uint32_t v0 = a + h;               // first sample of vector 0
+    const uint32_t nvec = (b - v0) >> 3;
+    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(sm.win);
+    const uint32_t odd = v0 & 1u;
+    const uint32_t bits = odd * 16u;
+    int4* dv = reinterpret_cast<int4*>(d + v0);
+    if ((v0 & 7u) == 0) {
+        const int4* sv = reinterpret_cast<const int4*>(sm.win + v0);
+        for (uint32_t v = tid; v < nvec; v += ASM_THREADS) dv[v] = sv[v];
+    } else {
+        for (uint32_t v = tid; v < nvec; v += ASM_THREADS) {
+            const uint32_t wi = (v0 + 8u * v) >> 1;
+            uint32_t r0 = w32[wi], r1 = w32[wi + 1], r2 = w32[wi + 2], r3 = w32[wi + 3], r4 = w32[wi + 4];
+            int4 q;
+            q.x = (int)__funnelshift_r(r0, r1, bits);
+            q.y = (int)__funnelshift_r(r1, r2, bits);
+            q.z = (int)__funnelshift_r(r2, r3, bits);
+            q.w = (int)__funnelshift_r(r3, r4, bits);
+            dv[v] = q;
+        }
+    }
+    const uint32_t t0 = v0 + (nvec << 3);
+    if (t0 + tid < b) d[t0 + tid] = sm.win[t0 + tid];
+}
+
+// Continue this task on the HBM slot (needs the base): the window becomes dst + base.
+__device__ void enter_global(State& s, const Smem& sm, const AsmArgs& A) {
+    need_base(s, sm, A);
+    if (s.in_smem) {
+        __syncthreads();
+        flush_window(s, sm, 0, s.cnt);
+        s.in_smem = false;
+        s.w = s.dst + s.base;
+        s.cap = s.dst_cap > s.base ? s.dst_cap - s.base : 0u;
+    }
+    // make the predecessors' finished samples (and our own flush) visible to every thread
+    __threadfence();
     __syncthreads();
 }
 
@@ -178,143 +228,252 @@ __device__ void region_switch(State& s, const Smem& sm, const AsmArgs& A, uint32
 // buffer tail `a` and the unit head `b`).
 //
 // The reference evaluates, for each lag in 55..275, three sequential float sums
-// over i < 220: corr += s[i]*s[i+lag], e1 += s[i]^2, e2 += s[i+lag]^2.  The sums
-// must keep that order, so the parallel axis is the lag.  Each of 2 x 64 threads
-// owns FOUR consecutive lags and walks i in steps of 4 with one 16-byte load of
-// x = s[i..i+3] (broadcast) and one of the 4 new y = s[i+lag0+3 .. i+lag0+6]; the
-// 7-value sliding window of y (and of y*y, computed once per value) feeds the 16
-// (lag, i) pairs of the step: 3.4 instructions per pair instead of 8.5 for the
-// one-lag-per-thread loop.  e1 does not depend on the lag: one thread per signal
-// computes it concurrently.  The argmax keeps the smallest lag on ties (the
-// reference scans lags upward with a strict >).
-constexpr int PITCH_Y_WORDS = 576;  // y staging per signal (index + 2 keeps the 16-byte loads aligned)
-constexpr int PITCH_X_WORDS = 224;
-constexpr int PITCH_SCRATCH_WORDS = 2 * PITCH_Y_WORDS + 2 * PITCH_X_WORDS + 8;
+// over i < 220: corr += s[i]*s[i+lag], e1 += s[i]^2, e2 += s[i+lag]^2, and keeps
+// the first lag whose corr/sqrtf(e1*e2) is the strict maximum (voiced iff > 0.3).
+// Those sums cannot be reordered, and at 3 non-fused FP32 operations per
+// (lag, i) pair they are 40 % of all instructions of the assembly path.  So
+// the search is done in two steps that together give the identical result:
+//
+//  1. FILTER: every lag gets an approximate score a[lag] = c~ / sqrtf(e1x * e2x),
+//     c~ accumulated with FMA (one instruction per pair, four lags per thread
+//     sharing the operand loads) and e1x, e2x EXACT integer window sums taken
+//     from a 64-bit prefix sum of the squares.  For 220 terms |a - r| <= 4.2e-5
+//     where r is the reference's score (standard summation error bound,
+//     n*u*sum|x_i*y_i| <= n*u*sqrt(e1*e2) by Cauchy-Schwarz; DESIGN.md derives it).
+//  2. EXACT: with eps = 1e-3 (24 x the bound), a signal is unvoiced if
+//     max a <= 0.3 - eps; otherwise only lags with a >= max a - 2*eps can be the
+//     reference's arg max, and those (typically 1-3) are evaluated by one thread
+//     each with the reference's exact operation order.
+//
+// Both signals are needed voiced by the caller, so step 2 is skipped entirely
+// when either signal fails the filter.
+constexpr int PITCH_LO = CTTS_PLAN_SAMPLE_RATE / 400;  // 55
+constexpr int PITCH_HI = CTTS_PLAN_SAMPLE_RATE / 80;   // 275
+constexpr int PITCH_LEN = CTTS_PLAN_SAMPLE_RATE / 100; // 220
+constexpr int PITCH_LAG0 = 53;        // lag of thread 0 (= 1 mod 4 keeps both float4 loads aligned)
+constexpr int PITCH_LPT = 4;          // lags per thread
+constexpr int PITCH_TPS = 64;         // threads per signal (57 used)
+constexpr int PITCH_Y = 512;          // staged floats per signal (zero padded)
+constexpr int PITCH_S = 504;          // prefix entries per signal
+constexpr int PITCH_MAX_CAND = 64;    // per signal, beyond that: every lag is evaluated exactly
+constexpr float PITCH_EPS = 1e-3f;
+constexpr int PITCH_SCRATCH_WORDS = 2 * PITCH_Y + 2 * 2 * PITCH_S + 4 + 2 * (PITCH_MAX_CAND + 2) + 16;
+static_assert(PITCH_LAG0 % 4 == 1 && PITCH_LAG0 <= PITCH_LO, "lag tiling");
+static_assert(PITCH_LAG0 + PITCH_LPT * 57 > PITCH_HI, "57 threads cover every lag");
+static_assert(PITCH_HI + PITCH_LPT + PITCH_LEN + 8 <= PITCH_Y, "staging covers the loop's reads");
+static_assert(PITCH_HI + PITCH_LEN < PITCH_S, "prefix covers every window");
+
+// exact score of one lag in the reference's order (ctts.c:1917-1931); lag 0 yields e1 in *e2_out
+__device__ __forceinline__ float pitch_exact_sums(const float* y, uint32_t lag, uint32_t len, float* e2_out) {
+    float c = 0.0f, e2 = 0.0f;
+    const float* x = y;
+    const float* z = y + lag;
+#pragma unroll 4
+    for (uint32_t i = 0; i < len; i++) {
+        const float a = x[i], b = z[i];
+        c += a * b;
+        e2 += b * b;
+    }
+    *e2_out = e2;
+    return c;
+}
 
 __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int16_t* b, uint32_t n,
                                     float* pa, float* pb) {
-    static_assert(ASM_THREADS >= 192, "needs 128 lag threads + 2 energy threads");
-    static_assert((CTTS_PLAN_SAMPLE_RATE / 400) % 4 == 3, "y staging offset assumes min lag = 3 (mod 4)");
     *pa = 0.0f;
     *pb = 0.0f;
     if (n < 200) return;
-    const int tid = threadIdx.x;
-    const uint32_t lo = CTTS_PLAN_SAMPLE_RATE / 400;
-    uint32_t hi = CTTS_PLAN_SAMPLE_RATE / 80;
+    const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    const uint32_t lo = PITCH_LO;
+    uint32_t hi = PITCH_HI;
     if (hi > n / 2) hi = n / 2;
-    uint32_t len = CTTS_PLAN_SAMPLE_RATE / 100;
+    uint32_t len = PITCH_LEN;
     if (len > n - hi) len = n - hi;
+    const uint32_t need = len + hi;  // <= 495 samples of each signal are ever read
+
     float* ya = reinterpret_cast<float*>(sm.scratch);
-    float* yb = ya + PITCH_Y_WORDS;
-    float* xa = yb + PITCH_Y_WORDS;
-    float* xb = xa + PITCH_X_WORDS;
-    float* e1s = xb + PITCH_X_WORDS;  // [2]
-    const uint32_t need = len + hi;   // <= 495
-    for (uint32_t i = tid; i < PITCH_Y_WORDS; i += ASM_THREADS) {
-        bool in = i >= 2 && i - 2 < need;
-        ya[i] = in ? (float)a[i - 2] : 0.0f;
-        yb[i] = in ? (float)b[i - 2] : 0.0f;
+    float* yb = ya + PITCH_Y;
+    unsigned long long* Sa = reinterpret_cast<unsigned long long*>(yb + PITCH_Y);  // 8-byte aligned: 2*PITCH_Y even
+    unsigned long long* Sb = Sa + PITCH_S;
+    unsigned long long* keys = Sb + PITCH_S;                      // [2]
+    uint32_t* cand = reinterpret_cast<uint32_t*>(keys + 2);       // [2][PITCH_MAX_CAND + 2]
+    uint32_t* ncand = cand + 2 * (PITCH_MAX_CAND + 2);            // [2]
+    float* amax = reinterpret_cast<float*>(ncand + 2);            // [4] per lag warp
+    float* e1s = amax + 4;                                        // [2]
+
+    for (uint32_t i = tid; i < PITCH_Y; i += ASM_THREADS) {
+        const bool in = i < need;
+        ya[i] = in ? (float)a[i] : 0.0f;
+        yb[i] = in ? (float)b[i] : 0.0f;
     }
-    for (uint32_t i = tid; i < PITCH_X_WORDS; i += ASM_THREADS) {
-        bool in = i < len;
-        xa[i] = in ? (float)a[i] : 0.0f;
-        xb[i] = in ? (float)b[i] : 0.0f;
+    if (tid < 2) {
+        ncand[tid] = 0;
+        keys[tid] = 0ull;
     }
     __syncthreads();
 
-    float c[4] = {0.0f, 0.0f, 0.0f, 0.0f}, e2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    // ---- step 1: FMA scores on warps 0-3, exact prefix sums of squares on warps 4-5
+    float c[PITCH_LPT] = {0.0f, 0.0f, 0.0f, 0.0f};
     const int sig = (tid >> 6) & 1;
-    const uint32_t lag0 = lo + 4u * (uint32_t)(tid & 63);
-    if (tid < 128 && lag0 <= hi) {
-        const float* x = sig ? xb : xa;
-        const float* y = (sig ? yb : ya) + 2 + lag0;  // y[j] = s[lag0 + j]
+    const uint32_t lag0 = PITCH_LAG0 + PITCH_LPT * (uint32_t)(tid & (PITCH_TPS - 1));
+    const bool lag_thread = tid < 2 * PITCH_TPS && lag0 <= hi;
+    if (lag_thread) {
+        const float* x = sig ? yb : ya;
+        const float* y = x + lag0;  // y[j] = s[lag0 + j]; (lag0 + 3) % 4 == 0
         float w0 = y[0], w1 = y[1], w2 = y[2];
-        float q0 = w0 * w0, q1 = w1 * w1, q2 = w2 * w2;
         const uint32_t len4 = len & ~3u;
         for (uint32_t i = 0; i < len4; i += 4) {
             const float4 xv = *reinterpret_cast<const float4*>(x + i);
             const float4 yn = *reinterpret_cast<const float4*>(y + i + 3);
             const float w3 = yn.x, w4 = yn.y, w5 = yn.z, w6 = yn.w;
-            const float q3 = w3 * w3, q4 = w4 * w4, q5 = w5 * w5, q6 = w6 * w6;
-            c[0] += xv.x * w0; c[1] += xv.x * w1; c[2] += xv.x * w2; c[3] += xv.x * w3;
-            e2[0] += q0; e2[1] += q1; e2[2] += q2; e2[3] += q3;
-            c[0] += xv.y * w1; c[1] += xv.y * w2; c[2] += xv.y * w3; c[3] += xv.y * w4;
-            e2[0] += q1; e2[1] += q2; e2[2] += q3; e2[3] += q4;
-            c[0] += xv.z * w2; c[1] += xv.z * w3; c[2] += xv.z * w4; c[3] += xv.z * w5;
-            e2[0] += q2; e2[1] += q3; e2[2] += q4; e2[3] += q5;
-            c[0] += xv.w * w3; c[1] += xv.w * w4; c[2] += xv.w * w5; c[3] += xv.w * w6;
-            e2[0] += q3; e2[1] += q4; e2[2] += q5; e2[3] += q6;
+            c[0] = __fmaf_rn(xv.x, w0, c[0]); c[1] = __fmaf_rn(xv.x, w1, c[1]);
+            c[2] = __fmaf_rn(xv.x, w2, c[2]); c[3] = __fmaf_rn(xv.x, w3, c[3]);
+            c[0] = __fmaf_rn(xv.y, w1, c[0]); c[1] = __fmaf_rn(xv.y, w2, c[1]);
+            c[2] = __fmaf_rn(xv.y, w3, c[2]); c[3] = __fmaf_rn(xv.y, w4, c[3]);
+            c[0] = __fmaf_rn(xv.z, w2, c[0]); c[1] = __fmaf_rn(xv.z, w3, c[1]);
+            c[2] = __fmaf_rn(xv.z, w4, c[2]); c[3] = __fmaf_rn(xv.z, w5, c[3]);
+            c[0] = __fmaf_rn(xv.w, w3, c[0]); c[1] = __fmaf_rn(xv.w, w4, c[1]);
+            c[2] = __fmaf_rn(xv.w, w5, c[2]); c[3] = __fmaf_rn(xv.w, w6, c[3]);
             w0 = w4; w1 = w5; w2 = w6;
-            q0 = q4; q1 = q5; q2 = q6;
         }
         for (uint32_t i = len4; i < len; i++) {
             const float xs = x[i];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float ys = y[i + k];
-                c[k] += xs * ys;
-                e2[k] += ys * ys;
+            for (int k = 0; k < PITCH_LPT; k++) c[k] = __fmaf_rn(xs, y[i + k], c[k]);
+        }
+    } else if (warp == 4 || warp == 5) {
+        // S[i] = sum_{j<i} s[j]^2, exact (values are int16, 504 * 2^30 < 2^64)
+        const float* y = warp == 5 ? yb : ya;
+        unsigned long long* S = warp == 5 ? Sb : Sa;
+        constexpr int PER = 16;  // 32 lanes * 16 = 512 >= PITCH_S
+        unsigned long long loc = 0;
+        const int i0 = lane * PER;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int v = (int)y[i0 + k];
+            loc += (unsigned long long)(uint32_t)(v * v);
+        }
+        unsigned long long inc = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        unsigned long long run = inc - loc;  // exclusive
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            if (i0 + k < PITCH_S) S[i0 + k] = run;
+            const int v = (int)y[i0 + k];
+            run += (unsigned long long)(uint32_t)(v * v);
+        }
+    }
+    __syncthreads();
+
+    // ---- scores and per-signal maximum
+    float sc[PITCH_LPT];
+    float my_max = -1.0f;
+    if (lag_thread) {
+        const unsigned long long* S = sig ? Sb : Sa;
+        const float e1 = (float)(S[len] - S[0]);
+#pragma unroll
+        for (int k = 0; k < PITCH_LPT; k++) {
+            const uint32_t lag = lag0 + k;
+            sc[k] = -1.0f;
+            if (lag >= lo && lag <= hi) {
+                const float e2 = (float)(S[lag + len] - S[lag]);
+                const float nrm = sqrtf(e1 * e2);
+                sc[k] = nrm > 0.0f ? c[k] / nrm : 0.0f;
+                my_max = fmaxf(my_max, sc[k]);
             }
         }
-    } else if (tid == 128 || tid == 160) {
-        const float* x = tid == 160 ? xb : xa;
-        float e1 = 0.0f;
-        for (uint32_t i = 0; i < len; i++) e1 += x[i] * x[i];
-        e1s[tid == 160 ? 1 : 0] = e1;
+    }
+    if (tid < 2 * PITCH_TPS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_max = fmaxf(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
+        if (lane == 0) amax[warp] = my_max;
     }
     __syncthreads();
-    unsigned long long key = 0ull;
-    if (tid < 128 && lag0 <= hi) {
-        const float e1 = e1s[sig];
-        float best = 0.0f;
-        uint32_t best_lag = 0;
+    const float max_a = fmaxf(amax[0], amax[1]), max_b = fmaxf(amax[2], amax[3]);
+    // unvoiced by the filter: the reference's best cannot exceed 0.3
+    if (!(max_a > 0.3f - PITCH_EPS) || !(max_b > 0.3f - PITCH_EPS)) {   // CTA-uniform
+        __syncthreads();   // scratch is reused by the caller
+        return;
+    }
+
+    // ---- candidates
+    if (lag_thread) {
+        const float thr = (sig ? max_b : max_a) - 2.0f * PITCH_EPS;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (lag0 + k > hi) break;
-            float v = c[k];
-            float nrm = sqrtf(e1 * e2[k]);
-            if (nrm > 0) v /= nrm;
-            if (v > best) {
-                best = v;
-                best_lag = lag0 + k;
+        for (int k = 0; k < PITCH_LPT; k++) {
+            if (sc[k] >= thr) {
+                uint32_t slot = atomicAdd(ncand + sig, 1u);
+                if (slot < PITCH_MAX_CAND) cand[sig * (PITCH_MAX_CAND + 2) + slot] = lag0 + k;
             }
         }
-        if (best_lag) key = ((unsigned long long)__float_as_uint(best) << 32) | (0xffffffffu - best_lag);
     }
-    // max per signal: warps 0-1 hold signal a, warps 2-3 signal b
-    if (tid < 128) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-            key = other > key ? other : key;
+    __syncthreads();
+    uint32_t na = ncand[0], nb = ncand[1];
+    const bool all_a = na > PITCH_MAX_CAND, all_b = nb > PITCH_MAX_CAND;  // degenerate: evaluate every lag
+    if (all_a) na = hi - lo + 1;
+    if (all_b) nb = hi - lo + 1;
+    __syncthreads();
+
+    // ---- step 2: exact evaluation, one thread per (signal, lag); job 0 of each signal is lag 0 (= e1)
+    const uint32_t jobs = na + nb + 2;
+    for (uint32_t j = tid; j < jobs; j += ASM_THREADS) {
+        const int sg = j < na + 1 ? 0 : 1;
+        const uint32_t jj = sg ? j - (na + 1) : j;
+        if (jj == 0) {
+            float e1;
+            (void)pitch_exact_sums(sg ? yb : ya, 0, len, &e1);
+            e1s[sg] = e1;
+        } else {
+            const bool all = sg ? all_b : all_a;
+            const uint32_t lag = all ? lo + (jj - 1) : cand[sg * (PITCH_MAX_CAND + 2) + (jj - 1)];
+            float e2;
+            const float cc = pitch_exact_sums(sg ? yb : ya, lag, len, &e2);
+            // park the raw sums; the score needs e1, which another thread is computing
+            reinterpret_cast<float2*>(sg ? Sb : Sa)[jj] = make_float2(cc, e2);   // S is dead from here on
         }
-        if (lane_id() == 0) sm.red[warp_id()] = key;
     }
     __syncthreads();
-    const unsigned long long ka = sm.red[0] > sm.red[1] ? sm.red[0] : sm.red[1];
-    const unsigned long long kb = sm.red[2] > sm.red[3] ? sm.red[2] : sm.red[3];
+    for (uint32_t j = tid; j < jobs; j += ASM_THREADS) {
+        const int sg = j < na + 1 ? 0 : 1;
+        const uint32_t jj = sg ? j - (na + 1) : j;
+        if (jj == 0) continue;
+        const bool all = sg ? all_b : all_a;
+        const uint32_t lag = all ? lo + (jj - 1) : cand[sg * (PITCH_MAX_CAND + 2) + (jj - 1)];
+        const float2 ce = reinterpret_cast<const float2*>(sg ? Sb : Sa)[jj];
+        float v = ce.x;
+        const float nrm = sqrtf(e1s[sg] * ce.y);
+        if (nrm > 0) v /= nrm;
+        // the reference keeps the first lag that is strictly greater than everything before it,
+        // starting from 0: the maximum positive score, smallest lag on ties
+        if (v > 0.0f) atomicMax(keys + sg, ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - lag));
+    }
     __syncthreads();
+    const unsigned long long ka = keys[0], kb = keys[1];
     {
-        float v = __uint_as_float((uint32_t)(ka >> 32));
-        uint32_t l = 0xffffffffu - (uint32_t)(ka & 0xffffffffu);
+        const float v = __uint_as_float((uint32_t)(ka >> 32));
+        const uint32_t l = 0xffffffffu - (uint32_t)(ka & 0xffffffffu);
         if (ka != 0ull && v > 0.3f && l > 0) *pa = (float)CTTS_PLAN_SAMPLE_RATE / (float)l;
     }
     {
-        float v = __uint_as_float((uint32_t)(kb >> 32));
-        uint32_t l = 0xffffffffu - (uint32_t)(kb & 0xffffffffu);
+        const float v = __uint_as_float((uint32_t)(kb >> 32));
+        const uint32_t l = 0xffffffffu - (uint32_t)(kb & 0xffffffffu);
         if (kb != 0ull && v > 0.3f && l > 0) *pb = (float)CTTS_PLAN_SAMPLE_RATE / (float)l;
     }
+    __syncthreads();   // scratch is reused by the caller
 }
 
-// smooth_pitch_boundary + apply_pitch_shift, ctts.c:1946-2024
-__device__ void smooth_pitch(const State& s, const Smem& sm, int16_t* us, uint32_t n, uint32_t xf) {
-    if (xf == 0 || s.count < 200 || n < 200) return;
+// smooth_pitch_boundary + apply_pitch_shift, ctts.c:1946-2024.  `reg` is the analysis length
+// min(2*xf, count/2, n/2) resolved by the caller (0 = the reference returns early); `us` is the
+// staged unit head.
+__device__ void smooth_pitch(const State& s, const Smem& sm, int16_t* us, uint32_t n, uint32_t xf, uint32_t reg) {
+    if (reg == 0) return;
     const int tid = threadIdx.x;
-    uint32_t reg = xf * 2;
-    if (reg > s.count / 2) reg = s.count / 2;
-    if (reg > n / 2) reg = n / 2;
     float pp, np;
-    estimate_pitch_pair(sm, s.w + (s.count - reg), us, reg, &pp, &np);
+    estimate_pitch_pair(sm, s.w + ((int)s.cnt - (int)reg), us, reg, &pp, &np);
     if (!(pp > 0 && np > 0)) return;
     float ratio = np / pp;
     if (!(ratio > 1.15f || ratio < 0.85f)) return;
@@ -322,7 +481,7 @@ __device__ void smooth_pitch(const State& s, const Smem& sm, int16_t* us, uint32
     float shift = target / ratio;
     uint32_t len = xf;
     if (len > n / 4) len = n / 4;
-    int16_t* tmp = reinterpret_cast<int16_t*>(sm.scratch);  // len <= ucap/4 samples
+    int16_t* tmp = reinterpret_cast<int16_t*>(sm.scratch);  // len <= hcap <= 2 * scr_words
     bool do_shift = !(shift < 0.9f || shift > 1.1f || len < 100);
     uint32_t keep = len;
     if (do_shift) {
@@ -350,14 +509,11 @@ __device__ void smooth_pitch(const State& s, const Smem& sm, int16_t* us, uint32
     __syncthreads();
 }
 
-// match_boundary_energy, ctts.c:1730 (sums of squares are exact integers)
-__device__ void match_energy(const State& s, const Smem& sm, int16_t* us, uint32_t n, uint32_t xf) {
-    if (xf == 0 || s.count == 0 || n == 0) return;
+// match_boundary_energy, ctts.c:1730 (sums of squares are exact integers); len = min(xf, count, n)
+__device__ void match_energy(const State& s, const Smem& sm, int16_t* us, uint32_t len) {
+    if (len == 0) return;
     const int tid = threadIdx.x;
-    uint32_t len = xf;
-    if (len > s.count) len = s.count;
-    if (len > n) len = n;
-    const int16_t* tail = s.w + (s.count - len);
+    const int16_t* tail = s.w + ((int)s.cnt - (int)len);
     long long sp = 0, sn = 0;
     for (uint32_t i = tid; i < len; i += ASM_THREADS) {
         int p = tail[i], q = us[i];
@@ -404,39 +560,106 @@ __device__ __forceinline__ int sub_dc(int v, int dc) {
     return max(__viaddmin_s32(v, -dc, 32767), -32768);
 }
 
-// ctts.c:3785-3846: gather -> normalize_rms -> [smooth, match] -> buffer_append_crossfade
+// normalize_rms's per-sample step (ctts.c:1720-1725)
+__device__ __forceinline__ int scale_sample(int x, bool scale, float g) {
+    return scale ? (int)f2s(clamp16f((float)x * g)) : x;
+}
+
+// 8 consecutive samples starting `sh` samples (1..8) into the 16-sample pair (lo, hi)
+__device__ __forceinline__ int4 shift_pick(const int4& lo, const int4& hi, uint32_t sh) {
+    const uint32_t r0 = lo.x, r1 = lo.y, r2 = lo.z, r3 = lo.w, r4 = hi.x, r5 = hi.y, r6 = hi.z, r7 = hi.w;
+    uint32_t a0, a1, a2, a3, a4;
+    switch (sh >> 1) {   // CTA-uniform
+        case 0: a0 = r0; a1 = r1; a2 = r2; a3 = r3; a4 = r4; break;
+        case 1: a0 = r1; a1 = r2; a2 = r3; a3 = r4; a4 = r5; break;
+        case 2: a0 = r2; a1 = r3; a2 = r4; a3 = r5; a4 = r6; break;
+        case 3: a0 = r3; a1 = r4; a2 = r5; a3 = r6; a4 = r7; break;
+        default: a0 = r4; a1 = r5; a2 = r6; a3 = r7; a4 = 0u; break;
+    }
+    const uint32_t bits = (sh & 1u) * 16u;
+    int4 q;
+    q.x = (int)__funnelshift_r(a0, a1, bits);
+    q.y = (int)__funnelshift_r(a1, a2, bits);
+    q.z = (int)__funnelshift_r(a2, a3, bits);
+    q.w = (int)__funnelshift_r(a3, a4, bits);
+    return q;
+}
+
+// ctts.c:3785-3846: gather -> normalize_rms -> [smooth, match] -> buffer_append_crossfade.
+//
+// The unit's first `hs` samples (everything the join may rewrite, and what the pitch analysis
+// reads) are staged in `hstage`; the rest is written straight to its final place in the window,
+// on the window's own 16-byte grid (the pool side is re-aligned with a funnel shift), and
+// revisited once in place to subtract the DC offset -- which is only known after the head has
+// been smoothed and energy matched.
 __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_plan_op& op) {
     const int tid = threadIdx.x;
     if (op.a >= A.n_units) { s.err = ERR_BAD_OP; return; }
     const uint32_t n = __ldg(A.unit_cnt + op.a);
     if (n == 0) return;
-    if (n > A.ucap) { s.err = ERR_UNIT_TOO_LONG; return; }
     const int16_t* src = A.pool + __ldg(A.unit_off + op.a);
-    int16_t* us = sm.ustage;
+    const int4* srcv = reinterpret_cast<const int4*>(src);
+    const uint32_t nvec = (n + 7) >> 3;
+    int16_t* us = sm.hstage;
     const uint32_t xf = op.b;
     const bool boundary = (op.flags & CTTS_UNIT_AFTER_BOUNDARY) != 0;
-    const bool join = !boundary && s.count > 0;
     const bool remove_dc = A.prm.remove_dc_offset != 0;
-    // samples [0, head) may still be rewritten by smooth_pitch / match_energy
-    const uint32_t head = join ? (xf < n ? xf : n) : 0u;
 
-    // gather with 16-byte loads (pool is zero-padded to 8 samples per unit) + sum of squares
+    // ---- decisions that depend on buf.count = base + cnt; the base is only waited for when
+    //      the samples of this task alone cannot settle them
+    bool join = false;
+    if (!boundary) {
+        if (s.cnt == 0) need_base(s, sm, A);
+        join = s.cnt > 0 || s.base > 0;
+    }
+    // !join <=> count == 0 || after_word_boundary: the unit starts fresh (fade-in, no crossfade)
+    uint32_t a = 0;             // crossfade = energy-match length min(xf, count, n), ctts.c:3319, :1736
+    uint32_t reg = 0;           // pitch analysis length, ctts.c:1983-1987
+    if (join && xf > 0) {
+        const uint32_t m = xf < n ? xf : n;
+        if (s.cnt >= m) a = m;
+        else {
+            need_base(s, sm, A);
+            const unsigned long long count = (unsigned long long)s.base + s.cnt;
+            a = count < m ? (uint32_t)count : m;
+        }
+        if (n >= 200) {
+            const uint32_t m2 = 2 * xf < n / 2 ? 2 * xf : n / 2;
+            if (s.cnt >= 200 && s.cnt / 2 >= m2) reg = m2;
+            else {
+                need_base(s, sm, A);
+                const unsigned long long count = (unsigned long long)s.base + s.cnt;
+                if (count >= 200) reg = count / 2 < m2 ? (uint32_t)(count / 2) : m2;
+            }
+        }
+        // a window that reaches back past the start of this task: continue on the HBM slot
+        if ((a > s.cnt || reg > s.cnt) && s.in_smem) enter_global(s, sm, A);
+    }
+    if ((unsigned long long)s.cnt + (n - a) > s.cap) { s.err = ERR_WINDOW_OVERFLOW; return; }
+
+    // staged head: what smooth/match may rewrite (min(xf, n)) and what the pitch analysis reads (<= 495)
+    uint32_t hs = 0;
+    if (join) {
+        uint32_t want = xf < n ? xf : n;
+        if (reg > 0 && want < 496) want = 496;
+        hs = (want + 7) & ~7u;
+        if (hs > (nvec << 3)) hs = nvec << 3;
+        if (hs > A.hcap) { s.err = ERR_UNIT_TOO_LONG; return; }
+    }
+    const uint32_t hsn = hs < n ? hs : n;   // staged samples that exist
+
+    // ---- pass 1: sum of squares (normalize_rms, ctts.c:1709; double sum of integers == integer sum)
     long long ss = 0;
-    const uint32_t nvec = (n + 7) >> 3;
     for (uint32_t v = tid; v < nvec; v += ASM_THREADS) {
-        int4 q = __ldg(reinterpret_cast<const int4*>(src) + v);
-        *(reinterpret_cast<int4*>(us) + v) = q;
+        const int4 q = __ldg(srcv + v);
         const int16_t* e = reinterpret_cast<const int16_t*>(&q);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            int x = e[k];
-            ss += (long long)x * x;
+            const int x = e[k];
+            ss += (long long)(x * x);
         }
     }
     ss = block_allreduce<ASM_THREADS>(ss, OpAddI64(), reinterpret_cast<long long*>(sm.red));
-    // normalize_rms, ctts.c:1709 (double sum of squares == integer sum, exactly); the DC sum of
-    // everything past `head` is taken on the way (integer, order-free)
-    int dsum = 0;
     bool scale = false;
     float g = 1.0f;
     if (A.prm.target_rms > 0) {
@@ -448,101 +671,109 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
             scale = true;
         }
     }
-    for (uint32_t v = tid; v < nvec; v += ASM_THREADS) {
-        int4 q = *(reinterpret_cast<int4*>(us) + v);
+
+    // ---- pass 2: scale; head -> hstage, body -> window (aligned vectors of the window)
+    for (uint32_t v = tid; v < (hs >> 3); v += ASM_THREADS) {
+        int4 q = __ldg(srcv + v);
         int16_t* e = reinterpret_cast<int16_t*>(&q);
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            int y = e[k];
-            if (scale) {
-                y = (int)f2s(clamp16f((float)y * g));
-                e[k] = (int16_t)y;
-            }
-            if (v * 8 + k >= head) dsum += y;   // padding past n is zero
+        for (int k = 0; k < 8; k++) e[k] = (int16_t)scale_sample((int)e[k], scale, g);
+        *(reinterpret_cast<int4*>(us) + v) = q;
+    }
+    // unit sample i lands at tail[i]; the body is [hs, n)
+    int16_t* tail = s.w + ((int)s.cnt - (int)a);
+    const uint32_t phase = (uint32_t)((reinterpret_cast<uintptr_t>(tail + hs) >> 1) & 7u);
+    int16_t* grid = tail + hs - phase;                       // 16-byte aligned
+    const uint32_t body = n - hsn;                            // may be 0
+    const uint32_t gvec = body ? (phase + body + 7) >> 3 : 0; // window vectors that hold body samples
+    const uint32_t pv0 = hs >> 3;                             // pool vector of unit sample hs
+    int dsum = 0;
+    for (uint32_t j = tid; j < gvec; j += ASM_THREADS) {
+        // window vector j holds unit samples i0 .. i0+7, i0 = hs - phase + 8j
+        int4 q;
+        if (phase == 0) {
+            q = __ldg(srcv + pv0 + j);
+        } else {
+            int4 lo = make_int4(0, 0, 0, 0), hi = make_int4(0, 0, 0, 0);
+            if (pv0 + j >= 1) lo = __ldg(srcv + pv0 + j - 1);
+            if (pv0 + j < nvec) hi = __ldg(srcv + pv0 + j);
+            q = shift_pick(lo, hi, 8u - phase);
         }
-        if (scale) *(reinterpret_cast<int4*>(us) + v) = q;
+        int16_t* e = reinterpret_cast<int16_t*>(&q);
+        const int i0 = (int)hs - (int)phase + 8 * (int)j;
+        const bool full = i0 >= (int)hs && i0 + 8 <= (int)n;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int y = scale_sample((int)e[k], scale, g);
+            e[k] = (int16_t)y;
+            if (full || (i0 + k >= (int)hs && i0 + k < (int)n)) dsum += y;
+        }
+        if (full) {
+            *(reinterpret_cast<int4*>(grid) + j) = q;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (i0 + k >= (int)hs && i0 + k < (int)n) grid[8 * j + k] = e[k];
+        }
     }
     __syncthreads();
 
     if (join) {
-        smooth_pitch(s, sm, us, n, xf);
-        match_energy(s, sm, us, n, xf);
+        smooth_pitch(s, sm, us, n, xf, reg);
+        match_energy(s, sm, us, a);
     }
 
-    // buffer_append_crossfade, ctts.c:3279
+    // ---- remove_dc_offset (ctts.c:1568) inside buffer_append_crossfade (ctts.c:3279)
     int dc = 0;
     if (remove_dc) {
-        for (uint32_t i = tid; i < head; i += ASM_THREADS) dsum += us[i];
+        for (uint32_t i = tid; i < hsn; i += ASM_THREADS) dsum += us[i];
         long long sum = block_allreduce<ASM_THREADS>((long long)dsum, OpAddI64(), reinterpret_cast<long long*>(sm.red));
         dc = (int)(int16_t)(sum / (long long)n);
     }
-    const bool fresh = (s.count == 0) || boundary;
-    uint32_t a = 0;
-    if (!fresh && xf > 0) {
-        a = xf;
-        if (a > s.count) a = s.count;
-        if (a > n) a = n;
-    }
-    if ((unsigned long long)s.count - s.base + (n - a) > s.cap) { s.err = ERR_WINDOW_OVERFLOW; return; }
-    int16_t* tail = s.w + (s.count - a);   // unit sample i lands at tail[i]
-
-    // prefix that is not a plain copy: the fade-in (ctts.c:3015) or the crossfade mix (ctts.c:3328-3344)
-    uint32_t pre = 0;
-    if (fresh) {
-        pre = A.prm.fade_in_samples < n ? A.prm.fade_in_samples : n;
-        if (pre) {
-            const float inv = 1.0f / (float)pre;
-            for (uint32_t i = tid; i < pre; i += ASM_THREADS) {
-                int v = us[i];
-                if (remove_dc) v = sub_dc(v, dc);
-                tail[i] = f2s((float)v * lut_lerp(A.tab.sine, (float)i * inv));
-            }
-        }
-    } else if (a) {
-        pre = a;
-        const float inv = 1.0f / (float)a;
-        for (uint32_t i = tid; i < a; i += ASM_THREADS) {
-            int v = us[i];
-            if (remove_dc) v = sub_dc(v, dc);
-            float pg, ng;
-            crossfade_gains(A.tab, (float)i * inv, &pg, &ng);
-            int p = tail[i];
-            int mix = (int)((float)p * pg + (float)v * ng);
-            tail[i] = (int16_t)max(min(mix, 32767), -32768);
-        }
-    }
-    // the rest: DC removal + copy, 8 samples per thread from the aligned staging buffer
-    {
-        const uint32_t v0 = pre >> 3;
-        for (uint32_t v = v0 + tid; v < nvec; v += ASM_THREADS) {
-            int4 q = *(reinterpret_cast<const int4*>(us) + v);
-            const int16_t* e = reinterpret_cast<const int16_t*>(&q);
-            const uint32_t i0 = v << 3;
-            int y[8];
+    // body in place
+    if (dc != 0) {
+        for (uint32_t j = tid; j < gvec; j += ASM_THREADS) {
+            const int i0 = (int)hs - (int)phase + 8 * (int)j;
+            const bool full = i0 >= (int)hs && i0 + 8 <= (int)n;
+            if (full) {
+                int4 q = *(reinterpret_cast<int4*>(grid) + j);
+                int16_t* e = reinterpret_cast<int16_t*>(&q);
 #pragma unroll
-            for (int k = 0; k < 8; k++) y[k] = remove_dc ? sub_dc((int)e[k], dc) : (int)e[k];
-            if (i0 >= pre && i0 + 8 <= n) {
-                int16_t* d = tail + i0;
-                if ((reinterpret_cast<uintptr_t>(d) & 3) == 0) {
-                    uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
-#pragma unroll
-                    for (int k = 0; k < 4; k++) d32[k] = (uint32_t)(y[2 * k] & 0xffff) | ((uint32_t)y[2 * k + 1] << 16);
-                } else {
-                    d[0] = (int16_t)y[0];
-                    uint32_t* d32 = reinterpret_cast<uint32_t*>(d + 1);
-#pragma unroll
-                    for (int k = 0; k < 3; k++)
-                        d32[k] = (uint32_t)(y[2 * k + 1] & 0xffff) | ((uint32_t)y[2 * k + 2] << 16);
-                    d[7] = (int16_t)y[7];
-                }
+                for (int k = 0; k < 8; k++) e[k] = (int16_t)sub_dc((int)e[k], dc);
+                *(reinterpret_cast<int4*>(grid) + j) = q;
             } else {
 #pragma unroll
                 for (int k = 0; k < 8; k++)
-                    if (i0 + k >= pre && i0 + k < n) tail[i0 + k] = (int16_t)y[k];
+                    if (i0 + k >= (int)hs && i0 + k < (int)n) grid[8 * j + k] = (int16_t)sub_dc((int)grid[8 * j + k], dc);
             }
         }
     }
-    s.count += n - a;
+    if (join) {
+        // staged head: crossfade mix (ctts.c:3328-3344) over [0, a), plain copy over [a, hsn)
+        const float inv = a ? 1.0f / (float)a : 0.0f;
+        for (uint32_t i = tid; i < hsn; i += ASM_THREADS) {
+            int v = us[i];
+            if (remove_dc) v = sub_dc(v, dc);
+            if (i < a) {
+                float pg, ng;
+                crossfade_gains(A.tab, (float)i * inv, &pg, &ng);
+                int p = tail[i];
+                int mix = (int)((float)p * pg + (float)v * ng);
+                v = max(min(mix, 32767), -32768);
+            }
+            tail[i] = (int16_t)v;
+        }
+    } else {
+        // fade-in of a word-initial unit (apply_fade_in, ctts.c:3015), after the DC removal
+        const uint32_t pre = A.prm.fade_in_samples < n ? A.prm.fade_in_samples : n;
+        if (pre) {
+            __syncthreads();
+            const float inv = 1.0f / (float)pre;
+            for (uint32_t i = tid; i < pre; i += ASM_THREADS)
+                tail[i] = f2s((float)tail[i] * lut_lerp(A.tab.sine, (float)i * inv));
+        }
+    }
+    s.cnt += n - a;
     __syncthreads();
 }
 
@@ -550,7 +781,7 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
 
 // remove_silence_regions, ctts.c:1634, as a bitmask + scan + in-place compaction.
 // Returns the new length.  `reg` = w + word_start, len = count - word_start.
-__device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t utt, int16_t* reg, uint32_t len) {
+__device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t big, int16_t* reg, uint32_t len) {
     const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const uint32_t min_sil = A.prm.min_silence_samples;
     int pk = 0;
@@ -567,7 +798,7 @@ __device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t utt, 
     const uint32_t wn = (len + 31) >> 5;
     uint32_t* words;
     if (2 * wn <= A.scr_words) words = sm.scratch;
-    else words = A.trim_scratch + (size_t)utt * A.trim_scratch_words;
+    else words = A.trim_scratch + (size_t)big * A.trim_scratch_words;   // host sized it for this task
     uint32_t* woff = words + wn;
 
     // 1 bit per sample: |x| <= threshold
@@ -817,15 +1048,15 @@ __device__ bool pitch_contour(const Smem& sm, int16_t* x, uint32_t n, float f0, 
 }
 
 // ctts.c:3693-3713 / :3878-3898: trim then phrase intonation on [word_start, count)
-__device__ void op_word_end(State& s, const Smem& sm, const AsmArgs& A, uint32_t utt, const ctts_plan_op& op) {
+__device__ void op_word_end(State& s, const Smem& sm, const AsmArgs& A, uint32_t big, const ctts_plan_op& op) {
     const int tid = threadIdx.x;
-    if ((op.flags & CTTS_WE_TRIM) && s.count > s.word_start) {
-        uint32_t len = s.count - s.word_start;
+    if ((op.flags & CTTS_WE_TRIM) && s.cnt > s.word_start) {
+        uint32_t len = s.cnt - s.word_start;
         if (len > A.prm.min_silence_samples)
-            s.count = s.word_start + trim_region(sm, A, utt, s.w + s.word_start, len);
+            s.cnt = s.word_start + trim_region(sm, A, big, s.w + s.word_start, len);
     }
-    if (s.count <= s.word_start) return;
-    const uint32_t n = s.count - s.word_start;
+    if (s.cnt <= s.word_start) return;
+    const uint32_t n = s.cnt - s.word_start;
     int16_t* x = s.w + s.word_start;
     // device half of apply_phrase_intonation, ctts.c:2740, :2774-2790, :2839-2865
     if (!(op.flags & CTTS_WE_INTON) || n < 100) return;
@@ -861,40 +1092,66 @@ __device__ void op_word_end(State& s, const Smem& sm, const AsmArgs& A, uint32_t
 
 // ---------------------------------------------------------------- kernel
 
-__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const AsmArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem sm;
-    sm.win = reinterpret_cast<int16_t*>(smem_raw);
-    sm.ustage = sm.win + A.wcap;
-    sm.scratch = reinterpret_cast<uint32_t*>(sm.ustage + A.ucap);
-    sm.hann256 = reinterpret_cast<float*>(sm.scratch + A.scr_words);
-    sm.nrm2 = sm.hann256 + PITCH_FRAME;
-    sm.red = reinterpret_cast<unsigned long long*>(sm.nrm2 + PITCH_FRAME / 2);
+// apply_fade_out on the buffer tail (ctts.c:3028): `if (buf.count > 0) apply_fade_out(buf, count, a)`
+__device__ void op_fade_out(State& s, const Smem& sm, const AsmArgs& A, uint32_t a) {
+    if (a == 0) return;
+    uint32_t f = a;
+    if (s.cnt < a) {
+        need_base(s, sm, A);
+        const unsigned long long count = (unsigned long long)s.base + s.cnt;
+        if (count == 0) return;
+        if (count < f) f = (uint32_t)count;
+        if (f > s.cnt && s.in_smem) enter_global(s, sm, A);
+    }
+    int16_t* p = s.w + ((int)s.cnt - (int)f);
+    const float inv = 1.0f / (float)f;
+    for (uint32_t i = threadIdx.x; i < f; i += ASM_THREADS)
+        p[i] = f2s((float)p[i] * lut_lerp(A.tab.sine, (float)(f - i) * inv));
+    __syncthreads();
+}
 
+// buffer_append_silence, ctts.c:3361
+__device__ void op_silence(State& s, uint32_t n) {
+    if ((unsigned long long)s.cnt + n > s.cap) { s.err = ERR_WINDOW_OVERFLOW; return; }
+    int16_t* p = s.w + s.cnt;
     const int tid = threadIdx.x;
-    for (int i = tid; i < PITCH_FRAME; i += ASM_THREADS) sm.hann256[i] = __ldg(A.tab.hann256 + i);
-    // norm of a sample covered by two frames: (0 + w[i+128]) + w[i], the reference's accumulation order
-    for (int i = tid; i < PITCH_FRAME / 2; i += ASM_THREADS)
-        sm.nrm2[i] = __ldg(A.tab.hann256 + i + PITCH_FRAME / 2) + __ldg(A.tab.hann256 + i);
+    // scalar head to the 16-byte grid, vector body, scalar tail
+    uint32_t h = (8u - (uint32_t)((reinterpret_cast<uintptr_t>(p) >> 1) & 7u)) & 7u;
+    if (h > n) h = n;
+    if ((uint32_t)tid < h) p[tid] = 0;
+    const uint32_t nv = (n - h) >> 3;
+    int4* pv = reinterpret_cast<int4*>(p + h);
+    for (uint32_t v = tid; v < nv; v += ASM_THREADS) pv[v] = make_int4(0, 0, 0, 0);
+    const uint32_t t0 = h + (nv << 3);
+    if (t0 + tid < n) p[t0 + tid] = 0;
+    s.cnt += n;
+    __syncthreads();
+}
 
-    const UttTask task = A.tasks[blockIdx.x];
+__device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
+    const int tid = threadIdx.x;
+    const RegionTask task = A.tasks[ti];
     State s;
-    s.dst = (task.to_pre ? A.dst_pre : A.dst_final) + task.dst_off;
+    s.dst = ((task.flags & TASK_TO_PRE) ? A.dst_pre : A.dst_final) + task.dst_off;
     s.dst_cap = task.dst_cap;
-    s.count = 0;
+    s.cnt = 0;
     s.word_start = 0;
     s.err = 0;
+    s.pred = task.pred;
+    s.have_base = task.pred < 0;
     s.base = 0;
-    if ((unsigned long long)task.first_bound + 8ull <= A.wcap) {
-        s.in_smem = true;
-        s.w = sm.win;
-        s.cap = A.wcap;
-    } else {
+    s.in_smem = true;
+    s.w = sm.win;
+    s.cap = A.wcap;
+    if (task.flags & TASK_GLOBAL) {
+        // the region does not fit the shared window: assemble it in place in the HBM slot
+        need_base(s, sm, A);
         s.in_smem = false;
-        s.w = s.dst;
-        s.cap = s.dst_cap;
+        s.w = s.dst + s.base;
+        s.cap = s.dst_cap > s.base ? s.dst_cap - s.base : 0u;
+        __threadfence();
+        __syncthreads();
     }
-    __syncthreads();
 
     for (uint32_t k = task.op_begin; k < task.op_end && !s.err; k++) {
         ctts_plan_op op;
@@ -905,46 +1162,74 @@ __global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(const AsmArgs 
             *(reinterpret_cast<int4*>(&op) + 1) = hi;
         }
         switch (op.kind) {
+            case OP_NOP:
+                break;
             case CTTS_OP_UNIT:
                 op_unit(s, sm, A, op);
                 break;
-            case CTTS_OP_SILENCE: {  // buffer_append_silence, ctts.c:3361
-                if ((unsigned long long)s.count - s.base + op.a > s.cap) { s.err = ERR_WINDOW_OVERFLOW; break; }
-                int16_t* p = s.w + s.count;
-                for (uint32_t i = tid; i < op.a; i += ASM_THREADS) p[i] = 0;
-                s.count += op.a;
-                __syncthreads();
+            case CTTS_OP_SILENCE:
+                op_silence(s, op.a);
                 break;
-            }
-            case CTTS_OP_FADE_OUT: {  // apply_fade_out on the buffer tail, ctts.c:3028
-                if (s.count > 0 && op.a > 0) {
-                    uint32_t f = op.a < s.count ? op.a : s.count;
-                    int16_t* p = s.w + (s.count - f);
-                    float inv = 1.0f / (float)f;
-                    for (uint32_t i = tid; i < f; i += ASM_THREADS)
-                        p[i] = f2s((float)p[i] * lut_lerp(A.tab.sine, (float)(f - i) * inv));
-                    __syncthreads();
-                }
+            case CTTS_OP_FADE_OUT:
+                op_fade_out(s, sm, A, op.a);
                 break;
-            }
             case CTTS_OP_WORD_END:
-                op_word_end(s, sm, A, task.utt, op);
+                op_word_end(s, sm, A, task.big, op);
                 break;
-            case CTTS_OP_MARK:
-                s.word_start = s.count;
-                region_switch(s, sm, A, op.a);
+            case CTTS_OP_MARK:   // word_start_sample = buf.count, ctts.c:3723, :3765
+                s.word_start = s.cnt;
                 break;
             default:
                 s.err = ERR_BAD_OP;
         }
     }
+
+    // ---- publish: the region's final position is base, known from the predecessor
+    need_base(s, sm, A);
     __syncthreads();
-    if (!s.err && s.in_smem) flush_range(s, s.base, s.count);
+    if (s.in_smem) {
+        if ((unsigned long long)s.base + s.cnt > s.dst_cap) s.err = s.err ? s.err : ERR_SLOT_OVERFLOW;
+        else flush_window(s, sm, 0, s.cnt);
+    }
+    __threadfence();
+    __syncthreads();
     if (tid == 0) {
-        uint32_t cnt = s.err ? 0u : s.count;
-        if (task.to_pre) A.pre_counts[task.utt] = cnt;
-        else A.out_counts[task.utt] = cnt;
-        A.err[task.utt] = s.err;
+        const uint32_t total = s.base + s.cnt;
+        if (s.err) atomicMax(A.err + task.utt, s.err);
+        if (task.flags & TASK_LAST) {
+            if (task.flags & TASK_TO_PRE) A.pre_counts[task.utt] = total;
+            else A.out_counts[task.utt] = total;
+        }
+        st_release_u64(A.chain + ti, ((unsigned long long)A.epoch << 32) | total);
+    }
+}
+
+__global__ void __launch_bounds__(ASM_THREADS, 3) assemble_kernel(const AsmArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem sm;
+    sm.win = reinterpret_cast<int16_t*>(smem_raw);
+    sm.hstage = sm.win + A.wcap + 16;
+    sm.scratch = reinterpret_cast<uint32_t*>(sm.hstage + A.hcap);
+    sm.hann256 = reinterpret_cast<float*>(sm.scratch + A.scr_words);
+    sm.nrm2 = sm.hann256 + PITCH_FRAME;
+    sm.red = reinterpret_cast<unsigned long long*>(sm.nrm2 + PITCH_FRAME / 2);
+    sm.bcast = reinterpret_cast<uint32_t*>(sm.red + 2 * ASM_WARPS);
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < PITCH_FRAME; i += ASM_THREADS) sm.hann256[i] = __ldg(A.tab.hann256 + i);
+    // norm of a sample covered by two frames: (0 + w[i+128]) + w[i], the reference's accumulation order
+    for (int i = tid; i < PITCH_FRAME / 2; i += ASM_THREADS)
+        sm.nrm2[i] = __ldg(A.tab.hann256 + i + PITCH_FRAME / 2) + __ldg(A.tab.hann256 + i);
+    __syncthreads();
+
+    // persistent CTAs: tasks are taken in ticket order (see the header comment)
+    for (;;) {
+        if (tid == 0) sm.bcast[1] = atomicAdd(A.ticket, 1u);
+        __syncthreads();
+        const uint32_t ti = sm.bcast[1];
+        __syncthreads();
+        if (ti >= A.n_tasks) break;
+        run_task(sm, A, ti);
     }
 }
 

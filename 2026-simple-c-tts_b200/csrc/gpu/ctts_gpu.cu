@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -67,7 +68,13 @@ struct ctts_gpu_plan {
     std::vector<uint64_t> offsets;  // n_utts + 1
     std::vector<uint64_t> bounds;
     ctts_plan_op* d_ops = nullptr;
-    ctts::UttTask* d_tasks = nullptr;
+    ctts::RegionTask* d_tasks = nullptr;
+    unsigned long long* d_chain = nullptr;
+    uint32_t* d_ticket = nullptr;
+    uint32_t n_tasks = 0;
+    uint32_t n_global_tasks = 0;
+    uint32_t epoch = 0;
+    uint32_t grid = 0;
     ctts::StretchTask* d_stasks = nullptr;
     uint32_t* d_counts = nullptr;
     uint32_t* d_pre_counts = nullptr;
@@ -85,7 +92,7 @@ struct ctts_gpu_plan {
     int16_t* d_out_last = nullptr;
     std::vector<uint64_t> pre_off;   // per utterance (stretch only), else ~0
     std::vector<uint64_t> pre_cap;
-    uint32_t wcap = 0, ucap = 0, halo = 0, scr_words = 0, smem_bytes = 0;
+    uint32_t wcap = 0, hcap = 0, scr_words = 0, smem_bytes = 0;
     ctts_gpu_run_info info{};
 };
 
@@ -280,6 +287,8 @@ void ctts_gpu_plan_destroy(ctts_gpu_plan* p) {
     }
     cudaFree(p->d_ops);
     cudaFree(p->d_tasks);
+    cudaFree(p->d_chain);
+    cudaFree(p->d_ticket);
     cudaFree(p->d_stasks);
     cudaFree(p->d_counts);
     cudaFree(p->d_pre_counts);
@@ -337,70 +346,121 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
         p->offsets[n] = o;
     }
 
-    // private copy of the ops: MARK.a <- upper bound of the next region
+    // ---- plan compile step 1: private copy of the ops; fade-outs that provably act on zeros
+    // (or on an empty buffer) become no-ops, so that a pause-only region never has to reach
+    // back into its predecessor's samples.  Trailing zeros: appended silence stays zero under
+    // apply_fade_out (0 * g == 0); a unit, or a WORD_END over a region that holds audio
+    // (trimming / the contour may move samples into the tail), resets the count.
     std::vector<ctts_plan_op> ops(plan->ops, plan->ops + plan->n_ops);
-    std::vector<uint32_t> first_bound(n, 0);
-    uint32_t xf_max = 0, fade_max = 0;
-    uint64_t region_max = 0, gather = 0;
+    uint32_t xf_max = 0;
+    uint64_t gather = 0;
     for (uint32_t u = 0; u < n; u++) {
-        uint64_t cur = 0;
-        int last_mark = -1;
+        uint64_t tz = 0, count_ub = 0;
+        bool audio = false;
         for (uint32_t k = plan->utt_op_begin[u]; k < plan->utt_op_begin[u + 1]; k++) {
             ctts_plan_op& op = ops[k];
-            if (op.kind == CTTS_OP_UNIT) {
-                cur += ctx->unit_cnt[op.a];
-                gather += ctx->unit_cnt[op.a];
-                xf_max = std::max(xf_max, op.b);
-            } else if (op.kind == CTTS_OP_SILENCE) {
-                cur += op.a;
-            } else if (op.kind == CTTS_OP_FADE_OUT) {
-                fade_max = std::max(fade_max, op.a);
-            } else if (op.kind == CTTS_OP_MARK) {
-                uint32_t c32 = (uint32_t)std::min<uint64_t>(cur, 0xffffffffull);
-                if (last_mark < 0) first_bound[u] = c32;
-                else ops[last_mark].a = c32;
-                region_max = std::max(region_max, cur);
-                last_mark = (int)k;
-                cur = 0;
+            switch (op.kind) {
+                case CTTS_OP_UNIT:
+                    count_ub += ctx->unit_cnt[op.a];
+                    gather += ctx->unit_cnt[op.a];
+                    if (ctx->unit_cnt[op.a]) { tz = 0; audio = true; }
+                    xf_max = std::max(xf_max, op.b);
+                    break;
+                case CTTS_OP_SILENCE:
+                    tz += op.a;
+                    count_ub += op.a;
+                    break;
+                case CTTS_OP_FADE_OUT:
+                    if (count_ub == 0 || tz >= op.a) op.kind = ctts::OP_NOP;
+                    break;
+                case CTTS_OP_WORD_END:
+                    if (audio) tz = 0;
+                    break;
+                case CTTS_OP_MARK:
+                    audio = false;
+                    break;
             }
         }
-        uint32_t c32 = (uint32_t)std::min<uint64_t>(cur, 0xffffffffull);
-        if (last_mark < 0) first_bound[u] = c32;
-        else ops[last_mark].a = c32;
-        region_max = std::max(region_max, cur);
     }
 
-    // window geometry.  Reach-back of later ops into finished samples:
-    //   pitch analysis  min(2*xf, count/2, n/2)   (ctts.c:1985-1987)
-    //   crossfade / energy match  min(xf, count, n)  (ctts.c:3319-3321, :1736-1738)
-    //   fade-out  min(fade, count)                 (ctts.c:3030)
+    // ---- shared-memory geometry
     const uint32_t max_unit = ctx->max_unit;
-    uint32_t halo = std::max(std::min(2 * xf_max, max_unit / 2), std::min(xf_max, max_unit));
-    halo = (uint32_t)up8(std::max(halo, fade_max));
-    const uint32_t ucap = (uint32_t)up8(std::max<uint32_t>(max_unit, 8));
-    const uint32_t fixed = ucap * 2 + 256 * 4 + 256 * 2 + 2 * (ctts::ASM_THREADS / 32) * 8 + 64;
+    const uint32_t hcap = (uint32_t)up8(std::max<uint32_t>(std::min(xf_max, max_unit), 496)) + 8;
     auto scr_for = [&](uint32_t wcap) {
-        uint32_t a = std::max<uint32_t>(ctts::PITCH_SCRATCH_WORDS, ctts::CONTOUR_SCRATCH_WORDS + 8), b = ucap / 8 + 8,
+        uint32_t a = std::max<uint32_t>(ctts::PITCH_SCRATCH_WORDS, ctts::CONTOUR_SCRATCH_WORDS + 8), b = hcap / 2 + 8,
                  c = 2 * ((wcap + 31) / 32) + 4;
-        return std::max(a, std::max(b, c));
+        return (std::max(a, std::max(b, c)) + 3u) & ~3u;
     };
-    // budget: two CTAs per SM (1 KB per CTA is reserved by the runtime)
-    const uint32_t budget = std::min<uint32_t>((uint32_t)ctx->smem_optin, (uint32_t)(ctx->smem_per_sm / 2 - 1024));
-    uint32_t wcap = (uint32_t)up8(std::min<uint64_t>(region_max + halo + 16, 1u << 20));
-    while (wcap > 1024 && fixed + wcap * 2 + scr_for(wcap) * 4 > budget) wcap -= 256;
+    auto smem_for = [&](uint32_t wcap) {
+        return (wcap + 16) * 2 + hcap * 2 + scr_for(wcap) * 4 + 256 * 4 + 128 * 4 + 2 * ctts::ASM_WARPS * 8 + 16;
+    };
+    // regions (the samples between two word marks) and their upper bounds
+    struct Region { uint32_t op_begin, op_end; uint64_t bound; uint32_t units; };
+    std::vector<std::vector<Region>> regions(n);
+    uint64_t region_max = 0;
+    for (uint32_t u = 0; u < n; u++) {
+        Region r{plan->utt_op_begin[u], plan->utt_op_begin[u], 0, 0};
+        for (uint32_t k = plan->utt_op_begin[u]; k < plan->utt_op_begin[u + 1]; k++) {
+            const ctts_plan_op& op = ops[k];
+            if (op.kind == CTTS_OP_UNIT) { r.bound += ctx->unit_cnt[op.a]; r.units++; }
+            else if (op.kind == CTTS_OP_SILENCE) r.bound += op.a;
+            r.op_end = k + 1;
+            if (op.kind == CTTS_OP_MARK) {
+                regions[u].push_back(r);
+                region_max = std::max(region_max, r.bound);
+                r = Region{k + 1, k + 1, 0, 0};
+            }
+        }
+        if (r.op_end > r.op_begin) {
+            regions[u].push_back(r);
+            region_max = std::max(region_max, r.bound);
+        }
+    }
+    // window: as large as the target occupancy allows, no larger than the largest region needs
+    int want_ctas = 3;
+    if (const char* e = getenv("CTTS_GPU_CTAS_PER_SM")) want_ctas = std::max(1, std::min(8, atoi(e)));
+    const uint32_t budget = std::min<uint32_t>((uint32_t)ctx->smem_optin, (uint32_t)(ctx->smem_per_sm / want_ctas - 1024));
+    uint32_t wcap = (uint32_t)up8(std::min<uint64_t>(region_max + 16, 1u << 20));
+    if (const char* e = getenv("CTTS_GPU_WINDOW")) wcap = (uint32_t)up8(std::max(256, atoi(e)));   // tests: force the HBM path
+    while (wcap > 1024 && smem_for(wcap) > budget) wcap -= 256;
     wcap &= ~7u;
-    if (fixed + wcap * 2 + scr_for(wcap) * 4 > budget) {
+    if (smem_for(wcap) > (uint32_t)ctx->smem_optin) {
         ctts_gpu_plan_destroy(p);
-        return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "voice.db units (max %u samples) do not fit shared memory", max_unit);
+        return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "crossfade / unit sizes (%u, %u samples) do not fit shared memory", xf_max, max_unit);
     }
     p->wcap = wcap;
-    p->ucap = ucap;
-    p->halo = halo;
+    p->hcap = hcap;
     p->scr_words = scr_for(wcap);
-    p->smem_bytes = fixed + wcap * 2 + p->scr_words * 4;
+    p->smem_bytes = smem_for(wcap);
 
-    // tasks, longest first
-    std::vector<ctts::UttTask> tasks(n);
+    // ---- plan compile step 2: region tasks.  A region with no unit (a pause) or a tiny one is
+    // appended to the task before it while the sum still fits the window.
+    struct HostTask { uint32_t utt, op_begin, op_end; uint64_t bound; uint32_t index_in_utt; uint32_t region_max; };
+    std::vector<std::vector<HostTask>> utt_tasks(n);
+    uint32_t max_tasks_per_utt = 0;
+    uint64_t n_tasks = 0;
+    for (uint32_t u = 0; u < n; u++) {
+        auto& T = utt_tasks[u];
+        for (const Region& r : regions[u]) {
+            const bool tiny = r.units == 0 || r.bound <= 2048;
+            if (!T.empty() && tiny && T.back().bound + r.bound <= wcap) {
+                T.back().op_end = r.op_end;
+                T.back().bound += r.bound;
+                T.back().region_max = (uint32_t)std::max<uint64_t>(T.back().region_max, r.bound);
+            } else {
+                T.push_back(HostTask{u, r.op_begin, r.op_end, r.bound, (uint32_t)T.size(),
+                                     (uint32_t)std::min<uint64_t>(r.bound, 0xffffffffull)});
+            }
+        }
+        max_tasks_per_utt = std::max<uint32_t>(max_tasks_per_utt, (uint32_t)T.size());
+        n_tasks += T.size();
+    }
+    if (n_tasks > 0x7fffffffull) {
+        ctts_gpu_plan_destroy(p);
+        return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "too many region tasks");
+    }
+
+    // slots: pre-stretch buffers and WSOLA tasks (utterances longest first)
     std::vector<ctts::StretchTask> stasks;
     std::vector<uint32_t> ola_task, ola_first;
     p->pre_off.assign(n, ~0ull);
@@ -409,24 +469,21 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
     std::vector<uint32_t> order(n);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pre[a] > pre[b]; });
+    std::vector<uint64_t> slot_off(n);
+    std::vector<uint32_t> slot_cap(n), to_pre(n, 0);
     for (uint32_t i = 0; i < n; i++) {
         uint32_t u = order[i];
-        ctts::UttTask& t = tasks[i];
-        t.utt = u;
-        t.op_begin = plan->utt_op_begin[u];
-        t.op_end = plan->utt_op_begin[u + 1];
-        t.first_bound = first_bound[u];
         uint32_t hop = 0;
         if (needs_stretch(plan->speed[u], &hop)) {
             if (pre[u] + 16 > 0xffffffffull) {
                 ctts_gpu_plan_destroy(p);
                 return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "utterance %u too long", u);
             }
-            t.to_pre = 1;
-            t.dst_off = pre_total;
-            t.dst_cap = (uint32_t)(up8(pre[u]) + 8);
+            to_pre[u] = 1;
+            slot_off[u] = pre_total;
+            slot_cap[u] = (uint32_t)(up8(pre[u]) + 8);
             p->pre_off[u] = pre_total;
-            p->pre_cap[u] = t.dst_cap;
+            p->pre_cap[u] = slot_cap[u];
             ctts::StretchTask st;
             st.utt = u;
             st.hop = hop;
@@ -442,23 +499,55 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
                 ola_first.push_back((uint32_t)f);
             }
             stasks.push_back(st);
-            pre_total += t.dst_cap;
+            pre_total += slot_cap[u];
             pos_total += st.max_frames;
             if (pos_total > 0xffffffffull) {
                 ctts_gpu_plan_destroy(p);
                 return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "too many WSOLA frames in one batch");
             }
         } else {
-            t.to_pre = 0;
-            t.dst_off = p->offsets[u];
-            t.dst_cap = (uint32_t)(p->offsets[u + 1] - p->offsets[u]);
+            slot_off[u] = p->offsets[u];
+            slot_cap[u] = (uint32_t)(p->offsets[u + 1] - p->offsets[u]);
         }
     }
     p->n_stretch = (uint32_t)stasks.size();
     p->n_ola_blocks = (uint32_t)ola_task.size();
 
-    // global fallback for the silence bitmask of regions whose mask exceeds the shared scratch
-    if (2 * ((region_max + 31) / 32) + 4 > p->scr_words) p->trim_words = (uint32_t)(2 * ((region_max + 31) / 32) + 8);
+    // ticket order: region-major (task k of every utterance before task k+1 of any), so that a
+    // task's predecessor has normally finished long before the task starts
+    std::vector<ctts::RegionTask> tasks;
+    tasks.reserve(n_tasks);
+    std::vector<int32_t> last_index(n, -1);
+    uint32_t n_big = 0, n_global = 0;
+    const uint64_t scr_samples = (uint64_t)(p->scr_words - 4) / 2 * 32;   // region length the shared trim mask covers
+    uint64_t big_region_max = 0;
+    for (uint32_t k = 0; k < max_tasks_per_utt; k++) {
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t u = order[i];
+            if (k >= utt_tasks[u].size()) continue;
+            const HostTask& h = utt_tasks[u][k];
+            ctts::RegionTask t{};
+            t.utt = u;
+            t.op_begin = h.op_begin;
+            t.op_end = h.op_end;
+            t.bound = (uint32_t)std::min<uint64_t>(h.bound, 0xffffffffull);
+            t.pred = last_index[u];
+            t.flags = (k + 1 == utt_tasks[u].size() ? ctts::TASK_LAST : 0u) | (to_pre[u] ? ctts::TASK_TO_PRE : 0u);
+            if (h.bound > wcap) { t.flags |= ctts::TASK_GLOBAL; n_global++; }
+            t.dst_cap = slot_cap[u];
+            t.dst_off = slot_off[u];
+            t.big = 0xffffffffu;
+            if (h.region_max > scr_samples) {
+                t.big = n_big++;
+                big_region_max = std::max<uint64_t>(big_region_max, h.region_max);
+            }
+            last_index[u] = (int32_t)tasks.size();
+            tasks.push_back(t);
+        }
+    }
+    p->n_tasks = (uint32_t)tasks.size();
+    p->n_global_tasks = n_global;
+    if (n_big) p->trim_words = (uint32_t)(2 * ((big_region_max + 31) / 32) + 8);
 
 #define CUP(call)                                                                               \
     do {                                                                                        \
@@ -483,8 +572,10 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
     CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_counts), std::max<size_t>(n, 1) * 4));
     CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_pre_counts), std::max<size_t>(n, 1) * 4));
     CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_err), std::max<size_t>(n, 1) * 4));
-    CUP(cudaMemsetAsync(p->d_pre_counts, 0, std::max<size_t>(n, 1) * 4, ctx->stream));
-    if (p->trim_words) CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_trim), (size_t)n * p->trim_words * 4));
+    if (p->trim_words) CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_trim), (size_t)n_big * p->trim_words * 4));
+    CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_chain), std::max<size_t>(tasks.size(), 1) * 8));
+    CUP(cudaMemsetAsync(p->d_chain, 0, std::max<size_t>(tasks.size(), 1) * 8, ctx->stream));
+    CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_ticket), 4));
     if (p->n_stretch) {
         CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_pre), pre_total * sizeof(int16_t)));
         CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_frame_pos), std::max<uint64_t>(pos_total, 1) * 4));
@@ -501,8 +592,18 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
     p->info.bound_samples = std::accumulate(bound.begin(), bound.end(), (uint64_t)0);
     p->info.smem_bytes = p->smem_bytes;
     p->info.window_samples = wcap;
-    p->info.halo_samples = halo;
+    p->info.halo_samples = hcap;
     p->info.threads = ctts::ASM_THREADS;
+    {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctts::assemble_kernel, ctts::ASM_THREADS, p->smem_bytes) != cudaSuccess || occ < 1)
+            occ = 1;
+        p->grid = (uint32_t)std::min<uint64_t>((uint64_t)occ * (uint64_t)ctx->sm_count, std::max<uint32_t>(p->n_tasks, 1));
+        p->info.n_tasks = p->n_tasks;
+        p->info.n_global_tasks = p->n_global_tasks;
+        p->info.ctas_per_sm = (uint32_t)occ;
+        p->info.grid = p->grid;
+    }
     *out = p;
     return CTTS_GPU_OK;
 }
@@ -534,34 +635,43 @@ int ctts_gpu_plan_run(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, int16_t* d_pcm_out) {
     if (p->n_utts == 0) return CTTS_GPU_OK;
     cudaStream_t st = ctx->stream;
     CU(ctx, cudaMemsetAsync(p->d_counts, 0, (size_t)p->n_utts * 4, st));
+    CU(ctx, cudaMemsetAsync(p->d_pre_counts, 0, (size_t)p->n_utts * 4, st));
+    CU(ctx, cudaMemsetAsync(p->d_err, 0, (size_t)p->n_utts * 4, st));
+    CU(ctx, cudaMemsetAsync(p->d_ticket, 0, 4, st));
+    p->epoch++;
+    if (p->epoch == 0) p->epoch = 1;   // (2^32 runs later) the chain words of the last lap are long gone
 
-    ctts::AsmArgs a{};
-    a.pool = ctx->d_pool;
-    a.unit_off = ctx->d_unit_off;
-    a.unit_cnt = ctx->d_unit_cnt;
-    a.n_units = ctx->n_units;
-    a.tab.fade_out = ctx->d_tables;
-    a.tab.fade_in = ctx->d_tables + 1024;
-    a.tab.sine = ctx->d_tables + 2048;
-    a.tab.hann256 = ctx->d_tables + 3072;
-    a.tab.hann512 = ctx->d_tables + 3328;
-    a.ops = p->d_ops;
-    a.tasks = p->d_tasks;
-    a.n_tasks = p->n_utts;
-    a.dst_final = d_pcm_out;
-    a.dst_pre = p->d_pre;
-    a.out_counts = p->d_counts;
-    a.pre_counts = p->d_pre_counts;
-    a.err = p->d_err;
-    a.trim_scratch = p->d_trim;
-    a.trim_scratch_words = p->trim_words;
-    a.prm = p->prm;
-    a.wcap = p->wcap;
-    a.ucap = p->ucap;
-    a.halo = p->halo;
-    a.scr_words = p->scr_words;
-    ctts::assemble_kernel<<<p->n_utts, ctts::ASM_THREADS, p->smem_bytes, st>>>(a);
-    CU(ctx, cudaGetLastError());
+    if (p->n_tasks) {
+        ctts::AsmArgs a{};
+        a.pool = ctx->d_pool;
+        a.unit_off = ctx->d_unit_off;
+        a.unit_cnt = ctx->d_unit_cnt;
+        a.n_units = ctx->n_units;
+        a.tab.fade_out = ctx->d_tables;
+        a.tab.fade_in = ctx->d_tables + 1024;
+        a.tab.sine = ctx->d_tables + 2048;
+        a.tab.hann256 = ctx->d_tables + 3072;
+        a.tab.hann512 = ctx->d_tables + 3328;
+        a.ops = p->d_ops;
+        a.tasks = p->d_tasks;
+        a.n_tasks = p->n_tasks;
+        a.dst_final = d_pcm_out;
+        a.dst_pre = p->d_pre;
+        a.out_counts = p->d_counts;
+        a.pre_counts = p->d_pre_counts;
+        a.err = p->d_err;
+        a.trim_scratch = p->d_trim;
+        a.trim_scratch_words = p->trim_words;
+        a.chain = p->d_chain;
+        a.ticket = p->d_ticket;
+        a.epoch = p->epoch;
+        a.prm = p->prm;
+        a.wcap = p->wcap;
+        a.hcap = p->hcap;
+        a.scr_words = p->scr_words;
+        ctts::assemble_kernel<<<p->grid, ctts::ASM_THREADS, p->smem_bytes, st>>>(a);
+        CU(ctx, cudaGetLastError());
+    }
 
     if (p->n_stretch) {
         ctts::WsolaArgs w{};

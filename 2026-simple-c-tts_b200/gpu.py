@@ -22,6 +22,8 @@ class RunInfo(C.Structure):
         ("gather_samples", C.c_uint64), ("bound_samples", C.c_uint64),
         ("smem_bytes", C.c_uint32), ("window_samples", C.c_uint32),
         ("halo_samples", C.c_uint32), ("threads", C.c_uint32),
+        ("n_tasks", C.c_uint32), ("n_global_tasks", C.c_uint32),
+        ("ctas_per_sm", C.c_uint32), ("grid", C.c_uint32),
     ]
 
 

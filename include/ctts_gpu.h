@@ -67,7 +67,7 @@ int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan,
 
 /* ---- resident-plan path: upload once, run many times, PCM stays in HBM ---- */
 
-/* Uploads the plan, derives the per-utterance tasks and output layout
+/* Uploads the plan, derives the region tasks and output layout
  * (slots sized by the bounds, 16-byte aligned) and allocates workspace.
  * `out_offsets` may be NULL (packed slots chosen by the library). */
 int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan,
@@ -97,8 +97,12 @@ typedef struct ctts_gpu_run_info {
     uint64_t bound_samples;      /* sum of output upper bounds */
     uint32_t smem_bytes;         /* dynamic shared memory of the assembly kernel */
     uint32_t window_samples;     /* shared-memory window capacity per CTA */
-    uint32_t halo_samples;
+    uint32_t halo_samples;       /* unit-head staging capacity per CTA */
     uint32_t threads;
+    uint32_t n_tasks;            /* region tasks of the assembly kernel */
+    uint32_t n_global_tasks;     /* of those: regions larger than the window, assembled in the HBM slot */
+    uint32_t ctas_per_sm;        /* resident CTAs per SM of the assembly kernel */
+    uint32_t grid;               /* persistent CTAs launched */
 } ctts_gpu_run_info;
 int ctts_gpu_plan_info(const ctts_gpu_plan* plan, ctts_gpu_run_info* info);
 

@@ -176,7 +176,7 @@ def test_resident_plan_is_idempotent(H, synth_small, oracle_small, front_small):
         want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(plan.speed[u]))
         _assert_same(b[u], want, f"resident utt {u}")
     info = rp.info()
-    assert info.kernel_launches == 3 and info.n_stretch == 4 and info.threads == 512
+    assert info.kernel_launches == 3 and info.n_stretch == 4 and info.threads == 256
     # pre-stretch buffer of a stretched utterance equals the oracle's
     _, _, pre = oracle_small.synth(prm, plan.utt_ops(9), 1.2, want_pre=True)
     _assert_same(rp.read_pre(9, len(pre) + 16), pre, "pre-stretch")

@@ -1,0 +1,322 @@
+// asm_pitch.cuh -- pitch smoothing at joins (ctts.c:1899-2024).
+#pragma once
+#include "asm_common.cuh"
+
+namespace ctts {
+
+// ---------------------------------------------------------------- pitch
+
+// estimate_pitch (ctts.c:1899) for two signals of the same length at once (the
+// buffer tail `a` and the unit head `b`).
+//
+// The reference evaluates, for each lag in 55..275, three sequential float sums
+// over i < 220: corr += s[i]*s[i+lag], e1 += s[i]^2, e2 += s[i+lag]^2, and keeps
+// the first lag whose corr/sqrtf(e1*e2) is the strict maximum (voiced iff > 0.3).
+// Those sums cannot be reordered, and at 3 non-fused FP32 operations per
+// (lag, i) pair they are 40 % of all instructions of the assembly path.  So
+// the search is done in two steps that together give the identical result:
+//
+//  1. FILTER: every lag gets an approximate score a[lag] = c~ / sqrtf(e1x * e2x),
+//     c~ accumulated with FMA (one instruction per pair, four lags per thread
+//     sharing the operand loads) and e1x, e2x EXACT integer window sums taken
+//     from a 64-bit prefix sum of the squares.  For 220 terms |a - r| <= 4.2e-5
+//     where r is the reference's score (standard summation error bound,
+//     n*u*sum|x_i*y_i| <= n*u*sqrt(e1*e2) by Cauchy-Schwarz; DESIGN.md derives it).
+//  2. EXACT: with eps = 1e-3 (24 x the bound), a signal is unvoiced if
+//     max a <= 0.3 - eps; otherwise only lags with a >= max a - 2*eps can be the
+//     reference's arg max, and those (typically 1-3) are evaluated by one thread
+//     each with the reference's exact operation order.
+//
+// Both signals are needed voiced by the caller, so step 2 is skipped entirely
+// when either signal fails the filter.
+constexpr int PITCH_LO = CTTS_PLAN_SAMPLE_RATE / 400;  // 55
+constexpr int PITCH_HI = CTTS_PLAN_SAMPLE_RATE / 80;   // 275
+constexpr int PITCH_LEN = CTTS_PLAN_SAMPLE_RATE / 100; // 220
+constexpr int PITCH_LAG0 = 53;        // lag of thread 0 (= 1 mod 4 keeps both float4 loads aligned)
+constexpr int PITCH_LPT = 4;          // lags per thread
+constexpr int PITCH_TPS = 64;         // threads per signal (57 used)
+constexpr int PITCH_Y = 512;          // staged floats per signal (zero padded)
+constexpr int PITCH_S = 504;          // prefix entries per signal
+constexpr int PITCH_MAX_CAND = 64;    // per signal, beyond that: every lag is evaluated exactly
+constexpr float PITCH_EPS = 1e-3f;
+constexpr int PITCH_SCRATCH_WORDS = 2 * PITCH_Y + 2 * 2 * PITCH_S + 4 + 2 * (PITCH_MAX_CAND + 2) + 16;
+static_assert(PITCH_LAG0 % 4 == 1 && PITCH_LAG0 <= PITCH_LO, "lag tiling");
+static_assert(PITCH_LAG0 + PITCH_LPT * 57 > PITCH_HI, "57 threads cover every lag");
+static_assert(PITCH_HI + PITCH_LPT + PITCH_LEN + 8 <= PITCH_Y, "staging covers the loop's reads");
+static_assert(PITCH_HI + PITCH_LEN < PITCH_S, "prefix covers every window");
+
+// exact score of one lag in the reference's order (ctts.c:1917-1931); lag 0 yields e1 in *e2_out
+__device__ __forceinline__ float pitch_exact_sums(const float* y, uint32_t lag, uint32_t len, float* e2_out) {
+    float c = 0.0f, e2 = 0.0f;
+    const float* x = y;
+    const float* z = y + lag;
+#pragma unroll 4
+    for (uint32_t i = 0; i < len; i++) {
+        const float a = x[i], b = z[i];
+        c += a * b;
+        e2 += b * b;
+    }
+    *e2_out = e2;
+    return c;
+}
+
+__device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int16_t* b, uint32_t n,
+                                    float* pa, float* pb) {
+    *pa = 0.0f;
+    *pb = 0.0f;
+    if (n < 200) return;
+    const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    const uint32_t lo = PITCH_LO;
+    uint32_t hi = PITCH_HI;
+    if (hi > n / 2) hi = n / 2;
+    uint32_t len = PITCH_LEN;
+    if (len > n - hi) len = n - hi;
+    const uint32_t need = len + hi;  // <= 495 samples of each signal are ever read
+
+    float* ya = reinterpret_cast<float*>(sm.scratch);
+    float* yb = ya + PITCH_Y;
+    unsigned long long* Sa = reinterpret_cast<unsigned long long*>(yb + PITCH_Y);  // 8-byte aligned: 2*PITCH_Y even
+    unsigned long long* Sb = Sa + PITCH_S;
+    unsigned long long* keys = Sb + PITCH_S;                      // [2]
+    uint32_t* cand = reinterpret_cast<uint32_t*>(keys + 2);       // [2][PITCH_MAX_CAND + 2]
+    uint32_t* ncand = cand + 2 * (PITCH_MAX_CAND + 2);            // [2]
+    float* amax = reinterpret_cast<float*>(ncand + 2);            // [4] per lag warp
+    float* e1s = amax + 4;                                        // [2]
+
+    for (uint32_t i = tid; i < PITCH_Y; i += ASM_THREADS) {
+        const bool in = i < need;
+        ya[i] = in ? (float)a[i] : 0.0f;
+        yb[i] = in ? (float)b[i] : 0.0f;
+    }
+    if (tid < 2) {
+        ncand[tid] = 0;
+        keys[tid] = 0ull;
+    }
+    __syncthreads();
+
+    // ---- step 1: FMA scores on warps 0-3, exact prefix sums of squares on warps 4-5
+    float c[PITCH_LPT] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const int sig = (tid >> 6) & 1;
+    const uint32_t lag0 = PITCH_LAG0 + PITCH_LPT * (uint32_t)(tid & (PITCH_TPS - 1));
+    const bool lag_thread = tid < 2 * PITCH_TPS && lag0 <= hi;
+    if (lag_thread) {
+        const float* x = sig ? yb : ya;
+        const float* y = x + lag0;  // y[j] = s[lag0 + j]; (lag0 + 3) % 4 == 0
+        float w0 = y[0], w1 = y[1], w2 = y[2];
+        const uint32_t len4 = len & ~3u;
+        for (uint32_t i = 0; i < len4; i += 4) {
+            const float4 xv = *reinterpret_cast<const float4*>(x + i);
+            const float4 yn = *reinterpret_cast<const float4*>(y + i + 3);
+            const float w3 = yn.x, w4 = yn.y, w5 = yn.z, w6 = yn.w;
+            c[0] = __fmaf_rn(xv.x, w0, c[0]); c[1] = __fmaf_rn(xv.x, w1, c[1]);
+            c[2] = __fmaf_rn(xv.x, w2, c[2]); c[3] = __fmaf_rn(xv.x, w3, c[3]);
+            c[0] = __fmaf_rn(xv.y, w1, c[0]); c[1] = __fmaf_rn(xv.y, w2, c[1]);
+            c[2] = __fmaf_rn(xv.y, w3, c[2]); c[3] = __fmaf_rn(xv.y, w4, c[3]);
+            c[0] = __fmaf_rn(xv.z, w2, c[0]); c[1] = __fmaf_rn(xv.z, w3, c[1]);
+            c[2] = __fmaf_rn(xv.z, w4, c[2]); c[3] = __fmaf_rn(xv.z, w5, c[3]);
+            c[0] = __fmaf_rn(xv.w, w3, c[0]); c[1] = __fmaf_rn(xv.w, w4, c[1]);
+            c[2] = __fmaf_rn(xv.w, w5, c[2]); c[3] = __fmaf_rn(xv.w, w6, c[3]);
+            w0 = w4; w1 = w5; w2 = w6;
+        }
+        for (uint32_t i = len4; i < len; i++) {
+            const float xs = x[i];
+#pragma unroll
+            for (int k = 0; k < PITCH_LPT; k++) c[k] = __fmaf_rn(xs, y[i + k], c[k]);
+        }
+    } else if (warp == 4 || warp == 5) {
+        // S[i] = sum_{j<i} s[j]^2, exact (values are int16, 504 * 2^30 < 2^64)
+        const float* y = warp == 5 ? yb : ya;
+        unsigned long long* S = warp == 5 ? Sb : Sa;
+        constexpr int PER = 16;  // 32 lanes * 16 = 512 >= PITCH_S
+        unsigned long long loc = 0;
+        const int i0 = lane * PER;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int v = (int)y[i0 + k];
+            loc += (unsigned long long)(uint32_t)(v * v);
+        }
+        unsigned long long inc = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        unsigned long long run = inc - loc;  // exclusive
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            if (i0 + k < PITCH_S) S[i0 + k] = run;
+            const int v = (int)y[i0 + k];
+            run += (unsigned long long)(uint32_t)(v * v);
+        }
+    }
+    __syncthreads();
+
+    // ---- scores and per-signal maximum
+    float sc[PITCH_LPT];
+    float my_max = -1.0f;
+    if (lag_thread) {
+        const unsigned long long* S = sig ? Sb : Sa;
+        const float e1 = (float)(S[len] - S[0]);
+#pragma unroll
+        for (int k = 0; k < PITCH_LPT; k++) {
+            const uint32_t lag = lag0 + k;
+            sc[k] = -1.0f;
+            if (lag >= lo && lag <= hi) {
+                const float e2 = (float)(S[lag + len] - S[lag]);
+                const float nrm = sqrtf(e1 * e2);
+                sc[k] = nrm > 0.0f ? c[k] / nrm : 0.0f;
+                my_max = fmaxf(my_max, sc[k]);
+            }
+        }
+    }
+    if (tid < 2 * PITCH_TPS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_max = fmaxf(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
+        if (lane == 0) amax[warp] = my_max;
+    }
+    __syncthreads();
+    const float max_a = fmaxf(amax[0], amax[1]), max_b = fmaxf(amax[2], amax[3]);
+    // unvoiced by the filter: the reference's best cannot exceed 0.3
+    if (!(max_a > 0.3f - PITCH_EPS) || !(max_b > 0.3f - PITCH_EPS)) {   // CTA-uniform
+        __syncthreads();   // scratch is reused by the caller
+        return;
+    }
+
+    // ---- candidates
+    if (lag_thread) {
+        const float thr = (sig ? max_b : max_a) - 2.0f * PITCH_EPS;
+#pragma unroll
+        for (int k = 0; k < PITCH_LPT; k++) {
+            if (sc[k] >= thr) {
+                uint32_t slot = atomicAdd(ncand + sig, 1u);
+                if (slot < PITCH_MAX_CAND) cand[sig * (PITCH_MAX_CAND + 2) + slot] = lag0 + k;
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t na = ncand[0], nb = ncand[1];
+    const bool all_a = na > PITCH_MAX_CAND, all_b = nb > PITCH_MAX_CAND;  // degenerate: evaluate every lag
+    if (all_a) na = hi - lo + 1;
+    if (all_b) nb = hi - lo + 1;
+    __syncthreads();
+
+    // ---- step 2: exact evaluation, one thread per (signal, lag); job 0 of each signal is lag 0 (= e1)
+    const uint32_t jobs = na + nb + 2;
+    for (uint32_t j = tid; j < jobs; j += ASM_THREADS) {
+        const int sg = j < na + 1 ? 0 : 1;
+        const uint32_t jj = sg ? j - (na + 1) : j;
+        if (jj == 0) {
+            float e1;
+            (void)pitch_exact_sums(sg ? yb : ya, 0, len, &e1);
+            e1s[sg] = e1;
+        } else {
+            const bool all = sg ? all_b : all_a;
+            const uint32_t lag = all ? lo + (jj - 1) : cand[sg * (PITCH_MAX_CAND + 2) + (jj - 1)];
+            float e2;
+            const float cc = pitch_exact_sums(sg ? yb : ya, lag, len, &e2);
+            // park the raw sums; the score needs e1, which another thread is computing
+            reinterpret_cast<float2*>(sg ? Sb : Sa)[jj] = make_float2(cc, e2);   // S is dead from here on
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = tid; j < jobs; j += ASM_THREADS) {
+        const int sg = j < na + 1 ? 0 : 1;
+        const uint32_t jj = sg ? j - (na + 1) : j;
+        if (jj == 0) continue;
+        const bool all = sg ? all_b : all_a;
+        const uint32_t lag = all ? lo + (jj - 1) : cand[sg * (PITCH_MAX_CAND + 2) + (jj - 1)];
+        const float2 ce = reinterpret_cast<const float2*>(sg ? Sb : Sa)[jj];
+        float v = ce.x;
+        const float nrm = sqrtf(e1s[sg] * ce.y);
+        if (nrm > 0) v /= nrm;
+        // the reference keeps the first lag that is strictly greater than everything before it,
+        // starting from 0: the maximum positive score, smallest lag on ties
+        if (v > 0.0f) atomicMax(keys + sg, ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - lag));
+    }
+    __syncthreads();
+    const unsigned long long ka = keys[0], kb = keys[1];
+    {
+        const float v = __uint_as_float((uint32_t)(ka >> 32));
+        const uint32_t l = 0xffffffffu - (uint32_t)(ka & 0xffffffffu);
+        if (ka != 0ull && v > 0.3f && l > 0) *pa = (float)CTTS_PLAN_SAMPLE_RATE / (float)l;
+    }
+    {
+        const float v = __uint_as_float((uint32_t)(kb >> 32));
+        const uint32_t l = 0xffffffffu - (uint32_t)(kb & 0xffffffffu);
+        if (kb != 0ull && v > 0.3f && l > 0) *pb = (float)CTTS_PLAN_SAMPLE_RATE / (float)l;
+    }
+    __syncthreads();   // scratch is reused by the caller
+}
+
+// smooth_pitch_boundary + apply_pitch_shift, ctts.c:1946-2024.  `reg` is the analysis length
+// min(2*xf, count/2, n/2) resolved by the caller (0 = the reference returns early); `us` is the
+// staged unit head.
+__device__ void smooth_pitch(const State& s, const Smem& sm, int16_t* us, uint32_t n, uint32_t xf, uint32_t reg) {
+    if (reg == 0) return;
+    const int tid = threadIdx.x;
+    float pp, np;
+    estimate_pitch_pair(sm, s.w + ((int)s.cnt - (int)reg), us, reg, &pp, &np);
+    if (!(pp > 0 && np > 0)) return;
+    float ratio = np / pp;
+    if (!(ratio > 1.15f || ratio < 0.85f)) return;
+    float target = (ratio > 1.0f) ? 1.0f + (ratio - 1.0f) * 0.5f : 1.0f - (1.0f - ratio) * 0.5f;
+    float shift = target / ratio;
+    uint32_t len = xf;
+    if (len > n / 4) len = n / 4;
+    int16_t* tmp = reinterpret_cast<int16_t*>(sm.scratch);  // len <= hcap <= 2 * scr_words
+    bool do_shift = !(shift < 0.9f || shift > 1.1f || len < 100);
+    uint32_t keep = len;
+    if (do_shift) {
+        uint32_t m = (uint32_t)(unsigned long long)((float)len / shift);
+        keep = m < len ? m : len;
+    }
+    for (uint32_t i = tid; i < len; i += ASM_THREADS) {
+        int16_t r = 0;
+        if (!do_shift) {
+            r = us[i];
+        } else if (i < keep) {
+            float x = (float)i * shift;
+            uint32_t k = (uint32_t)(unsigned long long)x;
+            float fr = x - (float)k;
+            if (k + 1 < len) r = f2s((float)us[k] * (1.0f - fr) + (float)us[k + 1] * fr);
+            else if (k < len) r = us[k];
+        }
+        tmp[i] = r;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < len; i += ASM_THREADS) {
+        float t = (float)i / (float)len;
+        us[i] = f2s((float)tmp[i] * (1.0f - t) + (float)us[i] * t);
+    }
+    __syncthreads();
+}
+
+// match_boundary_energy, ctts.c:1730 (sums of squares are exact integers); len = min(xf, count, n)
+__device__ void match_energy(const State& s, const Smem& sm, int16_t* us, uint32_t len) {
+    if (len == 0) return;
+    const int tid = threadIdx.x;
+    const int16_t* tail = s.w + ((int)s.cnt - (int)len);
+    long long sp = 0, sn = 0;
+    for (uint32_t i = tid; i < len; i += ASM_THREADS) {
+        int p = tail[i], q = us[i];
+        sp += (long long)p * p;
+        sn += (long long)q * q;
+    }
+    block_allreduce_add2<ASM_THREADS>(sp, sn, reinterpret_cast<long long*>(sm.red));
+    float pr = (float)sqrt((double)sp / (double)len);
+    float nr = (float)sqrt((double)sn / (double)len);
+    if (pr < 1.0f || nr < 1.0f) return;
+    float ratio = pr / nr;
+    if (ratio > 2.0f) ratio = 2.0f;
+    if (ratio < 0.5f) ratio = 0.5f;
+    const float flen = (float)len;
+    for (uint32_t i = tid; i < len; i += ASM_THREADS) {
+        float t = (float)i / flen;
+        float g = ratio * (1.0f - t) + 1.0f * t;
+        us[i] = f2s(clamp16f((float)us[i] * g));
+    }
+    __syncthreads();
+}
+
+
+}  // namespace ctts

@@ -1,0 +1,252 @@
+// asm_unit.cuh -- the UNIT op: gather, normalize_rms, join, buffer_append_crossfade.
+#pragma once
+#include "asm_common.cuh"
+#include "asm_pitch.cuh"
+
+namespace ctts {
+
+// ---------------------------------------------------------------- unit op
+
+// the two crossfade gains at t share the table position (fast_fade_out / fast_fade_in, ctts.c:76-92)
+__device__ __forceinline__ void crossfade_gains(const DevTables& tab, float t, float* pg, float* ng) {
+    float x = t * (float)(LUT_N - 1);
+    int k = (int)x;
+    if (k >= LUT_N - 1) {
+        *pg = __ldg(tab.fade_out + LUT_N - 1);
+        *ng = __ldg(tab.fade_in + LUT_N - 1);
+    } else if (k < 0) {
+        *pg = __ldg(tab.fade_out);
+        *ng = __ldg(tab.fade_in);
+    } else {
+        float fr = x - (float)k, om = 1.0f - fr;
+        *pg = __ldg(tab.fade_out + k) * om + __ldg(tab.fade_out + k + 1) * fr;
+        *ng = __ldg(tab.fade_in + k) * om + __ldg(tab.fade_in + k + 1) * fr;
+    }
+}
+
+__device__ __forceinline__ int sub_dc(int v, int dc) {
+    // clamp(v - dc) to int16 (remove_dc_offset, ctts.c:1577-1581)
+    return max(__viaddmin_s32(v, -dc, 32767), -32768);
+}
+
+// normalize_rms's per-sample step (ctts.c:1720-1725): (int16)clamp(x * g), truncating
+__device__ __forceinline__ uint32_t scale2(uint32_t w, float g) {
+    const int y0 = cvt_sat_s16((float)(short)(w & 0xffffu) * g);
+    const int y1 = cvt_sat_s16((float)(short)(w >> 16) * g);
+    return (uint32_t)(y0 & 0xffff) | ((uint32_t)y1 << 16);
+}
+__device__ __forceinline__ int4 scale8(const int4& q, float g) {
+    int4 r;
+    r.x = (int)scale2((uint32_t)q.x, g);
+    r.y = (int)scale2((uint32_t)q.y, g);
+    r.z = (int)scale2((uint32_t)q.z, g);
+    r.w = (int)scale2((uint32_t)q.w, g);
+    return r;
+}
+__device__ __forceinline__ int sum8_s16(const int4& q, int c) {
+    c = sum2_s16((uint32_t)q.x, c);
+    c = sum2_s16((uint32_t)q.y, c);
+    c = sum2_s16((uint32_t)q.z, c);
+    return sum2_s16((uint32_t)q.w, c);
+}
+
+// remove_dc_offset's per-sample step (ctts.c:1577-1581) on two samples: clamp(v - dc).
+// v is first clamped to [lo, hi] = the values whose difference cannot leave the int16 range,
+// then a wrapping packed subtract is exact.
+struct DcPack { uint32_t lo2, hi2, neg2; };
+__device__ __forceinline__ DcPack dc_pack(int dc) {
+    const int lo = dc > 0 ? -32768 + dc : -32768;
+    const int hi = dc < 0 ? 32767 + dc : 32767;
+    DcPack d;
+    d.lo2 = (uint32_t)(lo & 0xffff) * 0x10001u;
+    d.hi2 = (uint32_t)(hi & 0xffff) * 0x10001u;
+    d.neg2 = (uint32_t)((-dc) & 0xffff) * 0x10001u;
+    return d;
+}
+__device__ __forceinline__ uint32_t sub_dc2(uint32_t w, const DcPack& d) {
+    return __vadd2(__vmins2(__vmaxs2(w, d.lo2), d.hi2), d.neg2);
+}
+
+// ctts.c:3785-3846: gather -> normalize_rms -> [smooth, match] -> buffer_append_crossfade.
+//
+// The unit's first `hs` samples (everything the join may rewrite, and what the pitch analysis
+// reads) are staged in `hstage`; the rest is written straight to its final place in the window,
+// on the window's own 16-byte grid (the pool side is re-aligned with a funnel shift), and
+// revisited once in place to subtract the DC offset -- which is only known after the head has
+// been smoothed and energy matched.
+__device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_plan_op& op) {
+    const int tid = threadIdx.x;
+    if (op.a >= A.n_units) { s.err = ERR_BAD_OP; return; }
+    const uint32_t n = __ldg(A.unit_cnt + op.a);
+    if (n == 0) return;
+    const int16_t* src = A.pool + __ldg(A.unit_off + op.a);
+    const int4* srcv = reinterpret_cast<const int4*>(src);
+    const uint32_t nvec = (n + 7) >> 3;
+    int16_t* us = sm.hstage;
+    const uint32_t xf = op.b;
+    const bool boundary = (op.flags & CTTS_UNIT_AFTER_BOUNDARY) != 0;
+    const bool remove_dc = A.prm.remove_dc_offset != 0;
+
+    // ---- decisions that depend on buf.count = base + cnt; the base is only waited for when
+    //      the samples of this task alone cannot settle them
+    bool join = false;
+    if (!boundary) {
+        if (s.cnt == 0) need_base(s, sm, A);
+        join = s.cnt > 0 || s.base > 0;
+    }
+    // !join <=> count == 0 || after_word_boundary: the unit starts fresh (fade-in, no crossfade)
+    uint32_t a = 0;             // crossfade = energy-match length min(xf, count, n), ctts.c:3319, :1736
+    uint32_t reg = 0;           // pitch analysis length, ctts.c:1983-1987
+    if (join && xf > 0) {
+        const uint32_t m = xf < n ? xf : n;
+        if (s.cnt >= m) a = m;
+        else {
+            need_base(s, sm, A);
+            const unsigned long long count = (unsigned long long)s.base + s.cnt;
+            a = count < m ? (uint32_t)count : m;
+        }
+        if (n >= 200) {
+            const uint32_t m2 = 2 * xf < n / 2 ? 2 * xf : n / 2;
+            if (s.cnt >= 200 && s.cnt / 2 >= m2) reg = m2;
+            else {
+                need_base(s, sm, A);
+                const unsigned long long count = (unsigned long long)s.base + s.cnt;
+                if (count >= 200) reg = count / 2 < m2 ? (uint32_t)(count / 2) : m2;
+            }
+        }
+        // a window that reaches back past the start of this task: continue on the HBM slot
+        if ((a > s.cnt || reg > s.cnt) && s.in_smem) enter_global(s, sm, A);
+    }
+    if ((unsigned long long)s.cnt + (n - a) > s.cap) { s.err = ERR_WINDOW_OVERFLOW; return; }
+
+    // staged head: what smooth/match may rewrite (min(xf, n)) and what the pitch analysis reads (<= 495)
+    uint32_t hs = 0;
+    if (join) {
+        uint32_t want = xf < n ? xf : n;
+        if (reg > 0 && want < 496) want = 496;
+        hs = (want + 7) & ~7u;
+        if (hs > (nvec << 3)) hs = nvec << 3;
+        if (hs > A.hcap) { s.err = ERR_UNIT_TOO_LONG; return; }
+    }
+    const uint32_t hsn = hs < n ? hs : n;   // staged samples that exist
+
+    // ---- pass 1: sum of squares (normalize_rms, ctts.c:1709; double sum of integers == integer sum)
+    long long ss = 0;
+    for (uint32_t v = tid; v < nvec; v += ASM_THREADS) ss += sumsq8(__ldg(srcv + v));
+    ss = block_allreduce<ASM_THREADS>(ss, OpAddI64(), reinterpret_cast<long long*>(sm.red));
+    bool scale = false;
+    float g = 1.0f;
+    if (A.prm.target_rms > 0) {
+        float rms = (float)sqrt((double)ss / (double)n);
+        if (!(rms < 1.0f)) {
+            g = A.prm.target_rms / rms;
+            if (g > 3.0f) g = 3.0f;
+            if (g < 0.1f) g = 0.1f;
+            scale = true;
+        }
+    }
+
+    // ---- pass 2: scale; head -> hstage, body -> window (aligned vectors of the window)
+    for (uint32_t v = tid; v < (hs >> 3); v += ASM_THREADS) {
+        int4 q = __ldg(srcv + v);
+        if (scale) q = scale8(q, g);
+        *(reinterpret_cast<int4*>(us) + v) = q;
+    }
+    // unit sample i lands at tail[i]; the body is [hs, n)
+    int16_t* tail = s.w + ((int)s.cnt - (int)a);
+    const uint32_t phase = (uint32_t)((reinterpret_cast<uintptr_t>(tail + hs) >> 1) & 7u);
+    int16_t* grid = tail + hs - phase;                       // 16-byte aligned
+    const uint32_t body = n - hsn;                            // may be 0
+    const uint32_t gvec = body ? (phase + body + 7) >> 3 : 0; // window vectors that hold body samples
+    const uint32_t pv0 = hs >> 3;                             // pool vector of unit sample hs
+    int dsum = 0;
+    for (uint32_t j = tid; j < gvec; j += ASM_THREADS) {
+        // window vector j holds unit samples i0 .. i0+7, i0 = hs - phase + 8j
+        int4 q;
+        if (phase == 0) {
+            q = __ldg(srcv + pv0 + j);
+        } else {
+            int4 lo = make_int4(0, 0, 0, 0), hi = make_int4(0, 0, 0, 0);
+            if (pv0 + j >= 1) lo = __ldg(srcv + pv0 + j - 1);
+            if (pv0 + j < nvec) hi = __ldg(srcv + pv0 + j);
+            q = shift_pick(lo, hi, 8u - phase);
+        }
+        if (scale) q = scale8(q, g);
+        const int i0 = (int)hs - (int)phase + 8 * (int)j;
+        if (i0 >= (int)hs && i0 + 8 <= (int)n) {
+            dsum = sum8_s16(q, dsum);
+            *(reinterpret_cast<int4*>(grid) + j) = q;
+        } else {   // the (at most two) partial vectors at the ends of the body
+            const int16_t* e = reinterpret_cast<const int16_t*>(&q);
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (i0 + k >= (int)hs && i0 + k < (int)n) {
+                    dsum += (int)e[k];
+                    grid[8 * j + k] = e[k];
+                }
+        }
+    }
+    __syncthreads();
+
+    if (join) {
+        smooth_pitch(s, sm, us, n, xf, reg);
+        match_energy(s, sm, us, a);
+    }
+
+    // ---- remove_dc_offset (ctts.c:1568) inside buffer_append_crossfade (ctts.c:3279)
+    int dc = 0;
+    if (remove_dc) {
+        for (uint32_t i = tid; i < hsn; i += ASM_THREADS) dsum += us[i];
+        long long sum = block_allreduce<ASM_THREADS>((long long)dsum, OpAddI64(), reinterpret_cast<long long*>(sm.red));
+        dc = (int)(int16_t)(sum / (long long)n);
+    }
+    // body in place
+    if (dc != 0) {
+        const DcPack dp = dc_pack(dc);
+        for (uint32_t j = tid; j < gvec; j += ASM_THREADS) {
+            const int i0 = (int)hs - (int)phase + 8 * (int)j;
+            if (i0 >= (int)hs && i0 + 8 <= (int)n) {
+                int4 q = *(reinterpret_cast<int4*>(grid) + j);
+                q.x = (int)sub_dc2((uint32_t)q.x, dp);
+                q.y = (int)sub_dc2((uint32_t)q.y, dp);
+                q.z = (int)sub_dc2((uint32_t)q.z, dp);
+                q.w = (int)sub_dc2((uint32_t)q.w, dp);
+                *(reinterpret_cast<int4*>(grid) + j) = q;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (i0 + k >= (int)hs && i0 + k < (int)n) grid[8 * j + k] = (int16_t)sub_dc((int)grid[8 * j + k], dc);
+            }
+        }
+    }
+    if (join) {
+        // staged head: crossfade mix (ctts.c:3328-3344) over [0, a), plain copy over [a, hsn)
+        const float inv = a ? 1.0f / (float)a : 0.0f;
+        for (uint32_t i = tid; i < hsn; i += ASM_THREADS) {
+            int v = us[i];
+            if (remove_dc) v = sub_dc(v, dc);
+            if (i < a) {
+                float pg, ng;
+                crossfade_gains(A.tab, (float)i * inv, &pg, &ng);
+                int p = tail[i];
+                int mix = (int)((float)p * pg + (float)v * ng);
+                v = max(min(mix, 32767), -32768);
+            }
+            tail[i] = (int16_t)v;
+        }
+    } else {
+        // fade-in of a word-initial unit (apply_fade_in, ctts.c:3015), after the DC removal
+        const uint32_t pre = A.prm.fade_in_samples < n ? A.prm.fade_in_samples : n;
+        if (pre) {
+            __syncthreads();
+            const float inv = 1.0f / (float)pre;
+            for (uint32_t i = tid; i < pre; i += ASM_THREADS)
+                tail[i] = f2s((float)tail[i] * lut_lerp(A.tab.sine, (float)i * inv));
+        }
+    }
+    s.cnt += n - a;
+    __syncthreads();
+}
+
+
+}  // namespace ctts

@@ -354,6 +354,7 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
     std::vector<ctts_plan_op> ops(plan->ops, plan->ops + plan->n_ops);
     uint32_t xf_max = 0;
     uint64_t gather = 0;
+    bool bad_factor = false;
     for (uint32_t u = 0; u < n; u++) {
         uint64_t tz = 0, count_ub = 0;
         bool audio = false;
@@ -375,12 +376,23 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
                     break;
                 case CTTS_OP_WORD_END:
                     if (audio) tz = 0;
+                    if (op.flags & CTTS_WE_INTON) {
+                        // the contour kernel stages CONTOUR_AHEAD samples past a tile: factors come from
+                        // clamp_pitch(1 +- max_pitch_change) (ctts.c:2589), 0.9 .. 1.1 as shipped
+                        const float lo = std::min(op.f0, std::min(op.f1, op.f2)), hi = std::max(op.f0, std::max(op.f1, op.f2));
+                        if (!(lo >= 0.0f) || !(hi <= 2.05f)) bad_factor = true;
+                    }
                     break;
                 case CTTS_OP_MARK:
                     audio = false;
                     break;
             }
         }
+    }
+
+    if (bad_factor) {
+        ctts_gpu_plan_destroy(p);
+        return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "WORD_END pitch factors must lie in [0, 2.05]");
     }
 
     // ---- shared-memory geometry

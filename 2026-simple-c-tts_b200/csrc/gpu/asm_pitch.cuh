@@ -41,6 +41,7 @@ constexpr int PITCH_MAX_CAND = 64;    // per signal, beyond that: every lag is e
 constexpr float PITCH_EPS = 1e-3f;
 constexpr int PITCH_SCRATCH_WORDS = 2 * PITCH_Y + 2 * 2 * PITCH_S + 4 + 2 * (PITCH_MAX_CAND + 2) + 16;
 static_assert(PITCH_LAG0 % 4 == 1 && PITCH_LAG0 <= PITCH_LO, "lag tiling");
+static_assert(PITCH_SCRATCH_WORDS <= (int)SCR_WORDS, "pitch scratch fits");
 static_assert(PITCH_LAG0 + PITCH_LPT * 57 > PITCH_HI, "57 threads cover every lag");
 static_assert(PITCH_HI + PITCH_LPT + PITCH_LEN + 8 <= PITCH_Y, "staging covers the loop's reads");
 static_assert(PITCH_HI + PITCH_LEN < PITCH_S, "prefix covers every window");
@@ -263,7 +264,7 @@ __device__ void smooth_pitch(const State& s, const Smem& sm, int16_t* us, uint32
     float shift = target / ratio;
     uint32_t len = xf;
     if (len > n / 4) len = n / 4;
-    int16_t* tmp = reinterpret_cast<int16_t*>(sm.scratch);  // len <= hcap <= 2 * scr_words
+    int16_t* tmp = reinterpret_cast<int16_t*>(sm.scratch);  // len <= hcap <= 2 * SCR_WORDS (host check)
     bool do_shift = !(shift < 0.9f || shift > 1.1f || len < 100);
     uint32_t keep = len;
     if (do_shift) {
@@ -284,8 +285,9 @@ __device__ void smooth_pitch(const State& s, const Smem& sm, int16_t* us, uint32
         tmp[i] = r;
     }
     __syncthreads();
+    const float flen = (float)len, rlen = recip_for_div(flen);
     for (uint32_t i = tid; i < len; i += ASM_THREADS) {
-        float t = (float)i / (float)len;
+        const float t = div_by((float)i, flen, rlen);
         us[i] = f2s((float)tmp[i] * (1.0f - t) + (float)us[i] * t);
     }
     __syncthreads();
@@ -296,12 +298,7 @@ __device__ void match_energy(const State& s, const Smem& sm, int16_t* us, uint32
     if (len == 0) return;
     const int tid = threadIdx.x;
     const int16_t* tail = s.w + ((int)s.cnt - (int)len);
-    long long sp = 0, sn = 0;
-    for (uint32_t i = tid; i < len; i += ASM_THREADS) {
-        int p = tail[i], q = us[i];
-        sp += (long long)p * p;
-        sn += (long long)q * q;
-    }
+    long long sp = sumsq_range(tail, len), sn = sumsq_range(us, len);
     block_allreduce_add2<ASM_THREADS>(sp, sn, reinterpret_cast<long long*>(sm.red));
     float pr = (float)sqrt((double)sp / (double)len);
     float nr = (float)sqrt((double)sn / (double)len);
@@ -309,11 +306,22 @@ __device__ void match_energy(const State& s, const Smem& sm, int16_t* us, uint32
     float ratio = pr / nr;
     if (ratio > 2.0f) ratio = 2.0f;
     if (ratio < 0.5f) ratio = 0.5f;
-    const float flen = (float)len;
-    for (uint32_t i = tid; i < len; i += ASM_THREADS) {
-        float t = (float)i / flen;
-        float g = ratio * (1.0f - t) + 1.0f * t;
-        us[i] = f2s(clamp16f((float)us[i] * g));
+    // two samples per step (us is 4-byte aligned); t = i / len with the hoisted reciprocal
+    const float flen = (float)len, rlen = recip_for_div(flen);
+    uint32_t* us2 = reinterpret_cast<uint32_t*>(us);
+    for (uint32_t h = tid; 2 * h < len; h += ASM_THREADS) {
+        const uint32_t i = 2 * h;
+        const uint32_t w = us2[h];
+        const float t0 = div_by((float)i, flen, rlen);
+        const float g0 = ratio * (1.0f - t0) + 1.0f * t0;
+        const int y0 = cvt_sat_s16((float)(short)(w & 0xffffu) * g0);
+        int y1 = (int)(short)(w >> 16);
+        if (i + 1 < len) {
+            const float t1 = div_by((float)(i + 1), flen, rlen);
+            const float g1 = ratio * (1.0f - t1) + 1.0f * t1;
+            y1 = cvt_sat_s16((float)y1 * g1);
+        }
+        us2[h] = (uint32_t)(y0 & 0xffff) | ((uint32_t)y1 << 16);
     }
     __syncthreads();
 }

@@ -7,20 +7,24 @@ namespace ctts {
 
 // ---------------------------------------------------------------- unit op
 
-// the two crossfade gains at t share the table position (fast_fade_out / fast_fade_in, ctts.c:76-92)
+// the two crossfade gains at t share the table position (fast_fade_out / fast_fade_in, ctts.c:76-92);
+// xfade4[k] = {fade_out[k], fade_out[k+1], fade_in[k], fade_in[k+1]}: one 16-byte load
 __device__ __forceinline__ void crossfade_gains(const DevTables& tab, float t, float* pg, float* ng) {
     float x = t * (float)(LUT_N - 1);
     int k = (int)x;
     if (k >= LUT_N - 1) {
-        *pg = __ldg(tab.fade_out + LUT_N - 1);
-        *ng = __ldg(tab.fade_in + LUT_N - 1);
+        const float4 e = __ldg(tab.xfade4 + LUT_N - 1);
+        *pg = e.x;
+        *ng = e.z;
     } else if (k < 0) {
-        *pg = __ldg(tab.fade_out);
-        *ng = __ldg(tab.fade_in);
+        const float4 e = __ldg(tab.xfade4);
+        *pg = e.x;
+        *ng = e.z;
     } else {
+        const float4 e = __ldg(tab.xfade4 + k);
         float fr = x - (float)k, om = 1.0f - fr;
-        *pg = __ldg(tab.fade_out + k) * om + __ldg(tab.fade_out + k + 1) * fr;
-        *ng = __ldg(tab.fade_in + k) * om + __ldg(tab.fade_in + k + 1) * fr;
+        *pg = e.x * om + e.y * fr;
+        *ng = e.z * om + e.w * fr;
     }
 }
 

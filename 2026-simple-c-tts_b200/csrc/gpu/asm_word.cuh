@@ -40,7 +40,7 @@ __device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t big, 
 
     const uint32_t wn = (len + 31) >> 5;
     uint32_t* words;
-    if (2 * wn <= A.scr_words) words = sm.scratch;
+    if (2 * wn <= SCR_WORDS) words = sm.scratch;
     else words = A.trim_scratch + (size_t)big * A.trim_scratch_words;   // host sized it for this task
     uint32_t* woff = words + wn;
 
@@ -200,6 +200,7 @@ constexpr uint32_t CONTOUR_STAGE = CONTOUR_TILE + CONTOUR_CARRY;  // 256 behind,
 static_assert(CONTOUR_CARRY % 8 == 0, "carry is whole staging vectors");
 constexpr uint32_t CONTOUR_PF_MAX = 1024;                    // frames with a tabulated pitch factor
 constexpr uint32_t CONTOUR_SCRATCH_WORDS = CONTOUR_STAGE + CONTOUR_PF_MAX;
+static_assert(CONTOUR_SCRATCH_WORDS + 8 <= SCR_WORDS, "contour scratch fits");
 static_assert(ASM_THREADS % 128 == 0, "a thread's outputs must keep their position inside a frame");
 
 // one frame's contribution to an output sample (ctts.c:2236-2251): linear-interpolated read at
@@ -272,7 +273,36 @@ __device__ bool pitch_contour(const Smem& sm, int16_t* x, uint32_t n, float f0, 
         }
         __syncthreads();
         // ---- outputs of this tile
+        // interior tile: every output is covered by two whole frames; branch-free, the four
+        // outputs of a thread are independent instruction streams
+        const bool fast = tabulated && !degenerate && t0 >= 128 && t0 + CONTOUR_TILE <= n &&
+                          ((t0 + CONTOUR_TILE - 1) >> 7) < frames && w_2 > 0.01f;
+        if (fast) {
+            const uint32_t kb = (t0 >> 7) + ((uint32_t)tid >> 7);       // frame k1 of output r = 0
+            const float* fb0 = sbase + (int)((uint32_t)tid & ~127u) - 128;  // start of frame k1 - 1, r = 0
+            int o[CONTOUR_KPT];
 #pragma unroll
+            for (int r = 0; r < CONTOUR_KPT; r++) {
+                const float pfa = pft[kb + 2 * r - 1], pfb = pft[kb + 2 * r];
+                const float* fa = fb0 + ASM_THREADS * r;
+                const int ta = contour_term(fa, fi_hi, pfa, w_hi);
+                const int tb = contour_term(fa + 128, fi_lo, pfb, w_lo);
+                const int acc = (int)(int16_t)(ta + tb);
+                o[r] = cvt_sat_s16(div_by((float)acc, w_2, r_2));
+            }
+            if (energy) {
+#pragma unroll
+                for (int r = 0; r < CONTOUR_KPT; r++) {
+                    const float t = div_by((float)(t0 + (uint32_t)tid + (uint32_t)(ASM_THREADS * r) + ebase), eden, r_e);
+                    o[r] = cvt_sat_s16((float)o[r] * (e0 + de * t));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < CONTOUR_KPT; r++) x[t0 + (uint32_t)tid + (uint32_t)(ASM_THREADS * r)] = (int16_t)o[r];
+            __syncthreads();
+            continue;
+        }
+#pragma unroll 1
         for (int r = 0; r < CONTOUR_KPT; r++) {
             const uint32_t ju = (uint32_t)tid + (uint32_t)r * ASM_THREADS;   // index inside the tile
             const uint32_t j = t0 + ju;

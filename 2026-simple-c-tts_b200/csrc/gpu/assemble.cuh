@@ -123,14 +123,15 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
 
 __global__ void __launch_bounds__(ASM_THREADS, 3) assemble_kernel(const AsmArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // fixed-size parts first: their addresses are compile-time offsets (see SMEM_* in asm_common.cuh)
     Smem sm;
-    sm.win = reinterpret_cast<int16_t*>(smem_raw);
-    sm.hstage = sm.win + A.wcap + 16;
-    sm.scratch = reinterpret_cast<uint32_t*>(sm.hstage + A.hcap);
-    sm.hann256 = reinterpret_cast<float*>(sm.scratch + A.scr_words);
-    sm.nrm2 = sm.hann256 + PITCH_FRAME;
-    sm.red = reinterpret_cast<unsigned long long*>(sm.nrm2 + PITCH_FRAME / 2);
-    sm.bcast = reinterpret_cast<uint32_t*>(sm.red + 2 * ASM_WARPS);
+    sm.hann256 = reinterpret_cast<float*>(smem_raw + SMEM_HANN);
+    sm.nrm2 = reinterpret_cast<float*>(smem_raw + SMEM_NRM2);
+    sm.red = reinterpret_cast<unsigned long long*>(smem_raw + SMEM_RED);
+    sm.bcast = reinterpret_cast<uint32_t*>(smem_raw + SMEM_BCAST);
+    sm.scratch = reinterpret_cast<uint32_t*>(smem_raw + SMEM_SCRATCH);
+    sm.hstage = reinterpret_cast<int16_t*>(smem_raw + SMEM_HSTAGE);
+    sm.win = sm.hstage + A.hcap;
 
     const int tid = threadIdx.x;
     for (int i = tid; i < PITCH_FRAME; i += ASM_THREADS) sm.hann256[i] = __ldg(A.tab.hann256 + i);

@@ -49,7 +49,7 @@ struct ctts_gpu_ctx {
     int16_t* d_pool = nullptr;
     uint32_t* d_unit_off = nullptr;
     uint32_t* d_unit_cnt = nullptr;
-    float* d_tables = nullptr;  // fade_out, fade_in, sine (1024 each), hann256, hann512
+    float* d_tables = nullptr;  // fade_out, fade_in, sine (1024 each), hann256, hann512, xfade4 (4096)
     uint32_t n_units = 0;
     uint32_t max_unit = 0;
     std::vector<uint32_t> unit_cnt;
@@ -240,8 +240,16 @@ int ctts_gpu_init(ctts_gpu_ctx** out, const void* voice_db, size_t db_size, int 
         CUI(cudaMemcpy(ctx->d_unit_off, unit_off.data(), h.unit_count * 4ull, cudaMemcpyHostToDevice));
         CUI(cudaMemcpy(ctx->d_unit_cnt, ctx->unit_cnt.data(), h.unit_count * 4ull, cudaMemcpyHostToDevice));
     }
-    std::vector<float> tab(3 * 1024 + 256 + 512);
+    std::vector<float> tab(3 * 1024 + 256 + 512 + 4 * 1024);
     ctts_host_tables(tab.data(), tab.data() + 1024, tab.data() + 2048, tab.data() + 3072, tab.data() + 3328);
+    for (int k = 0; k < 1024; k++) {   // interleaved crossfade table: one 16-byte load per sample
+        const int k1 = k + 1 < 1024 ? k + 1 : 1023;
+        float* e = tab.data() + 3840 + 4 * k;
+        e[0] = tab[k];
+        e[1] = tab[k1];
+        e[2] = tab[1024 + k];
+        e[3] = tab[1024 + k1];
+    }
     CUI(cudaMalloc(reinterpret_cast<void**>(&ctx->d_tables), tab.size() * sizeof(float)));
     CUI(cudaMemcpy(ctx->d_tables, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
 #undef CUI
@@ -398,14 +406,11 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
     // ---- shared-memory geometry
     const uint32_t max_unit = ctx->max_unit;
     const uint32_t hcap = (uint32_t)up8(std::max<uint32_t>(std::min(xf_max, max_unit), 496)) + 8;
-    auto scr_for = [&](uint32_t wcap) {
-        uint32_t a = std::max<uint32_t>(ctts::PITCH_SCRATCH_WORDS, ctts::CONTOUR_SCRATCH_WORDS + 8), b = hcap / 2 + 8,
-                 c = 2 * ((wcap + 31) / 32) + 4;
-        return (std::max(a, std::max(b, c)) + 3u) & ~3u;
-    };
-    auto smem_for = [&](uint32_t wcap) {
-        return (wcap + 16) * 2 + hcap * 2 + scr_for(wcap) * 4 + 256 * 4 + 128 * 4 + 2 * ctts::ASM_WARPS * 8 + 16;
-    };
+    if (hcap > 2 * ctts::SCR_WORDS) {
+        ctts_gpu_plan_destroy(p);
+        return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "crossfade of %u samples exceeds the staging capacity", xf_max);
+    }
+    auto smem_for = [&](uint32_t wcap) { return ctts::SMEM_HSTAGE + hcap * 2 + (wcap + 16) * 2; };
     // regions (the samples between two word marks) and their upper bounds
     struct Region { uint32_t op_begin, op_end; uint64_t bound; uint32_t units; };
     std::vector<std::vector<Region>> regions(n);
@@ -442,7 +447,7 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
     }
     p->wcap = wcap;
     p->hcap = hcap;
-    p->scr_words = scr_for(wcap);
+    p->scr_words = ctts::SCR_WORDS;
     p->smem_bytes = smem_for(wcap);
 
     // ---- plan compile step 2: region tasks.  A region with no unit (a pause) or a tiny one is
@@ -531,7 +536,7 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
     tasks.reserve(n_tasks);
     std::vector<int32_t> last_index(n, -1);
     uint32_t n_big = 0, n_global = 0;
-    const uint64_t scr_samples = (uint64_t)(p->scr_words - 4) / 2 * 32;   // region length the shared trim mask covers
+    const uint64_t scr_samples = (uint64_t)(ctts::SCR_WORDS - 4) / 2 * 32;   // region length the shared trim mask covers
     uint64_t big_region_max = 0;
     for (uint32_t k = 0; k < max_tasks_per_utt; k++) {
         for (uint32_t i = 0; i < n; i++) {
@@ -664,6 +669,7 @@ int ctts_gpu_plan_run(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, int16_t* d_pcm_out) {
         a.tab.sine = ctx->d_tables + 2048;
         a.tab.hann256 = ctx->d_tables + 3072;
         a.tab.hann512 = ctx->d_tables + 3328;
+        a.tab.xfade4 = reinterpret_cast<const float4*>(ctx->d_tables + 3840);
         a.ops = p->d_ops;
         a.tasks = p->d_tasks;
         a.n_tasks = p->n_tasks;
@@ -680,7 +686,6 @@ int ctts_gpu_plan_run(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, int16_t* d_pcm_out) {
         a.prm = p->prm;
         a.wcap = p->wcap;
         a.hcap = p->hcap;
-        a.scr_words = p->scr_words;
         ctts::assemble_kernel<<<p->grid, ctts::ASM_THREADS, p->smem_bytes, st>>>(a);
         CU(ctx, cudaGetLastError());
     }

@@ -13,19 +13,21 @@ namespace ctts {
 // over i < 220: corr += s[i]*s[i+lag], e1 += s[i]^2, e2 += s[i+lag]^2, and keeps
 // the first lag whose corr/sqrtf(e1*e2) is the strict maximum (voiced iff > 0.3).
 // Those sums cannot be reordered, and at 3 non-fused FP32 operations per
-// (lag, i) pair they are 40 % of all instructions of the assembly path.  So
+// (lag, i) pair they would be 40 % of all instructions of the assembly path.  So
 // the search is done in two steps that together give the identical result:
 //
 //  1. FILTER: every lag gets an approximate score a[lag] = c~ / sqrtf(e1x * e2x),
 //     c~ accumulated with FMA (one instruction per pair, four lags per thread
-//     sharing the operand loads) and e1x, e2x EXACT integer window sums taken
-//     from a 64-bit prefix sum of the squares.  For 220 terms |a - r| <= 4.2e-5
-//     where r is the reference's score (standard summation error bound,
-//     n*u*sum|x_i*y_i| <= n*u*sqrt(e1*e2) by Cauchy-Schwarz; DESIGN.md derives it).
-//  2. EXACT: with eps = 1e-3 (24 x the bound), a signal is unvoiced if
-//     max a <= 0.3 - eps; otherwise only lags with a >= max a - 2*eps can be the
-//     reference's arg max, and those (typically 1-3) are evaluated by one thread
-//     each with the reference's exact operation order.
+//     sharing the operand loads, the i range split over two threads) and e1x, e2x
+//     EXACT integer window sums taken from a 64-bit prefix sum of the squares.
+//     For 220 terms |a - r| <= 4.0e-5 where r is the reference's score (standard
+//     summation error bound, gamma_n * sum|x_i*y_i| <= gamma_n * sqrt(e1*e2) by
+//     Cauchy-Schwarz; DESIGN.md derives it).
+//  2. DECIDE: with eps = 2.5e-4 (6 x the bound) a signal is unvoiced if
+//     max a <= 0.3 - eps.  Otherwise only lags with a >= max a - 2*eps can be the
+//     reference's arg max.  If that is a single lag and its score exceeds
+//     0.3 + eps, the answer is known.  Else the candidates (typically 2-3) are
+//     evaluated by one thread each with the reference's exact operation order.
 //
 // Both signals are needed voiced by the caller, so step 2 is skipped entirely
 // when either signal fails the filter.
@@ -34,19 +36,20 @@ constexpr int PITCH_HI = CTTS_PLAN_SAMPLE_RATE / 80;   // 275
 constexpr int PITCH_LEN = CTTS_PLAN_SAMPLE_RATE / 100; // 220
 constexpr int PITCH_LAG0 = 53;        // lag of thread 0 (= 1 mod 4 keeps both float4 loads aligned)
 constexpr int PITCH_LPT = 4;          // lags per thread
-constexpr int PITCH_TPS = 64;         // threads per signal (57 used)
+constexpr int PITCH_TPS = 64;         // threads per signal and half (57 used)
 constexpr int PITCH_Y = 512;          // staged floats per signal (zero padded)
 constexpr int PITCH_S = 504;          // prefix entries per signal
 constexpr int PITCH_MAX_CAND = 64;    // per signal, beyond that: every lag is evaluated exactly
-constexpr float PITCH_EPS = 1e-3f;
-constexpr int PITCH_SCRATCH_WORDS = 2 * PITCH_Y + 2 * 2 * PITCH_S + 4 + 2 * (PITCH_MAX_CAND + 2) + 16;
+constexpr float PITCH_EPS = 2.5e-4f;
+constexpr int PITCH_SCRATCH_WORDS = 2 * PITCH_Y + 2 * 2 * PITCH_S + 4 + 2 * (PITCH_MAX_CAND + 2) + 16 + 4 * 2 * PITCH_TPS;
+static_assert(ASM_THREADS == 4 * PITCH_TPS, "2 signals x 2 halves x PITCH_TPS threads");
 static_assert(PITCH_LAG0 % 4 == 1 && PITCH_LAG0 <= PITCH_LO, "lag tiling");
 static_assert(PITCH_SCRATCH_WORDS <= (int)SCR_WORDS, "pitch scratch fits");
 static_assert(PITCH_LAG0 + PITCH_LPT * 57 > PITCH_HI, "57 threads cover every lag");
 static_assert(PITCH_HI + PITCH_LPT + PITCH_LEN + 8 <= PITCH_Y, "staging covers the loop's reads");
 static_assert(PITCH_HI + PITCH_LEN < PITCH_S, "prefix covers every window");
 
-// exact score of one lag in the reference's order (ctts.c:1917-1931); lag 0 yields e1 in *e2_out
+// exact sums of one lag in the reference's order (ctts.c:1917-1931); lag 0 yields e1 in *e2_out
 __device__ __forceinline__ float pitch_exact_sums(const float* y, uint32_t lag, uint32_t len, float* e2_out) {
     float c = 0.0f, e2 = 0.0f;
     const float* x = y;
@@ -59,6 +62,32 @@ __device__ __forceinline__ float pitch_exact_sums(const float* y, uint32_t lag, 
     }
     *e2_out = e2;
     return c;
+}
+
+// S[i] = sum_{j<i} s[j]^2 for i < PITCH_S, exact (int16 inputs, 504 * 2^30 < 2^64); one warp
+__device__ __forceinline__ void pitch_prefix_warp(const int16_t* s, uint32_t need, unsigned long long* S) {
+    constexpr int PER = 16;  // 32 lanes * 16 = 512 >= PITCH_S
+    const int lane = lane_id();
+    const int i0 = lane * PER;
+    int v[PER];
+    unsigned long long loc = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        v[k] = (uint32_t)(i0 + k) < need ? (int)s[i0 + k] : 0;
+        loc += (unsigned long long)(uint32_t)(v[k] * v[k]);
+    }
+    unsigned long long inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    unsigned long long run = inc - loc;  // exclusive
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        if (i0 + k < PITCH_S) S[i0 + k] = run;
+        run += (unsigned long long)(uint32_t)(v[k] * v[k]);
+    }
 }
 
 __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int16_t* b, uint32_t n,
@@ -83,79 +112,69 @@ __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int1
     uint32_t* ncand = cand + 2 * (PITCH_MAX_CAND + 2);            // [2]
     float* amax = reinterpret_cast<float*>(ncand + 2);            // [4] per lag warp
     float* e1s = amax + 4;                                        // [2]
+    float4* cpart = reinterpret_cast<float4*>(e1s + 10);          // [2 * PITCH_TPS] second-half partial sums
 
-    for (uint32_t i = tid; i < PITCH_Y; i += ASM_THREADS) {
-        const bool in = i < need;
-        ya[i] = in ? (float)a[i] : 0.0f;
-        yb[i] = in ? (float)b[i] : 0.0f;
-    }
-    if (tid < 2) {
-        ncand[tid] = 0;
-        keys[tid] = 0ull;
+    // ---- warps 0-1: exact prefix sums of squares; warps 2-7: float staging
+    if (warp == 0) pitch_prefix_warp(a, need, Sa);
+    else if (warp == 1) pitch_prefix_warp(b, need, Sb);
+    else {
+        for (uint32_t i = tid - 64; i < 2 * PITCH_Y; i += ASM_THREADS - 64) {
+            const uint32_t k = i & (PITCH_Y - 1);
+            const int16_t* src = i < PITCH_Y ? a : b;
+            ya[i] = k < need ? (float)src[k] : 0.0f;   // yb == ya + PITCH_Y
+        }
+        if (tid < 66) {
+            ncand[tid - 64] = 0;
+            keys[tid - 64] = 0ull;
+        }
     }
     __syncthreads();
 
-    // ---- step 1: FMA scores on warps 0-3, exact prefix sums of squares on warps 4-5
+    // ---- step 1: FMA scores; thread (half, signal, lag group) accumulates its half of the i range
     float c[PITCH_LPT] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const int half = tid >> 7;
     const int sig = (tid >> 6) & 1;
     const uint32_t lag0 = PITCH_LAG0 + PITCH_LPT * (uint32_t)(tid & (PITCH_TPS - 1));
-    const bool lag_thread = tid < 2 * PITCH_TPS && lag0 <= hi;
+    const bool lag_thread = lag0 <= hi;
+    const uint32_t split = ((len >> 1) + 3u) & ~3u;          // multiple of 4: both halves keep the alignment
     if (lag_thread) {
         const float* x = sig ? yb : ya;
         const float* y = x + lag0;  // y[j] = s[lag0 + j]; (lag0 + 3) % 4 == 0
-        float w0 = y[0], w1 = y[1], w2 = y[2];
-        const uint32_t len4 = len & ~3u;
-        for (uint32_t i = 0; i < len4; i += 4) {
-            const float4 xv = *reinterpret_cast<const float4*>(x + i);
-            const float4 yn = *reinterpret_cast<const float4*>(y + i + 3);
-            const float w3 = yn.x, w4 = yn.y, w5 = yn.z, w6 = yn.w;
-            c[0] = __fmaf_rn(xv.x, w0, c[0]); c[1] = __fmaf_rn(xv.x, w1, c[1]);
-            c[2] = __fmaf_rn(xv.x, w2, c[2]); c[3] = __fmaf_rn(xv.x, w3, c[3]);
-            c[0] = __fmaf_rn(xv.y, w1, c[0]); c[1] = __fmaf_rn(xv.y, w2, c[1]);
-            c[2] = __fmaf_rn(xv.y, w3, c[2]); c[3] = __fmaf_rn(xv.y, w4, c[3]);
-            c[0] = __fmaf_rn(xv.z, w2, c[0]); c[1] = __fmaf_rn(xv.z, w3, c[1]);
-            c[2] = __fmaf_rn(xv.z, w4, c[2]); c[3] = __fmaf_rn(xv.z, w5, c[3]);
-            c[0] = __fmaf_rn(xv.w, w3, c[0]); c[1] = __fmaf_rn(xv.w, w4, c[1]);
-            c[2] = __fmaf_rn(xv.w, w5, c[2]); c[3] = __fmaf_rn(xv.w, w6, c[3]);
-            w0 = w4; w1 = w5; w2 = w6;
-        }
-        for (uint32_t i = len4; i < len; i++) {
-            const float xs = x[i];
+        const uint32_t i_begin = half ? split : 0u;
+        const uint32_t i_end = half ? len : (split < len ? split : len);
+        if (i_begin < i_end) {
+            float w0 = y[i_begin], w1 = y[i_begin + 1], w2 = y[i_begin + 2];
+            const uint32_t i4 = i_begin + ((i_end - i_begin) & ~3u);
+            for (uint32_t i = i_begin; i < i4; i += 4) {
+                const float4 xv = *reinterpret_cast<const float4*>(x + i);
+                const float4 yn = *reinterpret_cast<const float4*>(y + i + 3);
+                const float w3 = yn.x, w4 = yn.y, w5 = yn.z, w6 = yn.w;
+                c[0] = __fmaf_rn(xv.x, w0, c[0]); c[1] = __fmaf_rn(xv.x, w1, c[1]);
+                c[2] = __fmaf_rn(xv.x, w2, c[2]); c[3] = __fmaf_rn(xv.x, w3, c[3]);
+                c[0] = __fmaf_rn(xv.y, w1, c[0]); c[1] = __fmaf_rn(xv.y, w2, c[1]);
+                c[2] = __fmaf_rn(xv.y, w3, c[2]); c[3] = __fmaf_rn(xv.y, w4, c[3]);
+                c[0] = __fmaf_rn(xv.z, w2, c[0]); c[1] = __fmaf_rn(xv.z, w3, c[1]);
+                c[2] = __fmaf_rn(xv.z, w4, c[2]); c[3] = __fmaf_rn(xv.z, w5, c[3]);
+                c[0] = __fmaf_rn(xv.w, w3, c[0]); c[1] = __fmaf_rn(xv.w, w4, c[1]);
+                c[2] = __fmaf_rn(xv.w, w5, c[2]); c[3] = __fmaf_rn(xv.w, w6, c[3]);
+                w0 = w4; w1 = w5; w2 = w6;
+            }
+            for (uint32_t i = i4; i < i_end; i++) {
+                const float xs = x[i];
 #pragma unroll
-            for (int k = 0; k < PITCH_LPT; k++) c[k] = __fmaf_rn(xs, y[i + k], c[k]);
+                for (int k = 0; k < PITCH_LPT; k++) c[k] = __fmaf_rn(xs, y[i + k], c[k]);
+            }
         }
-    } else if (warp == 4 || warp == 5) {
-        // S[i] = sum_{j<i} s[j]^2, exact (values are int16, 504 * 2^30 < 2^64)
-        const float* y = warp == 5 ? yb : ya;
-        unsigned long long* S = warp == 5 ? Sb : Sa;
-        constexpr int PER = 16;  // 32 lanes * 16 = 512 >= PITCH_S
-        unsigned long long loc = 0;
-        const int i0 = lane * PER;
-#pragma unroll
-        for (int k = 0; k < PER; k++) {
-            const int v = (int)y[i0 + k];
-            loc += (unsigned long long)(uint32_t)(v * v);
-        }
-        unsigned long long inc = loc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        unsigned long long run = inc - loc;  // exclusive
-#pragma unroll
-        for (int k = 0; k < PER; k++) {
-            if (i0 + k < PITCH_S) S[i0 + k] = run;
-            const int v = (int)y[i0 + k];
-            run += (unsigned long long)(uint32_t)(v * v);
-        }
+        if (half) cpart[tid & (2 * PITCH_TPS - 1)] = make_float4(c[0], c[1], c[2], c[3]);
     }
     __syncthreads();
 
-    // ---- scores and per-signal maximum
+    // ---- scores and per-signal maximum (first-half threads)
     float sc[PITCH_LPT];
     float my_max = -1.0f;
-    if (lag_thread) {
+    if (lag_thread && !half) {
+        const float4 p2 = cpart[tid];
+        c[0] += p2.x; c[1] += p2.y; c[2] += p2.z; c[3] += p2.w;
         const unsigned long long* S = sig ? Sb : Sa;
         const float e1 = (float)(S[len] - S[0]);
 #pragma unroll
@@ -184,7 +203,7 @@ __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int1
     }
 
     // ---- candidates
-    if (lag_thread) {
+    if (lag_thread && !half) {
         const float thr = (sig ? max_b : max_a) - 2.0f * PITCH_EPS;
 #pragma unroll
         for (int k = 0; k < PITCH_LPT; k++) {
@@ -196,16 +215,27 @@ __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int1
     }
     __syncthreads();
     uint32_t na = ncand[0], nb = ncand[1];
+    // a single candidate well above the voicing threshold IS the reference's answer
+    const bool sure_a = na == 1 && max_a > 0.3f + PITCH_EPS, sure_b = nb == 1 && max_b > 0.3f + PITCH_EPS;
+    if (sure_a) *pa = (float)CTTS_PLAN_SAMPLE_RATE / (float)cand[0];
+    if (sure_b) *pb = (float)CTTS_PLAN_SAMPLE_RATE / (float)cand[PITCH_MAX_CAND + 2];
+    if (sure_a && sure_b) {
+        __syncthreads();
+        return;
+    }
     const bool all_a = na > PITCH_MAX_CAND, all_b = nb > PITCH_MAX_CAND;  // degenerate: evaluate every lag
     if (all_a) na = hi - lo + 1;
     if (all_b) nb = hi - lo + 1;
+    if (sure_a) na = 0;   // nothing to evaluate for a settled signal
+    if (sure_b) nb = 0;
     __syncthreads();
 
     // ---- step 2: exact evaluation, one thread per (signal, lag); job 0 of each signal is lag 0 (= e1)
-    const uint32_t jobs = na + nb + 2;
+    const uint32_t ja = sure_a ? 0u : na + 1, jb = sure_b ? 0u : nb + 1;
+    const uint32_t jobs = ja + jb;
     for (uint32_t j = tid; j < jobs; j += ASM_THREADS) {
-        const int sg = j < na + 1 ? 0 : 1;
-        const uint32_t jj = sg ? j - (na + 1) : j;
+        const int sg = j < ja ? 0 : 1;
+        const uint32_t jj = sg ? j - ja : j;
         if (jj == 0) {
             float e1;
             (void)pitch_exact_sums(sg ? yb : ya, 0, len, &e1);
@@ -221,8 +251,8 @@ __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int1
     }
     __syncthreads();
     for (uint32_t j = tid; j < jobs; j += ASM_THREADS) {
-        const int sg = j < na + 1 ? 0 : 1;
-        const uint32_t jj = sg ? j - (na + 1) : j;
+        const int sg = j < ja ? 0 : 1;
+        const uint32_t jj = sg ? j - ja : j;
         if (jj == 0) continue;
         const bool all = sg ? all_b : all_a;
         const uint32_t lag = all ? lo + (jj - 1) : cand[sg * (PITCH_MAX_CAND + 2) + (jj - 1)];
@@ -236,12 +266,12 @@ __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int1
     }
     __syncthreads();
     const unsigned long long ka = keys[0], kb = keys[1];
-    {
+    if (!sure_a) {
         const float v = __uint_as_float((uint32_t)(ka >> 32));
         const uint32_t l = 0xffffffffu - (uint32_t)(ka & 0xffffffffu);
         if (ka != 0ull && v > 0.3f && l > 0) *pa = (float)CTTS_PLAN_SAMPLE_RATE / (float)l;
     }
-    {
+    if (!sure_b) {
         const float v = __uint_as_float((uint32_t)(kb >> 32));
         const uint32_t l = 0xffffffffu - (uint32_t)(kb & 0xffffffffu);
         if (kb != 0ull && v > 0.3f && l > 0) *pb = (float)CTTS_PLAN_SAMPLE_RATE / (float)l;

@@ -273,13 +273,14 @@ __device__ bool pitch_contour(const Smem& sm, int16_t* x, uint32_t n, float f0, 
         }
         __syncthreads();
         // ---- outputs of this tile
-        // interior tile: every output is covered by two whole frames; branch-free, the four
-        // outputs of a thread are independent instruction streams
-        const bool fast = tabulated && !degenerate && t0 >= 128 && t0 + CONTOUR_TILE <= n &&
-                          ((t0 + CONTOUR_TILE - 1) >> 7) < frames && w_2 > 0.01f;
+        // A 256-output block is "interior" when each of its outputs is covered by two whole
+        // frames: branch-free code.  In an interior tile the four outputs of a thread are
+        // independent instruction streams.
+        const uint32_t kb = (t0 >> 7) + ((uint32_t)tid >> 7);           // frame k1 of output r = 0
+        const float* fb0 = sbase + (int)((uint32_t)tid & ~127u) - 128;  // start of frame k1 - 1, r = 0
+        const bool can_fast = tabulated && !degenerate && w_2 > 0.01f;
+        const bool fast = can_fast && t0 >= 128 && t0 + CONTOUR_TILE <= n && ((t0 + CONTOUR_TILE - 1) >> 7) < frames;
         if (fast) {
-            const uint32_t kb = (t0 >> 7) + ((uint32_t)tid >> 7);       // frame k1 of output r = 0
-            const float* fb0 = sbase + (int)((uint32_t)tid & ~127u) - 128;  // start of frame k1 - 1, r = 0
             int o[CONTOUR_KPT];
 #pragma unroll
             for (int r = 0; r < CONTOUR_KPT; r++) {
@@ -304,6 +305,21 @@ __device__ bool pitch_contour(const Smem& sm, int16_t* x, uint32_t n, float f0, 
         }
 #pragma unroll 1
         for (int r = 0; r < CONTOUR_KPT; r++) {
+            const uint32_t j0 = t0 + (uint32_t)r * ASM_THREADS;
+            if (can_fast && j0 >= 128 && j0 + ASM_THREADS <= n && ((j0 + ASM_THREADS - 1) >> 7) < frames) {
+                // interior block of an edge tile
+                const float pfa = pft[kb + 2 * r - 1], pfb = pft[kb + 2 * r];
+                const float* fa = fb0 + ASM_THREADS * r;
+                const int ta = contour_term(fa, fi_hi, pfa, w_hi);
+                const int tb = contour_term(fa + 128, fi_lo, pfb, w_lo);
+                int o = cvt_sat_s16(div_by((float)(int)(int16_t)(ta + tb), w_2, r_2));
+                if (energy) {
+                    const float t = div_by((float)(j0 + (uint32_t)tid + ebase), eden, r_e);
+                    o = cvt_sat_s16((float)o * (e0 + de * t));
+                }
+                x[j0 + (uint32_t)tid] = (int16_t)o;
+                continue;
+            }
             const uint32_t ju = (uint32_t)tid + (uint32_t)r * ASM_THREADS;   // index inside the tile
             const uint32_t j = t0 + ju;
             if (j >= t1) continue;

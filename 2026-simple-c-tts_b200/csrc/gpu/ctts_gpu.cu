@@ -538,10 +538,17 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
     uint32_t n_big = 0, n_global = 0;
     const uint64_t scr_samples = (uint64_t)(ctts::SCR_WORDS - 4) / 2 * 32;   // region length the shared trim mask covers
     uint64_t big_region_max = 0;
+    std::vector<uint32_t> row(n);
     for (uint32_t k = 0; k < max_tasks_per_utt; k++) {
-        for (uint32_t i = 0; i < n; i++) {
-            const uint32_t u = order[i];
-            if (k >= utt_tasks[u].size()) continue;
+        // inside a row: longest task first (it is the one a successor may have to wait for, and
+        // longest-first balances the tail of the launch)
+        uint32_t m = 0;
+        for (uint32_t i = 0; i < n; i++)
+            if (k < utt_tasks[order[i]].size()) row[m++] = order[i];
+        std::stable_sort(row.begin(), row.begin() + m,
+                         [&](uint32_t a, uint32_t b) { return utt_tasks[a][k].bound > utt_tasks[b][k].bound; });
+        for (uint32_t i = 0; i < m; i++) {
+            const uint32_t u = row[i];
             const HostTask& h = utt_tasks[u][k];
             ctts::RegionTask t{};
             t.utt = u;

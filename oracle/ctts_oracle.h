@@ -5,7 +5,7 @@
  * by the same batch plan the GPU back end consumes.  It exists to check the
  * CUDA path; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
  * leg may load it.  Pinned against the compiled reference (oracle/_ref, built
- * from /root/reference/ctts.c) by tests/test_oracle_vs_reference.py and against
+ * from /root/reference/ctts.c) by tests/test_oracle.py (test_oracle_vs_live_reference) and against
  * the committed vectors under tests/golden/.
  */
 #ifndef CTTS_ORACLE_H

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <numeric>
 #include <vector>
 
@@ -58,7 +59,21 @@ struct ctts_gpu_ctx {
     int smem_optin = 0;
     int16_t* d_batch_out = nullptr;  // reused by ctts_gpu_synth_batch
     uint64_t batch_out_cap = 0;
+    // grow-only workspaces of ctts_gpu_synth_batch (no cudaMalloc / cudaFree per call)
+    char* d_arena = nullptr;
+    size_t d_arena_cap = 0;
+    char* h_arena = nullptr;         // pinned staging for the plan upload
+    size_t h_arena_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> events;
     char err[512] = {0};
+};
+
+// one kernel launch: a contiguous range of utterances (= a contiguous span of output slots)
+struct PlanChunk {
+    uint32_t utt_begin = 0, utt_end = 0;
+    uint32_t task_begin = 0, n_tasks = 0;
+    uint32_t grid = 0;
 };
 
 struct ctts_gpu_plan {
@@ -67,14 +82,16 @@ struct ctts_gpu_plan {
     ctts_assembly_params prm{};
     std::vector<uint64_t> offsets;  // n_utts + 1
     std::vector<uint64_t> bounds;
+    bool in_arena = false;          // device buffers live in the context arena (batch path)
+    std::vector<void*> owned;       // else: cudaMalloc'ed buffers to free
     ctts_plan_op* d_ops = nullptr;
     ctts::RegionTask* d_tasks = nullptr;
     unsigned long long* d_chain = nullptr;
-    uint32_t* d_ticket = nullptr;
+    uint32_t* d_ticket = nullptr;   // one per chunk
+    std::vector<PlanChunk> chunks;
     uint32_t n_tasks = 0;
     uint32_t n_global_tasks = 0;
     uint32_t epoch = 0;
-    uint32_t grid = 0;
     ctts::StretchTask* d_stasks = nullptr;
     uint32_t* d_counts = nullptr;
     uint32_t* d_pre_counts = nullptr;
@@ -92,8 +109,16 @@ struct ctts_gpu_plan {
     int16_t* d_out_last = nullptr;
     std::vector<uint64_t> pre_off;   // per utterance (stretch only), else ~0
     std::vector<uint64_t> pre_cap;
-    uint32_t wcap = 0, hcap = 0, scr_words = 0, smem_bytes = 0;
+    uint32_t wcap = 0, hcap = 0, smem_bytes = 0;
     ctts_gpu_run_info info{};
+    // builder state (chunks are compiled and uploaded one at a time, see build_chunk)
+    const ctts_batch_plan* src = nullptr;   // borrowed until the last chunk is built
+    ctts_plan_op* h_ops = nullptr;          // staging: pinned (context arena) or the vectors below
+    ctts::RegionTask* h_tasks = nullptr;
+    std::vector<ctts_plan_op> ops_vec;
+    std::vector<ctts::RegionTask> tasks_vec;
+    uint32_t built_chunks = 0, n_big = 0, big_cap = 0, occ = 1;
+    uint64_t gather = 0;
 };
 
 namespace {
@@ -143,28 +168,93 @@ uint64_t stretch_bound(uint64_t pre, uint32_t hop) {
     return frames * hop + 512;
 }
 
-int compute_bounds(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, std::vector<uint64_t>* pre,
-                   std::vector<uint64_t>* out) {
-    pre->assign(plan->n_utts, 0);
-    out->assign(plan->n_utts, 0);
-    for (uint32_t u = 0; u < plan->n_utts; u++) {
-        uint32_t b = plan->utt_op_begin[u], e = plan->utt_op_begin[u + 1];
+// Upper bound of the samples a UNIT op appends, given a lower bound L of the samples already in
+// the current region.  The crossfade consumes a = min(xf, count, n) samples of the tail
+// (ctts.c:3319-3321) and count >= L, so a >= min(xf, n, L) whenever the unit is certain to be
+// joined (not after a word boundary and the buffer is certainly not empty).  L is updated to a
+// lower bound of the region length after the append (count + n - a >= max(L + n - min(xf, n), n)).
+inline uint64_t unit_append_bound(const ctts_plan_op& op, uint32_t n, uint64_t& L) {
+    if (n == 0) return 0;
+    const bool boundary = (op.flags & CTTS_UNIT_AFTER_BOUNDARY) != 0;
+    if (boundary) {
+        L += n;
+        return n;
+    }
+    const uint64_t m = std::min<uint64_t>(op.b, n);
+    if (L == 0) {   // joined or not: decided on the device
+        L = n;
+        return n;
+    }
+    const uint64_t a_lb = std::min<uint64_t>(m, L);
+    L = std::max<uint64_t>(L + n - m, n);
+    return n - a_lb;
+}
+
+struct PlanScan {
+    std::vector<uint64_t> pre, bound;   // per utterance: pre-stretch / output upper bounds
+    uint32_t xf_max = 0;
+    uint64_t region_max = 0, n_regions = 0, n_big_regions = 0, big_region_max = 0;
+    bool bad_factor = false, any_stretch = false;
+};
+
+// pass A over the plan: validation, upper bounds, global maxima
+int scan_plan(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, uint64_t big_threshold, PlanScan* sc, uint32_t* bad_utt) {
+    const uint32_t n = plan->n_utts;
+    sc->pre.assign(n, 0);
+    sc->bound.assign(n, 0);
+    const std::vector<uint32_t>& ucnt = ctx->unit_cnt;
+    for (uint32_t u = 0; u < n; u++) {
+        const uint32_t b = plan->utt_op_begin[u], e = plan->utt_op_begin[u + 1];
+        *bad_utt = u;
         if (b > e || e > plan->n_ops) return CTTS_GPU_ERR_INVALID_ARG;
-        uint64_t total = 0;
+        uint64_t total = 0, cur = 0, L = 0;
+        auto close_region = [&] {
+            total += cur;
+            if (cur > sc->region_max) sc->region_max = cur;
+            if (cur > big_threshold) {
+                sc->n_big_regions++;
+                if (cur > sc->big_region_max) sc->big_region_max = cur;
+            }
+            cur = 0;
+            L = 0;
+            sc->n_regions++;
+        };
         for (uint32_t k = b; k < e; k++) {
             const ctts_plan_op& op = plan->ops[k];
-            if (op.kind == CTTS_OP_UNIT) {
-                if (op.a >= ctx->n_units) return CTTS_GPU_ERR_INVALID_ARG;
-                total += ctx->unit_cnt[op.a];
-            } else if (op.kind == CTTS_OP_SILENCE) {
-                total += op.a;
-            } else if (op.kind < CTTS_OP_UNIT || op.kind > CTTS_OP_MARK) {
-                return CTTS_GPU_ERR_INVALID_ARG;
+            switch (op.kind) {
+                case CTTS_OP_UNIT:
+                    if (op.a >= ctx->n_units) return CTTS_GPU_ERR_INVALID_ARG;
+                    cur += unit_append_bound(op, ucnt[op.a], L);
+                    if (op.b > sc->xf_max) sc->xf_max = op.b;
+                    break;
+                case CTTS_OP_SILENCE:
+                    cur += op.a;
+                    L += op.a;
+                    break;
+                case CTTS_OP_FADE_OUT:
+                    break;
+                case CTTS_OP_WORD_END:
+                    if (op.flags & CTTS_WE_TRIM) L = 0;   // trimming may shrink the region by any amount
+                    if (op.flags & CTTS_WE_INTON) {
+                        // the contour kernel stages CONTOUR_AHEAD samples past a tile: factors come from
+                        // clamp_pitch(1 +- max_pitch_change) (ctts.c:2589), 0.9 .. 1.1 as shipped
+                        const float lo = std::min(op.f0, std::min(op.f1, op.f2)), hi = std::max(op.f0, std::max(op.f1, op.f2));
+                        if (!(lo >= 0.0f) || !(hi <= 2.05f)) sc->bad_factor = true;
+                    }
+                    break;
+                case CTTS_OP_MARK:
+                    close_region();
+                    break;
+                default:
+                    return CTTS_GPU_ERR_INVALID_ARG;
             }
         }
-        (*pre)[u] = total;
+        close_region();
+        sc->pre[u] = total;
         uint32_t hop = 0;
-        (*out)[u] = needs_stretch(plan->speed[u], &hop) ? stretch_bound(total, hop) : total;
+        const bool st = needs_stretch(plan->speed[u], &hop);
+        sc->any_stretch |= st;
+        sc->bound[u] = st ? stretch_bound(total, hop) : total;
     }
     return 0;
 }
@@ -266,6 +356,10 @@ void ctts_gpu_free(ctts_gpu_ctx* ctx) {
     cudaFree(ctx->d_unit_cnt);
     cudaFree(ctx->d_tables);
     cudaFree(ctx->d_batch_out);
+    cudaFree(ctx->d_arena);
+    if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -280,10 +374,12 @@ const char* ctts_gpu_last_error(const ctts_gpu_ctx* ctx) { return ctx ? ctx->err
 
 int ctts_gpu_plan_bounds(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, uint64_t* out_bound) {
     if (!ctx || !plan || !out_bound) return CTTS_GPU_ERR_INVALID_ARG;
-    std::vector<uint64_t> pre, out;
-    int rc = compute_bounds(ctx, plan, &pre, &out);
+    if (plan->n_utts && (!plan->utt_op_begin || !plan->speed)) return CTTS_GPU_ERR_INVALID_ARG;
+    PlanScan sc;
+    uint32_t bad = 0;
+    int rc = scan_plan(ctx, plan, ~0ull, &sc, &bad);
     if (rc) return rc;
-    std::copy(out.begin(), out.end(), out_bound);
+    std::copy(sc.bound.begin(), sc.bound.end(), out_bound);
     return CTTS_GPU_OK;
 }
 
@@ -293,26 +389,80 @@ void ctts_gpu_plan_destroy(ctts_gpu_plan* p) {
         cudaSetDevice(p->ctx->device);
         cudaStreamSynchronize(p->ctx->stream);
     }
-    cudaFree(p->d_ops);
-    cudaFree(p->d_tasks);
-    cudaFree(p->d_chain);
-    cudaFree(p->d_ticket);
-    cudaFree(p->d_stasks);
-    cudaFree(p->d_counts);
-    cudaFree(p->d_pre_counts);
-    cudaFree(p->d_err);
-    cudaFree(p->d_trim);
-    cudaFree(p->d_pre);
-    cudaFree(p->d_frame_pos);
-    cudaFree(p->d_n_frames);
-    cudaFree(p->d_ola_task);
-    cudaFree(p->d_ola_first);
+    for (void* d : p->owned) cudaFree(d);
     cudaFree(p->d_out_owned);
     delete p;
 }
 
-int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_assembly_params* params,
-                         const uint64_t* out_offsets, ctts_gpu_plan** out) {
+}  // extern "C"
+
+namespace {
+
+// Device / pinned allocation for one plan: individual cudaMallocs (resident plans), or bump
+// allocation from the context's grow-only arenas (ctts_gpu_synth_batch: no malloc/free per call).
+struct PlanAlloc {
+    ctts_gpu_ctx* ctx;
+    ctts_gpu_plan* p;
+    size_t d_used = 0, h_used = 0;
+    cudaError_t err = cudaSuccess;
+
+    static size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+    // phase 1 (arena mode): reserve() everything, then commit() grows the arenas once
+    template <typename T>
+    T* dev(size_t count) {
+        const size_t bytes = up256(std::max<size_t>(count, 1) * sizeof(T));
+        if (p->in_arena) {
+            T* r = reinterpret_cast<T*>(ctx->d_arena + d_used);
+            d_used += bytes;
+            return r;
+        }
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, bytes);
+        if (e != cudaSuccess) { err = e; return nullptr; }
+        p->owned.push_back(d);
+        return static_cast<T*>(d);
+    }
+};
+
+int ensure_arenas(ctts_gpu_ctx* ctx, size_t d_bytes, size_t h_bytes) {
+    if (d_bytes > ctx->d_arena_cap) {
+        cudaFree(ctx->d_arena);
+        ctx->d_arena = nullptr;
+        ctx->d_arena_cap = 0;
+        const size_t cap = d_bytes + d_bytes / 4;
+        if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_arena), cap) != cudaSuccess)
+            return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "device workspace of %zu bytes", cap);
+        ctx->d_arena_cap = cap;
+    }
+    if (h_bytes > ctx->h_arena_cap) {
+        if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
+        ctx->h_arena = nullptr;
+        ctx->h_arena_cap = 0;
+        const size_t cap = h_bytes + h_bytes / 4;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_arena), cap, cudaHostAllocDefault) != cudaSuccess)
+            return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "pinned staging of %zu bytes", cap);
+        ctx->h_arena_cap = cap;
+    }
+    return 0;
+}
+
+#define CUP(call)                                                                               \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            ctts_gpu_plan_destroy(p);                                                           \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? CTTS_GPU_ERR_OUT_OF_MEMORY : CTTS_GPU_ERR_CUDA, \
+                        "%s: %s", #call, cudaGetErrorString(e_));                               \
+        }                                                                                       \
+    } while (0)
+
+// The plan compiler, part 1.  chunk_samples == 0: one launch for the whole batch (best kernel
+// efficiency, the resident-plan path); > 0: utterances are cut, in slot order, into launches
+// of about that many output samples so that compiling / copying one chunk overlaps the
+// assembly of another (ctts_gpu_synth_batch).  Chunks are then built with build_chunk().
+int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_assembly_params* params,
+                 const uint64_t* out_offsets, uint64_t chunk_samples, bool in_arena, ctts_gpu_plan** out) {
     if (!ctx || !plan || !params || !out) return CTTS_GPU_ERR_INVALID_ARG;
     if (plan->n_utts && (!plan->utt_op_begin || !plan->speed)) return CTTS_GPU_ERR_INVALID_ARG;
     if (plan->n_ops && !plan->ops) return CTTS_GPU_ERR_INVALID_ARG;
@@ -321,26 +471,33 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
         return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "min_silence_samples < 10 is not memory-safe in the reference");
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
+    const uint32_t n = plan->n_utts;
 
-    std::vector<uint64_t> pre, bound;
-    int rc = compute_bounds(ctx, plan, &pre, &bound);
-    if (rc) return fail(ctx, rc, "invalid plan");
+    // ---- pass A
+    const uint64_t scr_samples = (uint64_t)(ctts::SCR_WORDS - 4) / 2 * 32;   // region length the shared trim mask covers
+    PlanScan sc;
+    uint32_t bad = 0;
+    int rc = scan_plan(ctx, plan, scr_samples, &sc, &bad);
+    if (rc) return fail(ctx, rc, "invalid plan (utterance %u)", bad);
+    if (sc.bad_factor) return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "WORD_END pitch factors must lie in [0, 2.05]");
+    const std::vector<uint64_t>&pre = sc.pre, &bound = sc.bound;
 
     ctts_gpu_plan* p = new ctts_gpu_plan();
     p->ctx = ctx;
-    p->n_utts = plan->n_utts;
+    p->n_utts = n;
     p->prm = *params;
     p->bounds = bound;
-    const uint32_t n = plan->n_utts;
+    p->in_arena = in_arena;
+    p->src = plan;
 
-    // output layout
+    // ---- output layout
     p->offsets.resize((size_t)n + 1);
     if (out_offsets) {
         for (uint32_t u = 0; u <= n; u++) p->offsets[u] = out_offsets[u];
         for (uint32_t u = 0; u < n; u++) {
             if ((out_offsets[u] & 7) || out_offsets[u + 1] < out_offsets[u] ||
                 out_offsets[u + 1] - out_offsets[u] < bound[u] || out_offsets[u + 1] - out_offsets[u] > 0xffffffffull) {
-                ctts_gpu_plan_destroy(p);
+                delete p;
                 return fail(ctx, CTTS_GPU_ERR_BOUNDS, "output slot %u is misaligned or smaller than its bound %llu", u,
                             (unsigned long long)bound[u]);
             }
@@ -354,153 +511,50 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
         p->offsets[n] = o;
     }
 
-    // ---- plan compile step 1: private copy of the ops; fade-outs that provably act on zeros
-    // (or on an empty buffer) become no-ops, so that a pause-only region never has to reach
-    // back into its predecessor's samples.  Trailing zeros: appended silence stays zero under
-    // apply_fade_out (0 * g == 0); a unit, or a WORD_END over a region that holds audio
-    // (trimming / the contour may move samples into the tail), resets the count.
-    std::vector<ctts_plan_op> ops(plan->ops, plan->ops + plan->n_ops);
-    uint32_t xf_max = 0;
-    uint64_t gather = 0;
-    bool bad_factor = false;
-    for (uint32_t u = 0; u < n; u++) {
-        uint64_t tz = 0, count_ub = 0;
-        bool audio = false;
-        for (uint32_t k = plan->utt_op_begin[u]; k < plan->utt_op_begin[u + 1]; k++) {
-            ctts_plan_op& op = ops[k];
-            switch (op.kind) {
-                case CTTS_OP_UNIT:
-                    count_ub += ctx->unit_cnt[op.a];
-                    gather += ctx->unit_cnt[op.a];
-                    if (ctx->unit_cnt[op.a]) { tz = 0; audio = true; }
-                    xf_max = std::max(xf_max, op.b);
-                    break;
-                case CTTS_OP_SILENCE:
-                    tz += op.a;
-                    count_ub += op.a;
-                    break;
-                case CTTS_OP_FADE_OUT:
-                    if (count_ub == 0 || tz >= op.a) op.kind = ctts::OP_NOP;
-                    break;
-                case CTTS_OP_WORD_END:
-                    if (audio) tz = 0;
-                    if (op.flags & CTTS_WE_INTON) {
-                        // the contour kernel stages CONTOUR_AHEAD samples past a tile: factors come from
-                        // clamp_pitch(1 +- max_pitch_change) (ctts.c:2589), 0.9 .. 1.1 as shipped
-                        const float lo = std::min(op.f0, std::min(op.f1, op.f2)), hi = std::max(op.f0, std::max(op.f1, op.f2));
-                        if (!(lo >= 0.0f) || !(hi <= 2.05f)) bad_factor = true;
-                    }
-                    break;
-                case CTTS_OP_MARK:
-                    audio = false;
-                    break;
-            }
-        }
-    }
-
-    if (bad_factor) {
-        ctts_gpu_plan_destroy(p);
-        return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "WORD_END pitch factors must lie in [0, 2.05]");
-    }
-
     // ---- shared-memory geometry
-    const uint32_t max_unit = ctx->max_unit;
+    const uint32_t max_unit = ctx->max_unit, xf_max = sc.xf_max;
     const uint32_t hcap = (uint32_t)up8(std::max<uint32_t>(std::min(xf_max, max_unit), 496)) + 8;
     if (hcap > 2 * ctts::SCR_WORDS) {
-        ctts_gpu_plan_destroy(p);
+        delete p;
         return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "crossfade of %u samples exceeds the staging capacity", xf_max);
     }
     auto smem_for = [&](uint32_t wcap) { return ctts::SMEM_HSTAGE + hcap * 2 + (wcap + 16) * 2; };
-    // regions (the samples between two word marks) and their upper bounds
-    struct Region { uint32_t op_begin, op_end; uint64_t bound; uint32_t units; };
-    std::vector<std::vector<Region>> regions(n);
-    uint64_t region_max = 0;
-    for (uint32_t u = 0; u < n; u++) {
-        Region r{plan->utt_op_begin[u], plan->utt_op_begin[u], 0, 0};
-        for (uint32_t k = plan->utt_op_begin[u]; k < plan->utt_op_begin[u + 1]; k++) {
-            const ctts_plan_op& op = ops[k];
-            if (op.kind == CTTS_OP_UNIT) { r.bound += ctx->unit_cnt[op.a]; r.units++; }
-            else if (op.kind == CTTS_OP_SILENCE) r.bound += op.a;
-            r.op_end = k + 1;
-            if (op.kind == CTTS_OP_MARK) {
-                regions[u].push_back(r);
-                region_max = std::max(region_max, r.bound);
-                r = Region{k + 1, k + 1, 0, 0};
-            }
-        }
-        if (r.op_end > r.op_begin) {
-            regions[u].push_back(r);
-            region_max = std::max(region_max, r.bound);
-        }
-    }
     // window: as large as the target occupancy allows, no larger than the largest region needs
     int want_ctas = 3;
     if (const char* e = getenv("CTTS_GPU_CTAS_PER_SM")) want_ctas = std::max(1, std::min(8, atoi(e)));
     const uint32_t budget = std::min<uint32_t>((uint32_t)ctx->smem_optin, (uint32_t)(ctx->smem_per_sm / want_ctas - 1024));
-    uint32_t wcap = (uint32_t)up8(std::min<uint64_t>(region_max + 16, 1u << 20));
+    uint32_t wcap = (uint32_t)up8(std::min<uint64_t>(sc.region_max + 16, 1u << 20));
     if (const char* e = getenv("CTTS_GPU_WINDOW")) wcap = (uint32_t)up8(std::max(256, atoi(e)));   // tests: force the HBM path
     while (wcap > 1024 && smem_for(wcap) > budget) wcap -= 256;
     wcap &= ~7u;
     if (smem_for(wcap) > (uint32_t)ctx->smem_optin) {
-        ctts_gpu_plan_destroy(p);
+        delete p;
         return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "crossfade / unit sizes (%u, %u samples) do not fit shared memory", xf_max, max_unit);
     }
     p->wcap = wcap;
     p->hcap = hcap;
-    p->scr_words = ctts::SCR_WORDS;
     p->smem_bytes = smem_for(wcap);
 
-    // ---- plan compile step 2: region tasks.  A region with no unit (a pause) or a tiny one is
-    // appended to the task before it while the sum still fits the window.
-    struct HostTask { uint32_t utt, op_begin, op_end; uint64_t bound; uint32_t index_in_utt; uint32_t region_max; };
-    std::vector<std::vector<HostTask>> utt_tasks(n);
-    uint32_t max_tasks_per_utt = 0;
-    uint64_t n_tasks = 0;
-    for (uint32_t u = 0; u < n; u++) {
-        auto& T = utt_tasks[u];
-        for (const Region& r : regions[u]) {
-            const bool tiny = r.units == 0 || r.bound <= 2048;
-            if (!T.empty() && tiny && T.back().bound + r.bound <= wcap) {
-                T.back().op_end = r.op_end;
-                T.back().bound += r.bound;
-                T.back().region_max = (uint32_t)std::max<uint64_t>(T.back().region_max, r.bound);
-            } else {
-                T.push_back(HostTask{u, r.op_begin, r.op_end, r.bound, (uint32_t)T.size(),
-                                     (uint32_t)std::min<uint64_t>(r.bound, 0xffffffffull)});
-            }
-        }
-        max_tasks_per_utt = std::max<uint32_t>(max_tasks_per_utt, (uint32_t)T.size());
-        n_tasks += T.size();
-    }
-    if (n_tasks > 0x7fffffffull) {
-        ctts_gpu_plan_destroy(p);
-        return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "too many region tasks");
-    }
-
-    // slots: pre-stretch buffers and WSOLA tasks (utterances longest first)
+    // ---- slots of stretched utterances (longest first) and WSOLA tasks
     std::vector<ctts::StretchTask> stasks;
     std::vector<uint32_t> ola_task, ola_first;
     p->pre_off.assign(n, ~0ull);
     p->pre_cap.assign(n, 0);
     uint64_t pre_total = 0, pos_total = 0;
-    std::vector<uint32_t> order(n);
-    std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pre[a] > pre[b]; });
-    std::vector<uint64_t> slot_off(n);
-    std::vector<uint32_t> slot_cap(n), to_pre(n, 0);
-    for (uint32_t i = 0; i < n; i++) {
-        uint32_t u = order[i];
-        uint32_t hop = 0;
-        if (needs_stretch(plan->speed[u], &hop)) {
+    if (sc.any_stretch) {
+        std::vector<uint32_t> order(n);
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pre[a] > pre[b]; });
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t u = order[i];
+            uint32_t hop = 0;
+            if (!needs_stretch(plan->speed[u], &hop)) continue;
             if (pre[u] + 16 > 0xffffffffull) {
-                ctts_gpu_plan_destroy(p);
+                delete p;
                 return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "utterance %u too long", u);
             }
-            to_pre[u] = 1;
-            slot_off[u] = pre_total;
-            slot_cap[u] = (uint32_t)(up8(pre[u]) + 8);
             p->pre_off[u] = pre_total;
-            p->pre_cap[u] = slot_cap[u];
+            p->pre_cap[u] = (uint32_t)(up8(pre[u]) + 8);
             ctts::StretchTask st;
             st.utt = u;
             st.hop = hop;
@@ -509,124 +563,355 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
             st.out_cap = (uint32_t)(p->offsets[u + 1] - p->offsets[u]);
             st.pos_off = (uint32_t)pos_total;
             st.max_frames = (uint32_t)(pre[u] > 512 ? (pre[u] - 512) / 128 + 1 : 1);
-            uint64_t used_max = (uint64_t)st.max_frames * hop + 512;
-            uint32_t per_block = ctts::OLA_THREADS * ctts::OLA_SPT;
+            const uint64_t used_max = (uint64_t)st.max_frames * hop + 512;
+            const uint32_t per_block = ctts::OLA_THREADS * ctts::OLA_SPT;
             for (uint64_t f = 0; f < used_max; f += per_block) {
                 ola_task.push_back((uint32_t)stasks.size());
                 ola_first.push_back((uint32_t)f);
             }
             stasks.push_back(st);
-            pre_total += slot_cap[u];
+            pre_total += p->pre_cap[u];
             pos_total += st.max_frames;
             if (pos_total > 0xffffffffull) {
-                ctts_gpu_plan_destroy(p);
+                delete p;
                 return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "too many WSOLA frames in one batch");
             }
-        } else {
-            slot_off[u] = p->offsets[u];
-            slot_cap[u] = (uint32_t)(p->offsets[u + 1] - p->offsets[u]);
         }
     }
     p->n_stretch = (uint32_t)stasks.size();
     p->n_ola_blocks = (uint32_t)ola_task.size();
+    if (p->n_stretch) chunk_samples = 0;   // the stretch kernels run over the whole batch
 
-    // ticket order: region-major (task k of every utterance before task k+1 of any), so that a
-    // task's predecessor has normally finished long before the task starts
-    std::vector<ctts::RegionTask> tasks;
-    tasks.reserve(n_tasks);
-    std::vector<int32_t> last_index(n, -1);
-    uint32_t n_big = 0, n_global = 0;
-    const uint64_t scr_samples = (uint64_t)(ctts::SCR_WORDS - 4) / 2 * 32;   // region length the shared trim mask covers
-    uint64_t big_region_max = 0;
-    std::vector<uint32_t> row(n);
-    for (uint32_t k = 0; k < max_tasks_per_utt; k++) {
-        // inside a row: longest task first (it is the one a successor may have to wait for, and
-        // longest-first balances the tail of the launch)
-        uint32_t m = 0;
-        for (uint32_t i = 0; i < n; i++)
-            if (k < utt_tasks[order[i]].size()) row[m++] = order[i];
-        std::stable_sort(row.begin(), row.begin() + m,
-                         [&](uint32_t a, uint32_t b) { return utt_tasks[a][k].bound > utt_tasks[b][k].bound; });
-        for (uint32_t i = 0; i < m; i++) {
-            const uint32_t u = row[i];
-            const HostTask& h = utt_tasks[u][k];
-            ctts::RegionTask t{};
-            t.utt = u;
-            t.op_begin = h.op_begin;
-            t.op_end = h.op_end;
-            t.bound = (uint32_t)std::min<uint64_t>(h.bound, 0xffffffffull);
-            t.pred = last_index[u];
-            t.flags = (k + 1 == utt_tasks[u].size() ? ctts::TASK_LAST : 0u) | (to_pre[u] ? ctts::TASK_TO_PRE : 0u);
-            if (h.bound > wcap) { t.flags |= ctts::TASK_GLOBAL; n_global++; }
-            t.dst_cap = slot_cap[u];
-            t.dst_off = slot_off[u];
-            t.big = 0xffffffffu;
-            if (h.region_max > scr_samples) {
-                t.big = n_big++;
-                big_region_max = std::max<uint64_t>(big_region_max, h.region_max);
+    // ---- chunks: contiguous utterance ranges of about chunk_samples output samples
+    if (chunk_samples == 0 || n == 0) {
+        PlanChunk ch;
+        ch.utt_end = n;
+        p->chunks.push_back(ch);
+    } else {
+        uint64_t acc = 0;
+        uint32_t u0 = 0;
+        for (uint32_t u = 0; u < n; u++) {
+            acc += bound[u];
+            if (acc >= chunk_samples || u + 1 == n) {
+                PlanChunk ch;
+                ch.utt_begin = u0;
+                ch.utt_end = u + 1;
+                p->chunks.push_back(ch);
+                u0 = u + 1;
+                acc = 0;
             }
-            last_index[u] = (int32_t)tasks.size();
-            tasks.push_back(t);
         }
     }
-    p->n_tasks = (uint32_t)tasks.size();
-    p->n_global_tasks = n_global;
-    if (n_big) p->trim_words = (uint32_t)(2 * ((big_region_max + 31) / 32) + 8);
+    const uint32_t n_chunks = (uint32_t)p->chunks.size();
+    if (sc.n_regions + 1 > 0x7fffffffull) {
+        delete p;
+        return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "too many region tasks");
+    }
 
-#define CUP(call)                                                                               \
-    do {                                                                                        \
-        cudaError_t e_ = (call);                                                                \
-        if (e_ != cudaSuccess) {                                                                \
-            ctts_gpu_plan_destroy(p);                                                           \
-            return fail(ctx, e_ == cudaErrorMemoryAllocation ? CTTS_GPU_ERR_OUT_OF_MEMORY : CTTS_GPU_ERR_CUDA, \
-                        "%s: %s", #call, cudaGetErrorString(e_));                               \
-        }                                                                                       \
-    } while (0)
-    auto up = [&](auto** d, const auto& h) -> cudaError_t {
-        using T = typename std::remove_reference<decltype(h[0])>::type;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(d), std::max<size_t>(h.size(), 1) * sizeof(T));
-        if (e != cudaSuccess || h.empty()) return e;
-        return cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
-    };
-    CUP(up(&p->d_ops, ops));
-    CUP(up(&p->d_tasks, tasks));
-    CUP(up(&p->d_stasks, stasks));
-    CUP(up(&p->d_ola_task, ola_task));
-    CUP(up(&p->d_ola_first, ola_first));
-    CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_counts), std::max<size_t>(n, 1) * 4));
-    CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_pre_counts), std::max<size_t>(n, 1) * 4));
-    CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_err), std::max<size_t>(n, 1) * 4));
-    if (p->trim_words) CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_trim), (size_t)n_big * p->trim_words * 4));
-    CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_chain), std::max<size_t>(tasks.size(), 1) * 8));
-    CUP(cudaMemsetAsync(p->d_chain, 0, std::max<size_t>(tasks.size(), 1) * 8, ctx->stream));
-    CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_ticket), 4));
+    // ---- workspace.  The private op copy and the tasks are built directly in (pinned) staging.
+    const size_t ops_bytes = std::max<size_t>(plan->n_ops, 1) * sizeof(ctts_plan_op);
+    const size_t tasks_cap = (size_t)sc.n_regions + 1;   // merging only lowers the count
+    const size_t tasks_bytes = tasks_cap * sizeof(ctts::RegionTask);
+    if (in_arena) {
+        // device side: ops, tasks, chain, tickets, counts, pre_counts, err (+ the stretch buffers)
+        size_t d_need = PlanAlloc::up256(ops_bytes) + PlanAlloc::up256(tasks_bytes) + PlanAlloc::up256(tasks_cap * 8) +
+                        PlanAlloc::up256((size_t)n_chunks * 4) + 3 * PlanAlloc::up256(std::max<size_t>(n, 1) * 4) + 65536;
+        if (!stasks.empty())
+            d_need += PlanAlloc::up256(stasks.size() * sizeof(ctts::StretchTask)) + 2 * PlanAlloc::up256(ola_task.size() * 4 + 4) +
+                      PlanAlloc::up256(pre_total * 2 + 16) + PlanAlloc::up256(pos_total * 4 + 4) + PlanAlloc::up256(stasks.size() * 4) + 4096;
+        const size_t h_need = PlanAlloc::up256(ops_bytes) + PlanAlloc::up256(tasks_bytes) + 4096;
+        rc = ensure_arenas(ctx, d_need, h_need);
+        if (rc) { delete p; return rc; }
+        p->h_ops = reinterpret_cast<ctts_plan_op*>(ctx->h_arena);
+        p->h_tasks = reinterpret_cast<ctts::RegionTask*>(ctx->h_arena + PlanAlloc::up256(ops_bytes));
+    } else {
+        p->ops_vec.resize(std::max<size_t>(plan->n_ops, 1));
+        p->tasks_vec.resize(tasks_cap);
+        p->h_ops = p->ops_vec.data();
+        p->h_tasks = p->tasks_vec.data();
+    }
+    PlanAlloc al{ctx, p};
+    p->d_ops = al.dev<ctts_plan_op>(plan->n_ops);
+    p->d_tasks = al.dev<ctts::RegionTask>(tasks_cap);
+    p->d_chain = al.dev<unsigned long long>(tasks_cap);
+    p->d_ticket = al.dev<uint32_t>(n_chunks);
+    p->d_counts = al.dev<uint32_t>(n);
+    p->d_pre_counts = al.dev<uint32_t>(n);
+    p->d_err = al.dev<uint32_t>(n);
+    if (sc.n_big_regions) {
+        // rare (regions longer than ~51 k samples): always a separate allocation
+        p->trim_words = (uint32_t)(2 * ((sc.big_region_max + 31) / 32) + 8);
+        p->big_cap = (uint32_t)sc.n_big_regions;
+        void* d = nullptr;
+        if (cudaMalloc(&d, (size_t)p->big_cap * p->trim_words * 4) != cudaSuccess) al.err = cudaErrorMemoryAllocation;
+        else { p->owned.push_back(d); p->d_trim = static_cast<uint32_t*>(d); }
+    }
     if (p->n_stretch) {
-        CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_pre), pre_total * sizeof(int16_t)));
-        CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_frame_pos), std::max<uint64_t>(pos_total, 1) * 4));
-        CUP(cudaMalloc(reinterpret_cast<void**>(&p->d_n_frames), (size_t)p->n_stretch * 4));
+        p->d_stasks = al.dev<ctts::StretchTask>(stasks.size());
+        p->d_ola_task = al.dev<uint32_t>(ola_task.size());
+        p->d_ola_first = al.dev<uint32_t>(ola_first.size());
+        p->d_pre = al.dev<int16_t>(pre_total);
+        p->d_frame_pos = al.dev<uint32_t>(pos_total);
+        p->d_n_frames = al.dev<uint32_t>(p->n_stretch);
+    }
+    if (al.err != cudaSuccess) {
+        ctts_gpu_plan_destroy(p);
+        return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "plan workspace: %s", cudaGetErrorString(al.err));
+    }
+    cudaStream_t st = ctx->stream;
+    CUP(cudaMemsetAsync(p->d_chain, 0, tasks_cap * 8, st));
+    if (p->n_stretch) {
+        CUP(cudaMemcpyAsync(p->d_stasks, stasks.data(), stasks.size() * sizeof(ctts::StretchTask), cudaMemcpyHostToDevice, st));
+        CUP(cudaMemcpyAsync(p->d_ola_task, ola_task.data(), ola_task.size() * 4, cudaMemcpyHostToDevice, st));
+        CUP(cudaMemcpyAsync(p->d_ola_first, ola_first.data(), ola_first.size() * 4, cudaMemcpyHostToDevice, st));
+        CUP(cudaStreamSynchronize(st));   // the vectors above are about to go out of scope
     }
     CUP(cudaFuncSetAttribute(ctts::assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
-    // the host vectors above must outlive the async copies
-    CUP(cudaStreamSynchronize(ctx->stream));
-#undef CUP
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctts::assemble_kernel, ctts::ASM_THREADS, p->smem_bytes) != cudaSuccess || occ < 1)
+        occ = 1;
+    p->occ = (uint32_t)occ;
 
-    p->info.kernel_launches = 1 + (p->n_stretch ? 2 : 0);
+    p->info.kernel_launches = n_chunks + (p->n_stretch ? 2 : 0);
     p->info.n_stretch = p->n_stretch;
-    p->info.gather_samples = gather;
     p->info.bound_samples = std::accumulate(bound.begin(), bound.end(), (uint64_t)0);
     p->info.smem_bytes = p->smem_bytes;
     p->info.window_samples = wcap;
     p->info.halo_samples = hcap;
     p->info.threads = ctts::ASM_THREADS;
-    {
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctts::assemble_kernel, ctts::ASM_THREADS, p->smem_bytes) != cudaSuccess || occ < 1)
-            occ = 1;
-        p->grid = (uint32_t)std::min<uint64_t>((uint64_t)occ * (uint64_t)ctx->sm_count, std::max<uint32_t>(p->n_tasks, 1));
-        p->info.n_tasks = p->n_tasks;
-        p->info.n_global_tasks = p->n_global_tasks;
-        p->info.ctas_per_sm = (uint32_t)occ;
-        p->info.grid = p->grid;
+    p->info.ctas_per_sm = p->occ;
+    *out = p;
+    return CTTS_GPU_OK;
+}
+
+// The plan compiler, part 2: private op copy (with provably dead fade-outs turned into
+// no-ops), regions -> tasks, ticket order, upload -- for chunk c.  Chunks are built in order.
+int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c) {
+    if (c != p->built_chunks || c >= p->chunks.size() || !p->src) return CTTS_GPU_ERR_INVALID_ARG;
+    const ctts_batch_plan* plan = p->src;
+    PlanChunk& ch = p->chunks[c];
+    const uint32_t u0 = ch.utt_begin, u1 = ch.utt_end;
+    const uint32_t* ub = plan->utt_op_begin;
+    const std::vector<uint32_t>& ucnt = ctx->unit_cnt;
+    const uint32_t wcap = p->wcap;
+    const uint64_t scr_samples = (uint64_t)(ctts::SCR_WORDS - 4) / 2 * 32;
+    ctts_plan_op* h_ops = p->h_ops;
+    const uint32_t op_lo = u1 > u0 ? ub[u0] : 0, op_hi = u1 > u0 ? ub[u1] : 0;
+    if (op_hi > op_lo) memcpy(h_ops + op_lo, plan->ops + op_lo, (size_t)(op_hi - op_lo) * sizeof(ctts_plan_op));
+
+    // A fade-out that provably acts on zeros (or on an empty buffer) becomes a no-op, so that a
+    // pause-only region never has to reach back into its predecessor's samples.  Trailing zeros:
+    // appended silence stays zero under apply_fade_out (0 * g == 0); a unit, or a WORD_END over a
+    // region that holds audio (trimming / the contour may move samples into the tail), resets it.
+    // A region with no unit (a pause) or a tiny one is appended to the task before it while the
+    // sum still fits the window.
+    struct HostTask { uint32_t op_begin, op_end; uint64_t bound; uint32_t region_max; };
+    std::vector<HostTask> ht;
+    std::vector<uint32_t> ht_begin(u1 - u0 + 1, 0);   // CSR: tasks of utterance u0 + i
+    uint32_t max_rows = 0;
+    for (uint32_t u = u0; u < u1; u++) {
+        ht_begin[u - u0] = (uint32_t)ht.size();
+        uint64_t tz = 0, count_ub = 0, rb = 0, L = 0;
+        uint32_t r_units = 0, r_begin = ub[u];
+        bool audio = false;
+        auto close_region = [&](uint32_t r_end) {
+            if (r_end == r_begin) return;
+            const bool tiny = r_units == 0 || rb <= 2048;
+            if (ht.size() > ht_begin[u - u0] && tiny && ht.back().bound + rb <= wcap) {
+                ht.back().op_end = r_end;
+                ht.back().bound += rb;
+                ht.back().region_max = (uint32_t)std::max<uint64_t>(ht.back().region_max, rb);
+            } else {
+                ht.push_back(HostTask{r_begin, r_end, rb, (uint32_t)std::min<uint64_t>(rb, 0xffffffffull)});
+            }
+            r_begin = r_end;
+            rb = 0;
+            r_units = 0;
+            L = 0;
+        };
+        for (uint32_t k = ub[u]; k < ub[u + 1]; k++) {
+            ctts_plan_op& op = h_ops[k];
+            switch (op.kind) {
+                case CTTS_OP_UNIT: {
+                    const uint32_t cn = ucnt[op.a];
+                    count_ub += cn;
+                    p->gather += cn;
+                    rb += unit_append_bound(op, cn, L);
+                    r_units++;
+                    if (cn) { tz = 0; audio = true; }
+                    break;
+                }
+                case CTTS_OP_SILENCE:
+                    tz += op.a;
+                    count_ub += op.a;
+                    rb += op.a;
+                    L += op.a;
+                    break;
+                case CTTS_OP_FADE_OUT:
+                    if (count_ub == 0 || tz >= op.a) op.kind = ctts::OP_NOP;
+                    break;
+                case CTTS_OP_WORD_END:
+                    if (audio) tz = 0;
+                    if (op.flags & CTTS_WE_TRIM) L = 0;
+                    break;
+                case CTTS_OP_MARK:
+                    audio = false;
+                    close_region(k + 1);
+                    break;
+            }
+        }
+        close_region(ub[u + 1]);
+        max_rows = std::max<uint32_t>(max_rows, (uint32_t)ht.size() - ht_begin[u - u0]);
+    }
+    ht_begin[u1 - u0] = (uint32_t)ht.size();
+
+    // ticket order: region-major (task k of every utterance before task k+1 of any), inside a
+    // row longest first (it is the one a successor may have to wait for, and longest-first
+    // balances the tail of the launch)
+    ch.task_begin = p->n_tasks;
+    uint32_t nt = p->n_tasks;
+    std::vector<int32_t> last_index(u1 - u0, -1);
+    std::vector<uint32_t> row(u1 - u0);
+    for (uint32_t k = 0; k < max_rows; k++) {
+        uint32_t m = 0;
+        for (uint32_t i = 0; i < u1 - u0; i++)
+            if (k < ht_begin[i + 1] - ht_begin[i]) row[m++] = i;
+        std::sort(row.begin(), row.begin() + m, [&](uint32_t a, uint32_t b) {
+            const uint64_t ba = ht[ht_begin[a] + k].bound, bb = ht[ht_begin[b] + k].bound;
+            return ba != bb ? ba > bb : a < b;
+        });
+        for (uint32_t i = 0; i < m; i++) {
+            const uint32_t ui = row[i], u = u0 + ui;
+            const HostTask& h = ht[ht_begin[ui] + k];
+            ctts::RegionTask t{};
+            t.utt = u;
+            t.op_begin = h.op_begin;
+            t.op_end = h.op_end;
+            t.bound = (uint32_t)std::min<uint64_t>(h.bound, 0xffffffffull);
+            t.pred = last_index[ui];
+            const bool stretched = p->pre_off[u] != ~0ull;
+            t.flags = (k + 1 == ht_begin[ui + 1] - ht_begin[ui] ? ctts::TASK_LAST : 0u) | (stretched ? ctts::TASK_TO_PRE : 0u);
+            if (h.bound > wcap) { t.flags |= ctts::TASK_GLOBAL; p->n_global_tasks++; }
+            t.dst_cap = stretched ? (uint32_t)p->pre_cap[u] : (uint32_t)(p->offsets[u + 1] - p->offsets[u]);
+            t.dst_off = stretched ? p->pre_off[u] : p->offsets[u];
+            t.big = 0xffffffffu;
+            if (h.region_max > scr_samples) {
+                if (p->n_big >= p->big_cap) return fail(ctx, CTTS_GPU_ERR_DEVICE, "internal: trim scratch slots");
+                t.big = p->n_big++;
+            }
+            last_index[ui] = (int32_t)(nt - ch.task_begin);   // index inside this chunk's launch
+            p->h_tasks[nt++] = t;
+        }
+    }
+    ch.n_tasks = nt - ch.task_begin;
+    p->n_tasks = nt;
+    ch.grid = (uint32_t)std::min<uint64_t>((uint64_t)p->occ * (uint64_t)ctx->sm_count, std::max<uint32_t>(ch.n_tasks, 1));
+
+    cudaStream_t st = ctx->stream;
+    if (op_hi > op_lo)
+        CU(ctx, cudaMemcpyAsync(p->d_ops + op_lo, h_ops + op_lo, (size_t)(op_hi - op_lo) * sizeof(ctts_plan_op), cudaMemcpyHostToDevice, st));
+    if (ch.n_tasks)
+        CU(ctx, cudaMemcpyAsync(p->d_tasks + ch.task_begin, p->h_tasks + ch.task_begin, (size_t)ch.n_tasks * sizeof(ctts::RegionTask),
+                                cudaMemcpyHostToDevice, st));
+    p->built_chunks++;
+    p->info.n_tasks = p->n_tasks;
+    p->info.n_global_tasks = p->n_global_tasks;
+    p->info.gather_samples = p->gather;
+    p->info.grid = std::max(p->info.grid, ch.grid);
+    if (p->built_chunks == p->chunks.size()) {
+        p->src = nullptr;
+        if (!p->in_arena) {
+            // pageable staging must outlive the async copies
+            CU(ctx, cudaStreamSynchronize(st));
+            std::vector<ctts_plan_op>().swap(p->ops_vec);
+            std::vector<ctts::RegionTask>().swap(p->tasks_vec);
+        }
+    }
+    return CTTS_GPU_OK;
+}
+#undef CUP
+
+// Enqueue one chunk's assembly kernel on the context stream.
+int launch_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, int16_t* d_pcm_out) {
+    const PlanChunk& ch = p->chunks[c];
+    if (ch.n_tasks == 0) return CTTS_GPU_OK;
+    ctts::AsmArgs a{};
+    a.pool = ctx->d_pool;
+    a.unit_off = ctx->d_unit_off;
+    a.unit_cnt = ctx->d_unit_cnt;
+    a.n_units = ctx->n_units;
+    a.tab.fade_out = ctx->d_tables;
+    a.tab.fade_in = ctx->d_tables + 1024;
+    a.tab.sine = ctx->d_tables + 2048;
+    a.tab.hann256 = ctx->d_tables + 3072;
+    a.tab.hann512 = ctx->d_tables + 3328;
+    a.tab.xfade4 = reinterpret_cast<const float4*>(ctx->d_tables + 3840);
+    a.ops = p->d_ops;
+    a.tasks = p->d_tasks + ch.task_begin;
+    a.n_tasks = ch.n_tasks;
+    a.dst_final = d_pcm_out;
+    a.dst_pre = p->d_pre;
+    a.out_counts = p->d_counts;
+    a.pre_counts = p->d_pre_counts;
+    a.err = p->d_err;
+    a.trim_scratch = p->d_trim;
+    a.trim_scratch_words = p->trim_words;
+    a.chain = p->d_chain + ch.task_begin;
+    a.ticket = p->d_ticket + c;
+    a.epoch = p->epoch;
+    a.prm = p->prm;
+    a.wcap = p->wcap;
+    a.hcap = p->hcap;
+    ctts::assemble_kernel<<<ch.grid, ctts::ASM_THREADS, p->smem_bytes, ctx->stream>>>(a);
+    CU(ctx, cudaGetLastError());
+    return CTTS_GPU_OK;
+}
+
+int begin_run(ctts_gpu_ctx* ctx, ctts_gpu_plan* p) {
+    cudaStream_t st = ctx->stream;
+    CU(ctx, cudaMemsetAsync(p->d_counts, 0, (size_t)p->n_utts * 4, st));
+    CU(ctx, cudaMemsetAsync(p->d_pre_counts, 0, (size_t)p->n_utts * 4, st));
+    CU(ctx, cudaMemsetAsync(p->d_err, 0, (size_t)p->n_utts * 4, st));
+    CU(ctx, cudaMemsetAsync(p->d_ticket, 0, p->chunks.size() * 4, st));
+    p->epoch++;
+    if (p->epoch == 0) p->epoch = 1;   // (2^32 runs later) the chain words of the last lap are long gone
+    return CTTS_GPU_OK;
+}
+
+int launch_stretch(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, int16_t* d_pcm_out) {
+    if (!p->n_stretch) return CTTS_GPU_OK;
+    cudaStream_t st = ctx->stream;
+    ctts::WsolaArgs w{};
+    w.tasks = p->d_stasks;
+    w.n_tasks = p->n_stretch;
+    w.pre = p->d_pre;
+    w.pre_counts = p->d_pre_counts;
+    w.out = d_pcm_out;
+    w.out_counts = p->d_counts;
+    w.frame_pos = p->d_frame_pos;
+    w.n_frames = p->d_n_frames;
+    w.hann512 = ctx->d_tables + 3328;
+    w.ola_block_task = p->d_ola_task;
+    w.ola_block_first = p->d_ola_first;
+    ctts::wsola_search_kernel<<<p->n_stretch, ctts::WS_THREADS, 0, st>>>(w);
+    CU(ctx, cudaGetLastError());
+    ctts::wsola_ola_kernel<<<p->n_ola_blocks, ctts::OLA_THREADS, 0, st>>>(w);
+    CU(ctx, cudaGetLastError());
+    return CTTS_GPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_assembly_params* params,
+                         const uint64_t* out_offsets, ctts_gpu_plan** out) {
+    ctts_gpu_plan* p = nullptr;
+    int rc = prepare_plan(ctx, plan, params, out_offsets, 0, false, &p);
+    for (uint32_t c = 0; !rc && c < p->chunks.size(); c++) rc = build_chunk(ctx, p, c);
+    if (rc) {
+        ctts_gpu_plan_destroy(p);
+        return rc;
     }
     *out = p;
     return CTTS_GPU_OK;
@@ -657,65 +942,10 @@ int ctts_gpu_plan_run(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, int16_t* d_pcm_out) {
     }
     p->d_out_last = d_pcm_out;
     if (p->n_utts == 0) return CTTS_GPU_OK;
-    cudaStream_t st = ctx->stream;
-    CU(ctx, cudaMemsetAsync(p->d_counts, 0, (size_t)p->n_utts * 4, st));
-    CU(ctx, cudaMemsetAsync(p->d_pre_counts, 0, (size_t)p->n_utts * 4, st));
-    CU(ctx, cudaMemsetAsync(p->d_err, 0, (size_t)p->n_utts * 4, st));
-    CU(ctx, cudaMemsetAsync(p->d_ticket, 0, 4, st));
-    p->epoch++;
-    if (p->epoch == 0) p->epoch = 1;   // (2^32 runs later) the chain words of the last lap are long gone
-
-    if (p->n_tasks) {
-        ctts::AsmArgs a{};
-        a.pool = ctx->d_pool;
-        a.unit_off = ctx->d_unit_off;
-        a.unit_cnt = ctx->d_unit_cnt;
-        a.n_units = ctx->n_units;
-        a.tab.fade_out = ctx->d_tables;
-        a.tab.fade_in = ctx->d_tables + 1024;
-        a.tab.sine = ctx->d_tables + 2048;
-        a.tab.hann256 = ctx->d_tables + 3072;
-        a.tab.hann512 = ctx->d_tables + 3328;
-        a.tab.xfade4 = reinterpret_cast<const float4*>(ctx->d_tables + 3840);
-        a.ops = p->d_ops;
-        a.tasks = p->d_tasks;
-        a.n_tasks = p->n_tasks;
-        a.dst_final = d_pcm_out;
-        a.dst_pre = p->d_pre;
-        a.out_counts = p->d_counts;
-        a.pre_counts = p->d_pre_counts;
-        a.err = p->d_err;
-        a.trim_scratch = p->d_trim;
-        a.trim_scratch_words = p->trim_words;
-        a.chain = p->d_chain;
-        a.ticket = p->d_ticket;
-        a.epoch = p->epoch;
-        a.prm = p->prm;
-        a.wcap = p->wcap;
-        a.hcap = p->hcap;
-        ctts::assemble_kernel<<<p->grid, ctts::ASM_THREADS, p->smem_bytes, st>>>(a);
-        CU(ctx, cudaGetLastError());
-    }
-
-    if (p->n_stretch) {
-        ctts::WsolaArgs w{};
-        w.tasks = p->d_stasks;
-        w.n_tasks = p->n_stretch;
-        w.pre = p->d_pre;
-        w.pre_counts = p->d_pre_counts;
-        w.out = d_pcm_out;
-        w.out_counts = p->d_counts;
-        w.frame_pos = p->d_frame_pos;
-        w.n_frames = p->d_n_frames;
-        w.hann512 = ctx->d_tables + 3328;
-        w.ola_block_task = p->d_ola_task;
-        w.ola_block_first = p->d_ola_first;
-        ctts::wsola_search_kernel<<<p->n_stretch, ctts::WS_THREADS, 0, st>>>(w);
-        CU(ctx, cudaGetLastError());
-        ctts::wsola_ola_kernel<<<p->n_ola_blocks, ctts::OLA_THREADS, 0, st>>>(w);
-        CU(ctx, cudaGetLastError());
-    }
-    return CTTS_GPU_OK;
+    int rc = begin_run(ctx, p);
+    for (uint32_t c = 0; !rc && c < p->chunks.size(); c++) rc = launch_chunk(ctx, p, c, d_pcm_out);
+    if (!rc) rc = launch_stretch(ctx, p, d_pcm_out);
+    return rc;
 }
 
 int ctts_gpu_plan_read_counts(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t* out_counts) {
@@ -754,10 +984,18 @@ int ctts_gpu_plan_read_pre(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t u, int1
 int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_assembly_params* params,
                          int16_t* pcm_out, const uint64_t* out_offsets, uint32_t* out_counts) {
     if (!ctx || !plan || !params || !pcm_out || !out_offsets || !out_counts) return CTTS_GPU_ERR_INVALID_ARG;
+    const bool trace = getenv("CTTS_GPU_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    auto t0 = now();
+    // launches of ~256 MB of PCM: the device->host copy of one chunk overlaps the assembly of the next
+    uint64_t chunk_samples = 128ull << 20;
+    if (const char* e = getenv("CTTS_GPU_CHUNK_SAMPLES")) chunk_samples = strtoull(e, nullptr, 10);
     ctts_gpu_plan* p = nullptr;
-    int rc = ctts_gpu_plan_create(ctx, plan, params, out_offsets, &p);
+    int rc = prepare_plan(ctx, plan, params, out_offsets, chunk_samples, true, &p);
     if (rc) return rc;
-    uint64_t total = p->offsets[p->n_utts];
+    auto t1 = now();
+    const uint64_t total = p->offsets[p->n_utts];
     if (total > ctx->batch_out_cap) {
         cudaFree(ctx->d_batch_out);
         ctx->d_batch_out = nullptr;
@@ -769,17 +1007,61 @@ int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
         }
         ctx->batch_out_cap = total;
     }
-    rc = ctts_gpu_plan_run(ctx, p, ctx->d_batch_out);
-    if (!rc) rc = ctts_gpu_plan_read_counts(ctx, p, out_counts);
-    if (!rc && total) {
-        // one copy of the occupied span; slots keep their caller-chosen offsets
-        uint64_t lo = out_offsets[0];
-        cudaError_t e = cudaMemcpyAsync(pcm_out + lo, ctx->d_batch_out + lo, (total - lo) * sizeof(int16_t),
-                                        cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = fail(ctx, CTTS_GPU_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
+    int16_t* d_out = ctx->d_batch_out;
+    p->d_out_last = d_out;
+    const uint32_t nc = (uint32_t)p->chunks.size();
+    auto cu_fail = [&](cudaError_t e, const char* what) {
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        ctts_gpu_plan_destroy(p);
+        return fail(ctx, CTTS_GPU_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    };
+    if (!ctx->copy_stream) {
+        cudaError_t e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return cu_fail(e, "copy stream");
     }
+    while (ctx->events.size() < nc) {
+        cudaEvent_t ev;
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return cu_fail(e, "event");
+        ctx->events.push_back(ev);
+    }
+    if (p->n_utts) {
+        rc = begin_run(ctx, p);
+        for (uint32_t c = 0; !rc && c < nc; c++) {
+            // compile + upload chunk c on the host while the device assembles chunk c-1
+            rc = build_chunk(ctx, p, c);
+            if (!rc) rc = launch_chunk(ctx, p, c, d_out);
+            if (rc) break;
+            if (p->n_stretch) continue;   // single chunk: copied after the stretch kernels below
+            // the chunk's slots are one contiguous span; copy it while the next chunk is assembled
+            const PlanChunk& ch = p->chunks[c];
+            const uint64_t lo = p->offsets[ch.utt_begin], hi = p->offsets[ch.utt_end];
+            cudaError_t e = cudaEventRecord(ctx->events[c], ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->events[c], 0);
+            if (e == cudaSuccess && hi > lo)
+                e = cudaMemcpyAsync(pcm_out + lo, d_out + lo, (hi - lo) * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+            if (e != cudaSuccess) return cu_fail(e, "D2H");
+        }
+        if (!rc && p->n_stretch) {
+            rc = launch_stretch(ctx, p, d_out);
+            if (!rc && total > out_offsets[0]) {
+                cudaError_t e = cudaMemcpyAsync(pcm_out + out_offsets[0], d_out + out_offsets[0],
+                                                (total - out_offsets[0]) * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream);
+                if (e != cudaSuccess) return cu_fail(e, "D2H");
+            }
+        }
+    }
+    auto t2 = now();
+    if (!rc) rc = ctts_gpu_plan_read_counts(ctx, p, out_counts);   // waits for the kernels
+    auto t3 = now();
+    cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+    if (e != cudaSuccess && !rc) rc = fail(ctx, CTTS_GPU_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
+    auto t4 = now();
     ctts_gpu_plan_destroy(p);
+    if (trace)
+        fprintf(stderr, "ctts_gpu_synth_batch: compile+upload %.1f ms, enqueue %u chunks %.1f ms, kernels done +%.1f ms, copies done +%.1f ms\n",
+                ms(t0, t1), nc, ms(t1, t2), ms(t2, t3), ms(t3, t4));
     return rc;
 }
 

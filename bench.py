@@ -347,6 +347,9 @@ def main() -> int:
                 "l2": "output per step (%.2f GB) exceeds the 126 MB L2; the 18 MB voice pool is L2-resident by design" % (2 * n_out / 1e9),
                 "front_end_plan_seconds": plan_s,
                 "window_samples": int(info.window_samples), "smem_bytes": int(info.smem_bytes),
+                "region_tasks": int(info.n_tasks), "region_tasks_in_hbm_window": int(info.n_global_tasks),
+                "persistent_ctas": int(info.grid), "ctas_per_sm": int(info.ctas_per_sm),
+                "threads_per_cta": int(info.threads),
             },
             "gpu_launches": int(info.kernel_launches) * args.steps,
             "clocks": clocks,
@@ -354,7 +357,7 @@ def main() -> int:
                 "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(dominant), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
-                "note": "step = one assemble_kernel launch (+16 KB memset)" if args.workload == "speed1"
+                "note": "step = one assemble_kernel launch (+4 small memsets)" if args.workload == "speed1"
                         else "step = assemble + wsola_search + wsola_ola; the stretch stage is FP32-issue bound, HBM fraction reported as the metric demands",
             },
         }

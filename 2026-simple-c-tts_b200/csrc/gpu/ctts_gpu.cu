@@ -618,7 +618,7 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
                         PlanAlloc::up256((size_t)n_chunks * 4) + 3 * PlanAlloc::up256(std::max<size_t>(n, 1) * 4) + 65536;
         if (!stasks.empty())
             d_need += PlanAlloc::up256(stasks.size() * sizeof(ctts::StretchTask)) + 2 * PlanAlloc::up256(ola_task.size() * 4 + 4) +
-                      PlanAlloc::up256(pre_total * 2 + 16) + PlanAlloc::up256(pos_total * 4 + 4) + PlanAlloc::up256(stasks.size() * 4) + 4096;
+                      PlanAlloc::up256(pre_total * 2 + 16) + PlanAlloc::up256(pos_total * 4 + 4) + PlanAlloc::up256(stasks.size() * 8) + 4096;
         const size_t h_need = PlanAlloc::up256(ops_bytes) + PlanAlloc::up256(tasks_bytes) + 4096;
         rc = ensure_arenas(ctx, d_need, h_need);
         if (rc) { delete p; return rc; }
@@ -652,7 +652,7 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
         p->d_ola_first = al.dev<uint32_t>(ola_first.size());
         p->d_pre = al.dev<int16_t>(pre_total);
         p->d_frame_pos = al.dev<uint32_t>(pos_total);
-        p->d_n_frames = al.dev<uint32_t>(p->n_stretch);
+        p->d_n_frames = al.dev<uint32_t>(2 * (size_t)p->n_stretch);   // frames, then exact-evaluation counts
     }
     if (al.err != cudaSuccess) {
         ctts_gpu_plan_destroy(p);
@@ -966,6 +966,22 @@ int ctts_gpu_plan_read_pcm(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, int16_t* dst, ui
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemcpyAsync(dst, p->d_out_last + first, n * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return CTTS_GPU_OK;
+}
+
+int ctts_gpu_plan_wsola_stats(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint64_t* frames, uint64_t* exact_decisions) {
+    if (!ctx || !p || !frames || !exact_decisions) return CTTS_GPU_ERR_INVALID_ARG;
+    *frames = 0;
+    *exact_decisions = 0;
+    if (!p->n_stretch) return CTTS_GPU_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint32_t> h(2 * (size_t)p->n_stretch);
+    CU(ctx, cudaMemcpyAsync(h.data(), p->d_n_frames, h.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < p->n_stretch; i++) {
+        *frames += h[i];
+        *exact_decisions += h[p->n_stretch + i];
+    }
     return CTTS_GPU_OK;
 }
 

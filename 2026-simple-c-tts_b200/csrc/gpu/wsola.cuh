@@ -1,26 +1,33 @@
 // wsola.cuh -- time stretching (time_stretch, ctts.c:3490-3617) as two kernels.
 //
-// 1. wsola_search_kernel: the frame-to-frame dependent chain.  One CTA per
-//    stretched utterance walks the frames in order; inside a frame the <= 65
-//    coarse candidates (offsets -128..128 step 4) run one per thread, then the
-//    <= 6 fine candidates.  Each candidate's correlation is one thread's
-//    sequential float loop in the reference's order (groups of 4:
-//    ((p0+p1)+p2)+p3, then +=, ctts.c:3411-3413); the coarse candidates share
-//    the 4-aligned group sums of squares.  Output: the analysis position of
-//    every frame.
+// 1. wsola_search_kernel: the frame-to-frame dependent chain (the analysis position of frame k
+//    depends on where frame k-1 was taken).  One CTA per stretched utterance walks the frames
+//    in order.  The reference scores <= 65 coarse candidates (offsets -128..128 step 4) and
+//    then <= 6 fine ones around the best, each score a 384-term sequential float loop
+//    (groups of 4: ((p0+p1)+p2)+p3, then +=, ctts.c:3411-3413) -- 91 % of its run time.
+//    Here every frame is decided in two steps that give the identical result:
+//      FILTER  all candidates get an approximate score: the cross term by FMA in any order
+//              (4 candidates per thread share the operand loads, the 384 terms are split
+//              over 8 threads), the two energies EXACTLY from a 64-bit prefix sum of squares
+//              of the 640 samples the frame can see.  |approx - reference| <= 2e-5
+//              (summation error bound as in asm_pitch.cuh; eps = 1e-4 is used).
+//      DECIDE  candidates whose interval [a-eps, a+eps] reaches the best lower bound are the
+//              only possible winners.  One candidate: done.  Several: those (typically 2-3)
+//              are evaluated with the reference's exact loop, one thread each, and compared
+//              exactly (largest score, first in scan order on ties).  A score whose
+//              denominator is clearly < 1 is exactly 0 (ctts.c:3426) and needs no evaluation.
+//    The 640-sample view of frame k+1 does not depend on the decision for frame k, so it is
+//    prefetched while frame k is decided.  Output: the analysis position of every frame.
 // 2. wsola_ola_kernel: embarrassingly parallel gather-form overlap-add.  Each
 //    output sample adds its <= 8 windowed frame contributions in frame order
 //    into an int16 accumulator that wraps exactly like the reference's `+=`
 //    (ctts.c:3577) and a float norm (ctts.c:3578), normalises, and the CTA
 //    reports the last non-zero sample for the trailing-zero trim (ctts.c:3611).
-//
-// This stage is FP32-issue bound (about 13 non-FMA instructions per candidate
-// per 4 samples), not HBM bound.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
-#include "assemble.cuh"
+#include "asm_common.cuh"
 
 namespace ctts {
 
@@ -28,8 +35,14 @@ constexpr int WS_FRAME = 512;    // ctts.c:3506
 constexpr int WS_HOP = 128;      // analysis hop
 constexpr int WS_OVERLAP = 384;  // correlation length
 constexpr int WS_SHIFT = 128;    // +-search range
-constexpr int WS_THREADS = 128;
 constexpr int WS_RANGE = 2 * WS_SHIFT + WS_OVERLAP;  // 640 samples visible to the candidates
+constexpr int WS_THREADS = 192;  // 17 candidate groups x 8 splits = 136 filter threads, 1 prefix warp
+constexpr int WS_GROUPS = 17;    // groups of 4 coarse candidates (65 candidates, the last group holds 1)
+constexpr int WS_SPLITS = 8;     // threads sharing the 384 terms of a group
+constexpr int WS_FINE_SPLITS = 16;
+constexpr int WS_XPAD = 672;     // staged floats (640 + what the partial last group reads past the end)
+constexpr int WS_MAXC = 72;      // candidates of one decision
+constexpr float WS_EPS = 1e-4f;
 constexpr int OLA_THREADS = 256;
 constexpr int OLA_SPT = 8;  // samples per thread
 
@@ -51,138 +64,335 @@ struct WsolaArgs {
     int16_t* out;
     uint32_t* out_counts;
     uint32_t* frame_pos;
-    uint32_t* n_frames;   // per task
+    uint32_t* n_frames;   // per task; [n_tasks + task] = decisions that needed an exact evaluation
     const float* hann512;
     const uint32_t* ola_block_task;   // per OLA block: task index
     const uint32_t* ola_block_first;  // per OLA block: first output sample
 };
 
-__device__ __forceinline__ uint32_t sortable(float v) {
-    uint32_t b = __float_as_uint(v);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+// cross_correlation (ctts.c:3390) sums of one candidate in the reference's order.
+// a = candidate window, b = target; when b == nullptr only the energy of a is formed.
+__device__ __forceinline__ void ws_exact_sums(const float* a, const float* b, float* sp_out, float* sa_out) {
+    float sp = 0.0f, sa = 0.0f;
+#pragma unroll 2
+    for (int m = 0; m < WS_OVERLAP / 4; m++) {
+        const float a0 = a[4 * m], a1 = a[4 * m + 1], a2 = a[4 * m + 2], a3 = a[4 * m + 3];
+        sa += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+        if (b) {
+            const float b0 = b[4 * m], b1 = b[4 * m + 1], b2 = b[4 * m + 2], b3 = b[4 * m + 3];
+            sp += a0 * b0 + a1 * b1 + a2 * b2 + a3 * b3;
+        }
+    }
+    *sp_out = sp;
+    *sa_out = sa;
+}
+
+// One decision of find_best_match_wsola (ctts.c:3436): `cnt` candidates in the reference's scan
+// order, each with an approximate score ca[i] and an error radius ce[i] (0: the score is exact).
+// The winner is the first candidate in scan order that holds the maximum exact score.  Returns
+// its index; CTA-uniform; all threads must call.
+struct WsDecide {
+    float* ca;       // [WS_MAXC]
+    float* ce;       // [WS_MAXC]
+    int* xoff;       // [WS_MAXC] start of the candidate's window in xin
+    int* list;       // [WS_MAXC]
+    int* cnt_s;      // shared counter
+    float* sb_s;     // exact target energy (valid after the first exact evaluation of a frame)
+    int* sb_valid;
+    uint32_t* exact_count;
+};
+
+__device__ int ws_decide(const WsDecide& D, int cnt, const float* xin, const float* tgt) {
+    const int tid = threadIdx.x;
+    // ---- the best lower bound, by warp 0
+    if (tid < 32) {
+        float lb = -3.0f;
+        for (int i = tid; i < cnt; i += 32) lb = fmaxf(lb, D.ca[i] - D.ce[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+        // survivors, in scan order (a warp-ordered compaction keeps the order)
+        int base = 0;
+        for (int i0 = 0; i0 < cnt; i0 += 32) {
+            const int i = i0 + tid;
+            const bool in = i < cnt && D.ca[i] + D.ce[i] >= lb;
+            const uint32_t m = __ballot_sync(0xffffffffu, in);
+            if (in) D.list[base + __popc(m & ((1u << tid) - 1u))] = i;
+            base += __popc(m);
+        }
+        if (tid == 0) *D.cnt_s = base;
+    }
+    __syncthreads();
+    const int ns = *D.cnt_s;
+    if (ns == 1) {
+        const int w = D.list[0];
+        __syncthreads();
+        return w;
+    }
+    // ---- several possible winners: exact scores for those that are not already exact
+    bool need = false;
+    for (int j = 0; j < ns; j++) need |= D.ce[D.list[j]] != 0.0f;
+    if (need) {
+        if (tid == 0) atomicAdd(D.exact_count, 1u);
+        const bool need_sb = *D.sb_valid == 0;
+        __syncthreads();
+        // job 0: the target's energy (once per frame); jobs 1..ns: the survivors
+        for (int j = tid; j <= ns; j += WS_THREADS) {
+            if (j == 0) {
+                if (need_sb) {
+                    float sp, sb;
+                    ws_exact_sums(tgt, nullptr, &sp, &sb);
+                    *D.sb_s = sb;
+                    *D.sb_valid = 1;
+                }
+            } else {
+                const int i = D.list[j - 1];
+                if (D.ce[i] != 0.0f) {
+                    float sp, sa;
+                    ws_exact_sums(xin + D.xoff[i], tgt, &sp, &sa);
+                    D.ca[i] = sp;             // parked: the score needs sb
+                    D.ce[i] = -sa - 1.0f;     // < 0 marks "raw sums"
+                }
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < ns; j += WS_THREADS) {
+            const int i = D.list[j];
+            if (D.ce[i] < 0.0f) {
+                const float sa = -(D.ce[i] + 1.0f);
+                const float den = sqrtf(sa * *D.sb_s);
+                D.ca[i] = den < 1.0f ? 0.0f : D.ca[i] / den;
+                D.ce[i] = 0.0f;
+            }
+        }
+        __syncthreads();
+    }
+    // first in scan order with the maximum exact score
+    int w = D.list[0];
+    float best = D.ca[w];
+    for (int j = 1; j < ns; j++) {
+        const int i = D.list[j];
+        if (D.ca[i] > best) {
+            best = D.ca[i];
+            w = i;
+        }
+    }
+    __syncthreads();
+    return w;
 }
 
 __global__ void __launch_bounds__(WS_THREADS) wsola_search_kernel(const WsolaArgs A) {
-    __shared__ __align__(16) float xin[WS_RANGE];    // input[nominal-128 .. nominal+512)
-    __shared__ __align__(16) float tgt[WS_OVERLAP];  // previous frame's last 384 samples
-    __shared__ float gsq[WS_RANGE / 4];              // 4-aligned group sums of squares of xin
-    __shared__ float s_tsq;                          // target sum of squares
-    __shared__ unsigned long long s_red[WS_THREADS / 32];
-    __shared__ int s_best;
+    __shared__ __align__(16) float xbuf[2][WS_XPAD];   // input[nominal-128 .. nominal+512), zero padded
+    __shared__ __align__(16) float tgt[WS_OVERLAP];    // previous frame's last 384 samples
+    __shared__ unsigned long long S[WS_RANGE + 8];     // S[i] = sum_{j<i} xin[j]^2 (exact)
+    __shared__ float ca[WS_MAXC], ce[WS_MAXC];
+    __shared__ int xoff[WS_MAXC], list[WS_MAXC], coff[WS_MAXC];
+    __shared__ int s_cnt, s_sb_valid;
+    __shared__ float s_sb;
 
     const StretchTask task = A.tasks[blockIdx.x];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = A.pre_counts[task.utt];
     const int16_t* in = A.pre + task.pre_off;
     uint32_t* fpos = A.frame_pos + task.pos_off;
+    uint32_t* exact_count = A.n_frames + A.n_tasks + blockIdx.x;
 
     uint32_t frames = n >= WS_FRAME ? (n - WS_FRAME) / WS_HOP + 1 : 0;
     if (frames > task.max_frames) frames = task.max_frames;
-    if (tid == 0) A.n_frames[blockIdx.x] = frames;
+    if (tid == 0) {
+        A.n_frames[blockIdx.x] = frames;
+        *exact_count = 0;
+    }
     if (frames == 0) return;
     if (tid == 0) fpos[0] = 0;
     uint32_t prev_pos = 0;
 
+    WsDecide D{ca, ce, xoff, list, &s_cnt, &s_sb, &s_sb_valid, exact_count};
+
+    // the view of frame k: xin[i] = in[k*128 - 128 + i]; loaded one frame ahead into registers
+    constexpr int PER = (WS_XPAD + WS_THREADS - 1) / WS_THREADS;   // 4
+    float pre_v[PER];
+    auto fetch = [&](uint32_t k) {
+#pragma unroll
+        for (int r = 0; r < PER; r++) {
+            const int i = tid + r * WS_THREADS;
+            const int pidx = (int)(k * WS_HOP) - WS_SHIFT + i;
+            pre_v[r] = (i < WS_RANGE && pidx >= 0 && (uint32_t)pidx < n) ? (float)in[pidx] : 0.0f;
+        }
+    };
+    auto commit = [&](float* xin) {
+#pragma unroll
+        for (int r = 0; r < PER; r++) {
+            const int i = tid + r * WS_THREADS;
+            if (i < WS_XPAD) xin[i] = pre_v[r];
+        }
+    };
+    if (frames > 1) fetch(1);
+
     for (uint32_t k = 1; k < frames; k++) {
+        float* xin = xbuf[k & 1];
         const int nominal = (int)(k * WS_HOP);
-        // stage the candidates' view and the target as floats
-        for (int i = tid; i < WS_RANGE; i += WS_THREADS) {
-            int p = nominal - WS_SHIFT + i;
-            xin[i] = (p >= 0 && (uint32_t)p < n) ? (float)in[p] : 0.0f;
-        }
-        for (int i = tid; i < WS_OVERLAP; i += WS_THREADS) tgt[i] = (float)in[prev_pos + (WS_FRAME - WS_OVERLAP) + i];
+        commit(xin);
+        if (tid == 0) s_sb_valid = 0;
         __syncthreads();
-        for (int g = tid; g < WS_RANGE / 4; g += WS_THREADS) {
-            float a0 = xin[4 * g], a1 = xin[4 * g + 1], a2 = xin[4 * g + 2], a3 = xin[4 * g + 3];
-            gsq[g] = a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
-        }
-        if (tid == WS_THREADS - 1) {
-            float sb = 0.0f;
-            for (int m = 0; m < WS_OVERLAP / 4; m++) {
-                float b0 = tgt[4 * m], b1 = tgt[4 * m + 1], b2 = tgt[4 * m + 2], b3 = tgt[4 * m + 3];
-                sb += b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
-            }
-            s_tsq = sb;
-        }
-        __syncthreads();
+        if (k + 1 < frames) fetch(k + 1);   // in flight while this frame is decided
+        // the target inside the view: in[prev_pos + 128 ..) = xin[ti ..], ti in [0, 256]
+        const int ti = (int)prev_pos + (WS_FRAME - WS_OVERLAP) - (nominal - WS_SHIFT);
+        for (int i = tid; i < WS_OVERLAP; i += WS_THREADS) tgt[i] = xin[ti + i];
 
-        // coarse: candidate c has offset -128 + 4c
-        unsigned long long key = 0ull;
-        if (tid <= 2 * WS_SHIFT / 4) {
-            int off = -WS_SHIFT + 4 * tid;
-            int cpos = nominal + off;
-            if (cpos >= 0 && (uint32_t)cpos + WS_FRAME <= n) {
-                float sp = 0.0f, sa = 0.0f;
-                const float4* xa = reinterpret_cast<const float4*>(xin) + tid;
-                const float4* xb = reinterpret_cast<const float4*>(tgt);
-                const float* gq = gsq + tid;
+        // ---- FILTER, coarse: group g = candidates 4g..4g+3 (window starts 16g + 4j), split s = terms [48s, 48s+48)
+        float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const int g = tid >> 3, sidx = tid & 7;
+        __syncthreads();   // tgt
+        if (g < WS_GROUPS) {
+            const float4* x4 = reinterpret_cast<const float4*>(tgt) + 12 * sidx;
+            const float4* y4 = reinterpret_cast<const float4*>(xin) + 4 * g + 12 * sidx;
+            float4 y0 = y4[0], y1 = y4[1], y2 = y4[2];
 #pragma unroll 4
-                for (int m = 0; m < WS_OVERLAP / 4; m++) {
-                    float4 a = xa[m], b = xb[m];
-                    sp += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
-                    sa += gq[m];
-                }
-                float den = sqrtf(sa * s_tsq);
-                float c = den < 1.0f ? 0.0f : sp / den;
-                key = ((unsigned long long)sortable(c) << 32) | (unsigned long long)(0xffffu - (uint32_t)tid);
+            for (int m = 0; m < 12; m++) {
+                const float4 x = x4[m];
+                const float4 y3 = y4[m + 3];
+                sp[0] = __fmaf_rn(x.x, y0.x, sp[0]); sp[0] = __fmaf_rn(x.y, y0.y, sp[0]);
+                sp[0] = __fmaf_rn(x.z, y0.z, sp[0]); sp[0] = __fmaf_rn(x.w, y0.w, sp[0]);
+                sp[1] = __fmaf_rn(x.x, y1.x, sp[1]); sp[1] = __fmaf_rn(x.y, y1.y, sp[1]);
+                sp[1] = __fmaf_rn(x.z, y1.z, sp[1]); sp[1] = __fmaf_rn(x.w, y1.w, sp[1]);
+                sp[2] = __fmaf_rn(x.x, y2.x, sp[2]); sp[2] = __fmaf_rn(x.y, y2.y, sp[2]);
+                sp[2] = __fmaf_rn(x.z, y2.z, sp[2]); sp[2] = __fmaf_rn(x.w, y2.w, sp[2]);
+                sp[3] = __fmaf_rn(x.x, y3.x, sp[3]); sp[3] = __fmaf_rn(x.y, y3.y, sp[3]);
+                sp[3] = __fmaf_rn(x.z, y3.z, sp[3]); sp[3] = __fmaf_rn(x.w, y3.w, sp[3]);
+                y0 = y1; y1 = y2; y2 = y3;
+            }
+        } else if (warp == WS_THREADS / 32 - 1) {
+            // exact prefix sums of squares of the view (20 values per lane, 640 * 2^30 < 2^64)
+            constexpr int P = WS_RANGE / 32;
+            const int i0 = lane * P;
+            unsigned long long loc = 0;
+#pragma unroll
+            for (int q = 0; q < P; q++) {
+                const int v = (int)xin[i0 + q];
+                loc += (unsigned long long)(uint32_t)(v * v);
+            }
+            unsigned long long inc = loc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            unsigned long long run = inc - loc;
+#pragma unroll
+            for (int q = 0; q < P; q++) {
+                S[i0 + q] = run;
+                const int v = (int)xin[i0 + q];
+                run += (unsigned long long)(uint32_t)(v * v);
+            }
+            if (lane == 31) S[WS_RANGE] = run;
+        }
+        // reduce the 8 splits of a group (adjacent lanes)
+        if (warp < WS_THREADS / 32 - 1) {
+#pragma unroll
+            for (int o = 1; o < WS_SPLITS; o <<= 1) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) sp[j] += __shfl_xor_sync(0xffffffffu, sp[j], o);
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-            key = other > key ? other : key;
+        __syncthreads();   // S
+        const float sb = (float)(S[ti + WS_OVERLAP] - S[ti]);
+        // scan order of the coarse stage: ascending offset, candidates out of bounds skipped (ctts.c:3452)
+        // candidate c (offset -128 + 4c) is in bounds iff cpos >= 0 && cpos + 512 <= n
+        const int c_first = nominal >= WS_SHIFT ? 0 : (WS_SHIFT - nominal + 3) / 4;
+        int c_last = 2 * WS_SHIFT / 4;
+        {
+            const long long room = (long long)n - WS_FRAME - nominal;   // largest offset in bounds (>= 0)
+            if (room < WS_SHIFT) c_last = (int)((room + WS_SHIFT) / 4);
         }
-        if (lane_id() == 0) s_red[warp_id()] = key;
+        if (g < WS_GROUPS && sidx < 4) {
+            // every lane of a group holds the four sums: lane j scores candidate j
+            const int c = 4 * g + sidx;
+            const float spc = sidx == 0 ? sp[0] : sidx == 1 ? sp[1] : sidx == 2 ? sp[2] : sp[3];
+            if (c >= c_first && c <= c_last) {
+                const float sa = (float)(S[4 * c + WS_OVERLAP] - S[4 * c]);
+                const float den = sqrtf(sa * sb);
+                float a = 0.0f, e = 0.0f;
+                if (den > 1.01f) {
+                    a = spc / den;
+                    e = WS_EPS;
+                } else if (den >= 0.99f) {   // cannot tell which side of 1 the reference's denominator falls
+                    a = 0.0f;
+                    e = 4.0f;
+                }
+                ca[c - c_first] = a;
+                ce[c - c_first] = e;
+                xoff[c - c_first] = 4 * c;
+                coff[c - c_first] = -WS_SHIFT + 4 * c;
+            }
+        }
         __syncthreads();
-        unsigned long long best = 0ull;
-#pragma unroll
-        for (int w = 0; w < WS_THREADS / 32; w++) best = s_red[w] > best ? s_red[w] : best;
-        int best_off = 0;
-        uint32_t best_corr_key = sortable(-2.0f);
-        if (best != 0ull) {
-            best_off = -WS_SHIFT + 4 * (int)(0xffffu - (uint32_t)(best & 0xffffu));
-            best_corr_key = (uint32_t)(best >> 32);
-        }
+        const int w1 = ws_decide(D, c_last - c_first + 1, xin, tgt);
+        const int best_off = coff[w1];
+        const float best_a = ca[w1], best_e = ce[w1];
         __syncthreads();
 
-        // fine: best_off-3 .. best_off+3 without best_off, ascending, strict >
+        // ---- FILTER, fine: best_off-3 .. best_off+3 without best_off, ascending, in bounds (ctts.c:3466-3483)
         int lo = best_off - 3, hi = best_off + 3;
         if (lo < -WS_SHIFT) lo = -WS_SHIFT;
         if (hi > WS_SHIFT) hi = WS_SHIFT;
-        unsigned long long fkey = 0ull;
-        if (tid <= hi - lo) {
-            int off = lo + tid;
-            int cpos = nominal + off;
-            if (off != best_off && cpos >= 0 && (uint32_t)cpos + WS_FRAME <= n) {
-                float sp = 0.0f, sa = 0.0f;
-                const float* xa = xin + (off + WS_SHIFT);
-#pragma unroll 2
-                for (int m = 0; m < WS_OVERLAP / 4; m++) {
-                    float a0 = xa[4 * m], a1 = xa[4 * m + 1], a2 = xa[4 * m + 2], a3 = xa[4 * m + 3];
-                    float b0 = tgt[4 * m], b1 = tgt[4 * m + 1], b2 = tgt[4 * m + 2], b3 = tgt[4 * m + 3];
-                    sp += a0 * b0 + a1 * b1 + a2 * b2 + a3 * b3;
-                    sa += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+        // candidate f = thread / 16, split = thread % 16 (24 terms each)
+        {
+            const int f = tid >> 4, fs = tid & 15;
+            const int off = lo + f;
+            float spf = 0.0f;
+            const bool live = f <= hi - lo && off != best_off;
+            if (live) {
+                const float* y = xin + (off + WS_SHIFT) + 24 * fs;
+                const float* x = tgt + 24 * fs;
+#pragma unroll
+                for (int q = 0; q < 24; q++) spf = __fmaf_rn(x[q], y[q], spf);
+            }
+            if (tid < 128) {   // whole warps; f <= 7
+#pragma unroll
+                for (int o = 1; o < WS_FINE_SPLITS; o <<= 1) spf += __shfl_xor_sync(0xffffffffu, spf, o);
+            }
+            if (tid == 0) {   // scan order: the coarse winner first (it is `best`), then the fine candidates ascending
+                ca[0] = best_a;
+                ce[0] = best_e;
+                xoff[0] = best_off + WS_SHIFT;
+                coff[0] = best_off;
+            }
+            __syncthreads();
+            if (live && fs == 0) {
+                const int cpos = nominal + off;
+                const bool inb = cpos >= 0 && (long long)cpos + WS_FRAME <= (long long)n;
+                // slot: 1 + number of live in-bounds candidates before this one
+                int slot = 1;
+                for (int o2 = lo; o2 < off; o2++) {
+                    const int cp2 = nominal + o2;
+                    if (o2 != best_off && cp2 >= 0 && (long long)cp2 + WS_FRAME <= (long long)n) slot++;
                 }
-                float den = sqrtf(sa * s_tsq);
-                float c = den < 1.0f ? 0.0f : sp / den;
-                uint32_t ck = sortable(c);
-                if (ck > best_corr_key) fkey = ((unsigned long long)ck << 32) | (unsigned long long)(0xffu - (uint32_t)tid);
+                if (inb) {
+                    const int xo = off + WS_SHIFT;
+                    const float sa = (float)(S[xo + WS_OVERLAP] - S[xo]);
+                    const float den = sqrtf(sa * sb);
+                    float a = 0.0f, e = 0.0f;
+                    if (den > 1.01f) {
+                        a = spf / den;
+                        e = WS_EPS;
+                    } else if (den >= 0.99f) {
+                        e = 4.0f;
+                    }
+                    ca[slot] = a;
+                    ce[slot] = e;
+                    xoff[slot] = xo;
+                    coff[slot] = off;
+                }
             }
         }
-        if (tid < 32) {
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                unsigned long long other = __shfl_xor_sync(0xffffffffu, fkey, o);
-                fkey = other > fkey ? other : fkey;
-            }
-            if (tid == 0) {
-                int off = best_off;
-                if (fkey != 0ull) off = lo + (int)(0xffu - (uint32_t)(fkey & 0xffu));
-                s_best = off;
-            }
+        int nfine = 0;
+        for (int o2 = lo; o2 <= hi; o2++) {
+            const int cp2 = nominal + o2;
+            if (o2 != best_off && cp2 >= 0 && (long long)cp2 + WS_FRAME <= (long long)n) nfine++;
         }
         __syncthreads();
-        int off = s_best;
+        const int w2 = ws_decide(D, 1 + nfine, xin, tgt);
+        const int off = coff[w2];
         uint32_t pos = (uint32_t)(nominal + off);
         if (pos + WS_FRAME > n) pos = n - WS_FRAME;
         if (tid == 0) fpos[k] = pos;

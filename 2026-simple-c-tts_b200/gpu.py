@@ -58,6 +58,7 @@ def lib(build: bool = True) -> C.CDLL:
         L.ctts_gpu_plan_read_pcm.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64]
         L.ctts_gpu_plan_read_pre.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint64, u64p]
         L.ctts_gpu_plan_info.argtypes = [vp, C.POINTER(RunInfo)]
+        L.ctts_gpu_plan_wsola_stats.argtypes = [vp, vp, u64p, u64p]
         _lib = L
     return _lib
 
@@ -118,6 +119,12 @@ class ResidentPlan:
         n = C.c_uint64()
         self._ctx._check(lib().ctts_gpu_plan_read_pre(self._ctx._h, self._h, u, out.ctypes.data, cap, C.byref(n)))
         return out[:min(int(n.value), cap)]
+
+    def wsola_stats(self) -> tuple[int, int]:
+        """(frames searched, decisions that needed the exact correlation loop) of the last run."""
+        f, e = C.c_uint64(), C.c_uint64()
+        self._ctx._check(lib().ctts_gpu_plan_wsola_stats(self._ctx._h, self._h, C.byref(f), C.byref(e)))
+        return int(f.value), int(e.value)
 
     def utterances(self) -> list[np.ndarray]:
         """Convenience for tests: per-utterance PCM read back from the plan-owned buffer."""

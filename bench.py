@@ -361,6 +361,10 @@ def main() -> int:
                         else "step = assemble + wsola_search + wsola_ola; the stretch stage is FP32-issue bound, HBM fraction reported as the metric demands",
             },
         }
+        if args.workload == "mixed":
+            fr_n, ex_n = rp.wsola_stats()
+            line["config"]["wsola_frames"] = fr_n
+            line["config"]["wsola_exact_decisions"] = ex_n
         if e2e:
             line["e2e"] = {"value": e2e_audio_all / e2e_s_all, "unit": UNIT,
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],

@@ -90,6 +90,11 @@ int ctts_gpu_plan_read_pcm(ctts_gpu_ctx* ctx, ctts_gpu_plan* plan, int16_t* dst,
 int ctts_gpu_plan_read_pre(ctts_gpu_ctx* ctx, ctts_gpu_plan* plan, uint32_t u, int16_t* dst,
                            uint64_t cap, uint64_t* n);
 
+/* After a run: WSOLA frames searched over the batch, and how many of the (two per frame)
+ * candidate decisions needed the reference's exact correlation loop after the FMA filter. */
+int ctts_gpu_plan_wsola_stats(ctts_gpu_ctx* ctx, ctts_gpu_plan* plan, uint64_t* frames,
+                              uint64_t* exact_decisions);
+
 typedef struct ctts_gpu_run_info {
     uint32_t kernel_launches;    /* kernels enqueued by one ctts_gpu_plan_run */
     uint32_t n_stretch;          /* utterances that go through WSOLA */

@@ -96,21 +96,69 @@ struct WsDecide {
     float* ce;       // [WS_MAXC]
     int* xoff;       // [WS_MAXC] start of the candidate's window in xin
     int* list;       // [WS_MAXC]
-    int* cnt_s;      // shared counter
+    int* cnt_s;      // [4] shared: survivors, inexact survivors, fast-path winner, lower bound
     float* sb_s;     // exact target energy (valid after the first exact evaluation of a frame)
     int* sb_valid;
     uint32_t* exact_count;
 };
 
+// order-preserving map float -> uint32
+__device__ __forceinline__ uint32_t ws_sortable(float v) {
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
 __device__ int ws_decide(const WsDecide& D, int cnt, const float* xin, const float* tgt) {
     const int tid = threadIdx.x;
-    // ---- the best lower bound, by warp 0
+    // ---- warp 0, three candidates per lane: the best lower bound, who survives it, and -- if every
+    //      survivor's score is already exact, or there is only one -- the winner
     if (tid < 32) {
+        float a[3], e[3];
         float lb = -3.0f;
-        for (int i = tid; i < cnt; i += 32) lb = fmaxf(lb, D.ca[i] - D.ce[i]);
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int i = tid + 32 * r;
+            a[r] = i < cnt ? D.ca[i] : -3.0f;
+            e[r] = i < cnt ? D.ce[i] : 0.0f;
+            lb = fmaxf(lb, a[r] - e[r]);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
-        // survivors, in scan order (a warp-ordered compaction keeps the order)
+        int ns = 0, inexact = 0;
+        unsigned long long key = 0ull;   // (score, scan position reversed): max = best score, first in scan order
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int i = tid + 32 * r;
+            const bool in = i < cnt && a[r] + e[r] >= lb;
+            ns += __popc(__ballot_sync(0xffffffffu, in));
+            inexact += __popc(__ballot_sync(0xffffffffu, in && e[r] != 0.0f));
+            if (in) {
+                const unsigned long long k2 = ((unsigned long long)ws_sortable(a[r]) << 32) | (uint32_t)(0xffff - i);
+                key = k2 > key ? k2 : key;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+        }
+        if (tid == 0) {
+            D.cnt_s[0] = ns;
+            D.cnt_s[1] = inexact;
+            D.cnt_s[2] = 0xffff - (int)(uint32_t)(key & 0xffffu);
+            D.cnt_s[3] = __float_as_int(lb);
+        }
+    }
+    __syncthreads();
+    const int ns = D.cnt_s[0], inexact = D.cnt_s[1];
+    if (ns == 1 || inexact == 0) {
+        const int w = D.cnt_s[2];
+        __syncthreads();
+        return w;
+    }
+    // ---- several possible winners, not all exact: the reference's loop for those, one thread each
+    const float lb = __int_as_float(D.cnt_s[3]);
+    if (tid < 32) {   // survivors in scan order (a warp-ordered compaction keeps the order)
         int base = 0;
         for (int i0 = 0; i0 < cnt; i0 += 32) {
             const int i = i0 + tid;
@@ -119,53 +167,40 @@ __device__ int ws_decide(const WsDecide& D, int cnt, const float* xin, const flo
             if (in) D.list[base + __popc(m & ((1u << tid) - 1u))] = i;
             base += __popc(m);
         }
-        if (tid == 0) *D.cnt_s = base;
+    }
+    if (tid == 0) atomicAdd(D.exact_count, 1u);
+    const bool need_sb = *D.sb_valid == 0;
+    __syncthreads();
+    // job 0: the target's energy (once per frame); jobs 1..ns: the survivors
+    for (int j = tid; j <= ns; j += WS_THREADS) {
+        if (j == 0) {
+            if (need_sb) {
+                float sp, sb;
+                ws_exact_sums(tgt, nullptr, &sp, &sb);
+                *D.sb_s = sb;
+                *D.sb_valid = 1;
+            }
+        } else {
+            const int i = D.list[j - 1];
+            if (D.ce[i] != 0.0f) {
+                float sp, sa;
+                ws_exact_sums(xin + D.xoff[i], tgt, &sp, &sa);
+                D.ca[i] = sp;             // parked: the score needs sb
+                D.ce[i] = -sa - 1.0f;     // < 0 marks "raw sums"
+            }
+        }
     }
     __syncthreads();
-    const int ns = *D.cnt_s;
-    if (ns == 1) {
-        const int w = D.list[0];
-        __syncthreads();
-        return w;
-    }
-    // ---- several possible winners: exact scores for those that are not already exact
-    bool need = false;
-    for (int j = 0; j < ns; j++) need |= D.ce[D.list[j]] != 0.0f;
-    if (need) {
-        if (tid == 0) atomicAdd(D.exact_count, 1u);
-        const bool need_sb = *D.sb_valid == 0;
-        __syncthreads();
-        // job 0: the target's energy (once per frame); jobs 1..ns: the survivors
-        for (int j = tid; j <= ns; j += WS_THREADS) {
-            if (j == 0) {
-                if (need_sb) {
-                    float sp, sb;
-                    ws_exact_sums(tgt, nullptr, &sp, &sb);
-                    *D.sb_s = sb;
-                    *D.sb_valid = 1;
-                }
-            } else {
-                const int i = D.list[j - 1];
-                if (D.ce[i] != 0.0f) {
-                    float sp, sa;
-                    ws_exact_sums(xin + D.xoff[i], tgt, &sp, &sa);
-                    D.ca[i] = sp;             // parked: the score needs sb
-                    D.ce[i] = -sa - 1.0f;     // < 0 marks "raw sums"
-                }
-            }
+    for (int j = tid; j < ns; j += WS_THREADS) {
+        const int i = D.list[j];
+        if (D.ce[i] < 0.0f) {
+            const float sa = -(D.ce[i] + 1.0f);
+            const float den = sqrtf(sa * *D.sb_s);
+            D.ca[i] = den < 1.0f ? 0.0f : D.ca[i] / den;
+            D.ce[i] = 0.0f;
         }
-        __syncthreads();
-        for (int j = tid; j < ns; j += WS_THREADS) {
-            const int i = D.list[j];
-            if (D.ce[i] < 0.0f) {
-                const float sa = -(D.ce[i] + 1.0f);
-                const float den = sqrtf(sa * *D.sb_s);
-                D.ca[i] = den < 1.0f ? 0.0f : D.ca[i] / den;
-                D.ce[i] = 0.0f;
-            }
-        }
-        __syncthreads();
     }
+    __syncthreads();
     // first in scan order with the maximum exact score
     int w = D.list[0];
     float best = D.ca[w];
@@ -186,7 +221,7 @@ __global__ void __launch_bounds__(WS_THREADS) wsola_search_kernel(const WsolaArg
     __shared__ unsigned long long S[WS_RANGE + 8];     // S[i] = sum_{j<i} xin[j]^2 (exact)
     __shared__ float ca[WS_MAXC], ce[WS_MAXC];
     __shared__ int xoff[WS_MAXC], list[WS_MAXC], coff[WS_MAXC];
-    __shared__ int s_cnt, s_sb_valid;
+    __shared__ int s_cnt[4], s_sb_valid;
     __shared__ float s_sb;
 
     const StretchTask task = A.tasks[blockIdx.x];
@@ -206,17 +241,27 @@ __global__ void __launch_bounds__(WS_THREADS) wsola_search_kernel(const WsolaArg
     if (tid == 0) fpos[0] = 0;
     uint32_t prev_pos = 0;
 
-    WsDecide D{ca, ce, xoff, list, &s_cnt, &s_sb, &s_sb_valid, exact_count};
+    WsDecide D{ca, ce, xoff, list, s_cnt, &s_sb, &s_sb_valid, exact_count};
 
     // the view of frame k: xin[i] = in[k*128 - 128 + i]; loaded one frame ahead into registers
     constexpr int PER = (WS_XPAD + WS_THREADS - 1) / WS_THREADS;   // 4
     float pre_v[PER];
     auto fetch = [&](uint32_t k) {
+        const int p0 = (int)(k * WS_HOP) - WS_SHIFT;   // first sample of the view (>= 0 for k >= 1)
+        if (p0 >= 0 && (uint32_t)(p0 + WS_RANGE) <= n) {
+            // interior frame (all but the last few): no bounds checks
 #pragma unroll
-        for (int r = 0; r < PER; r++) {
-            const int i = tid + r * WS_THREADS;
-            const int pidx = (int)(k * WS_HOP) - WS_SHIFT + i;
-            pre_v[r] = (i < WS_RANGE && pidx >= 0 && (uint32_t)pidx < n) ? (float)in[pidx] : 0.0f;
+            for (int r = 0; r < PER; r++) {
+                const int i = tid + r * WS_THREADS;
+                pre_v[r] = i < WS_RANGE ? (float)in[p0 + i] : 0.0f;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < PER; r++) {
+                const int i = tid + r * WS_THREADS;
+                const int pidx = p0 + i;
+                pre_v[r] = (i < WS_RANGE && pidx >= 0 && (uint32_t)pidx < n) ? (float)in[pidx] : 0.0f;
+            }
         }
     };
     auto commit = [&](float* xin) {
@@ -237,12 +282,29 @@ __global__ void __launch_bounds__(WS_THREADS) wsola_search_kernel(const WsolaArg
         if (k + 1 < frames) fetch(k + 1);   // in flight while this frame is decided
         // the target inside the view: in[prev_pos + 128 ..) = xin[ti ..], ti in [0, 256]
         const int ti = (int)prev_pos + (WS_FRAME - WS_OVERLAP) - (nominal - WS_SHIFT);
-        for (int i = tid; i < WS_OVERLAP; i += WS_THREADS) tgt[i] = xin[ti + i];
-
+        int tgt_nz = 0;
+        for (int i = tid; i < WS_OVERLAP; i += WS_THREADS) {
+            const float v = xin[ti + i];
+            tgt[i] = v;
+            tgt_nz |= v != 0.0f;
+        }
+        // scan order of the coarse stage: ascending offset, candidates out of bounds skipped (ctts.c:3452)
+        // candidate c (offset -128 + 4c) is in bounds iff cpos >= 0 && cpos + 512 <= n
+        const int c_first = nominal >= WS_SHIFT ? 0 : (WS_SHIFT - nominal + 3) / 4;
+        int c_last = 2 * WS_SHIFT / 4;
+        const long long room = (long long)n - WS_FRAME - nominal;   // largest offset in bounds (>= 0)
+        if (room < WS_SHIFT) c_last = (int)((room + WS_SHIFT) / 4);
+        if (!__syncthreads_or(tgt_nz)) {
+            // digital silence behind us: every denominator is 0 < 1, every score is exactly 0
+            // (ctts.c:3426), the first candidate in bounds wins and no fine candidate beats it
+            uint32_t pos = (uint32_t)(nominal - WS_SHIFT + 4 * c_first);
+            if (tid == 0) fpos[k] = pos;
+            prev_pos = pos;
+            continue;
+        }
         // ---- FILTER, coarse: group g = candidates 4g..4g+3 (window starts 16g + 4j), split s = terms [48s, 48s+48)
         float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         const int g = tid >> 3, sidx = tid & 7;
-        __syncthreads();   // tgt
         if (g < WS_GROUPS) {
             const float4* x4 = reinterpret_cast<const float4*>(tgt) + 12 * sidx;
             const float4* y4 = reinterpret_cast<const float4*>(xin) + 4 * g + 12 * sidx;
@@ -296,14 +358,6 @@ __global__ void __launch_bounds__(WS_THREADS) wsola_search_kernel(const WsolaArg
         }
         __syncthreads();   // S
         const float sb = (float)(S[ti + WS_OVERLAP] - S[ti]);
-        // scan order of the coarse stage: ascending offset, candidates out of bounds skipped (ctts.c:3452)
-        // candidate c (offset -128 + 4c) is in bounds iff cpos >= 0 && cpos + 512 <= n
-        const int c_first = nominal >= WS_SHIFT ? 0 : (WS_SHIFT - nominal + 3) / 4;
-        int c_last = 2 * WS_SHIFT / 4;
-        {
-            const long long room = (long long)n - WS_FRAME - nominal;   // largest offset in bounds (>= 0)
-            if (room < WS_SHIFT) c_last = (int)((room + WS_SHIFT) / 4);
-        }
         if (g < WS_GROUPS && sidx < 4) {
             // every lane of a group holds the four sums: lane j scores candidate j
             const int c = 4 * g + sidx;
@@ -336,6 +390,7 @@ __global__ void __launch_bounds__(WS_THREADS) wsola_search_kernel(const WsolaArg
         if (lo < -WS_SHIFT) lo = -WS_SHIFT;
         if (hi > WS_SHIFT) hi = WS_SHIFT;
         // candidate f = thread / 16, split = thread % 16 (24 terms each)
+        int nfine = 0;
         {
             const int f = tid >> 4, fs = tid & 15;
             const int off = lo + f;
@@ -358,37 +413,27 @@ __global__ void __launch_bounds__(WS_THREADS) wsola_search_kernel(const WsolaArg
                 coff[0] = best_off;
             }
             __syncthreads();
-            if (live && fs == 0) {
-                const int cpos = nominal + off;
-                const bool inb = cpos >= 0 && (long long)cpos + WS_FRAME <= (long long)n;
-                // slot: 1 + number of live in-bounds candidates before this one
-                int slot = 1;
-                for (int o2 = lo; o2 < off; o2++) {
-                    const int cp2 = nominal + o2;
-                    if (o2 != best_off && cp2 >= 0 && (long long)cp2 + WS_FRAME <= (long long)n) slot++;
+            // fine candidates in bounds: offsets [flo, fhi] without best_off, in ascending order
+            const int flo = lo > -nominal ? lo : -nominal;
+            const int fhi = (long long)hi < room ? hi : (int)room;
+            if (live && fs == 0 && off >= flo && off <= fhi) {
+                const int slot = 1 + (off - flo) - (best_off >= flo && best_off < off ? 1 : 0);
+                const int xo = off + WS_SHIFT;
+                const float sa = (float)(S[xo + WS_OVERLAP] - S[xo]);
+                const float den = sqrtf(sa * sb);
+                float a = 0.0f, e = 0.0f;
+                if (den > 1.01f) {
+                    a = spf / den;
+                    e = WS_EPS;
+                } else if (den >= 0.99f) {
+                    e = 4.0f;
                 }
-                if (inb) {
-                    const int xo = off + WS_SHIFT;
-                    const float sa = (float)(S[xo + WS_OVERLAP] - S[xo]);
-                    const float den = sqrtf(sa * sb);
-                    float a = 0.0f, e = 0.0f;
-                    if (den > 1.01f) {
-                        a = spf / den;
-                        e = WS_EPS;
-                    } else if (den >= 0.99f) {
-                        e = 4.0f;
-                    }
-                    ca[slot] = a;
-                    ce[slot] = e;
-                    xoff[slot] = xo;
-                    coff[slot] = off;
-                }
+                ca[slot] = a;
+                ce[slot] = e;
+                xoff[slot] = xo;
+                coff[slot] = off;
             }
-        }
-        int nfine = 0;
-        for (int o2 = lo; o2 <= hi; o2++) {
-            const int cp2 = nominal + o2;
-            if (o2 != best_off && cp2 >= 0 && (long long)cp2 + WS_FRAME <= (long long)n) nfine++;
+            nfine = fhi >= flo ? fhi - flo + 1 - (best_off >= flo && best_off <= fhi ? 1 : 0) : 0;
         }
         __syncthreads();
         const int w2 = ws_decide(D, 1 + nfine, xin, tgt);

@@ -215,10 +215,10 @@ __device__ int ws_decide(const WsDecide& D, int cnt, const float* xin, const flo
     return w;
 }
 
-__global__ void __launch_bounds__(WS_THREADS) wsola_search_kernel(const WsolaArgs A) {
+__global__ void __launch_bounds__(WS_THREADS, 8) wsola_search_kernel(const WsolaArgs A) {
     __shared__ __align__(16) float xbuf[2][WS_XPAD];   // input[nominal-128 .. nominal+512), zero padded
     __shared__ __align__(16) float tgt[WS_OVERLAP];    // previous frame's last 384 samples
-    __shared__ unsigned long long S[WS_RANGE + 8];     // S[i] = sum_{j<i} xin[j]^2 (exact)
+    __shared__ __align__(16) unsigned long long S[WS_RANGE + 8];     // S[i] = sum_{j<i} xin[j]^2 (exact)
     __shared__ float ca[WS_MAXC], ce[WS_MAXC];
     __shared__ int xoff[WS_MAXC], list[WS_MAXC], coff[WS_MAXC];
     __shared__ int s_cnt[4], s_sb_valid;
@@ -306,11 +306,13 @@ __global__ void __launch_bounds__(WS_THREADS) wsola_search_kernel(const WsolaArg
         float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         const int g = tid >> 3, sidx = tid & 7;
         if (g < WS_GROUPS) {
-            const float4* x4 = reinterpret_cast<const float4*>(tgt) + 12 * sidx;
-            const float4* y4 = reinterpret_cast<const float4*>(xin) + 4 * g + 12 * sidx;
+            // split s takes terms [52 s, 52 s + 52) (the last one 20): starts 13 float4 apart put the
+            // eight lanes of a quarter warp on eight different bank groups (12 would collide 4-way)
+            const int m_cnt = sidx == WS_SPLITS - 1 ? WS_OVERLAP / 4 - 13 * (WS_SPLITS - 1) : 13;
+            const float4* x4 = reinterpret_cast<const float4*>(tgt) + 13 * sidx;
+            const float4* y4 = reinterpret_cast<const float4*>(xin) + 4 * g + 13 * sidx;
             float4 y0 = y4[0], y1 = y4[1], y2 = y4[2];
-#pragma unroll 4
-            for (int m = 0; m < 12; m++) {
+            for (int m = 0; m < m_cnt; m++) {
                 const float4 x = x4[m];
                 const float4 y3 = y4[m + 3];
                 sp[0] = __fmaf_rn(x.x, y0.x, sp[0]); sp[0] = __fmaf_rn(x.y, y0.y, sp[0]);
@@ -325,14 +327,17 @@ __global__ void __launch_bounds__(WS_THREADS) wsola_search_kernel(const WsolaArg
             }
         } else if (warp == WS_THREADS / 32 - 1) {
             // exact prefix sums of squares of the view (20 values per lane, 640 * 2^30 < 2^64)
-            constexpr int P = WS_RANGE / 32;
+            constexpr int P = WS_RANGE / 32;   // 20: five float4 loads, ten 16-byte stores per lane
             const int i0 = lane * P;
+            int v[P];
             unsigned long long loc = 0;
 #pragma unroll
-            for (int q = 0; q < P; q++) {
-                const int v = (int)xin[i0 + q];
-                loc += (unsigned long long)(uint32_t)(v * v);
+            for (int q = 0; q < P / 4; q++) {
+                const float4 f = *reinterpret_cast<const float4*>(xin + i0 + 4 * q);
+                v[4 * q] = (int)f.x; v[4 * q + 1] = (int)f.y; v[4 * q + 2] = (int)f.z; v[4 * q + 3] = (int)f.w;
             }
+#pragma unroll
+            for (int q = 0; q < P; q++) loc += (unsigned long long)(uint32_t)(v[q] * v[q]);
             unsigned long long inc = loc;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -341,10 +346,13 @@ __global__ void __launch_bounds__(WS_THREADS) wsola_search_kernel(const WsolaArg
             }
             unsigned long long run = inc - loc;
 #pragma unroll
-            for (int q = 0; q < P; q++) {
-                S[i0 + q] = run;
-                const int v = (int)xin[i0 + q];
-                run += (unsigned long long)(uint32_t)(v * v);
+            for (int q = 0; q < P; q += 2) {
+                ulonglong2 two;
+                two.x = run;
+                run += (unsigned long long)(uint32_t)(v[q] * v[q]);
+                two.y = run;
+                run += (unsigned long long)(uint32_t)(v[q + 1] * v[q + 1]);
+                *reinterpret_cast<ulonglong2*>(S + i0 + q) = two;
             }
             if (lane == 31) S[WS_RANGE] = run;
         }
@@ -397,10 +405,12 @@ __global__ void __launch_bounds__(WS_THREADS) wsola_search_kernel(const WsolaArg
             float spf = 0.0f;
             const bool live = f <= hi - lo && off != best_off;
             if (live) {
-                const float* y = xin + (off + WS_SHIFT) + 24 * fs;
-                const float* x = tgt + 24 * fs;
+                // interleaved split (term 16 q + fs): the 16 lanes of a candidate read consecutive words
+                const float* y = xin + (off + WS_SHIFT) + fs;
+                const float* x = tgt + fs;
 #pragma unroll
-                for (int q = 0; q < 24; q++) spf = __fmaf_rn(x[q], y[q], spf);
+                for (int q = 0; q < WS_OVERLAP / WS_FINE_SPLITS; q++)
+                    spf = __fmaf_rn(x[WS_FINE_SPLITS * q], y[WS_FINE_SPLITS * q], spf);
             }
             if (tid < 128) {   // whole warps; f <= 7
 #pragma unroll

@@ -38,7 +38,7 @@ constexpr int PITCH_LAG0 = 53;        // lag of thread 0 (= 1 mod 4 keeps both f
 constexpr int PITCH_LPT = 4;          // lags per thread
 constexpr int PITCH_TPS = 64;         // threads per signal and half (57 used)
 constexpr int PITCH_Y = 512;          // staged floats per signal (zero padded)
-constexpr int PITCH_S = 504;          // prefix entries per signal
+constexpr int PITCH_S = 512;          // prefix entries per signal
 constexpr int PITCH_MAX_CAND = 64;    // per signal, beyond that: every lag is evaluated exactly
 constexpr float PITCH_EPS = 2.5e-4f;
 constexpr int PITCH_SCRATCH_WORDS = 2 * PITCH_Y + 2 * 2 * PITCH_S + 4 + 2 * (PITCH_MAX_CAND + 2) + 16 + 4 * 2 * PITCH_TPS;
@@ -64,29 +64,43 @@ __device__ __forceinline__ float pitch_exact_sums(const float* y, uint32_t lag, 
     return c;
 }
 
-// S[i] = sum_{j<i} s[j]^2 for i < PITCH_S, exact (int16 inputs, 504 * 2^30 < 2^64); one warp
+// S[i] = sum_{j<i} s[j]^2 for i < PITCH_S, exact (int16 inputs, 512 * 2^30 < 2^64); one warp.
+// A lane owns four groups of four consecutive samples, group q at 4 * (lane + 32 q): consecutive
+// lanes touch consecutive 8-byte (input) / 32-byte (output) pieces, so neither the loads nor the
+// 16-byte stores collide on a bank (a contiguous 16-sample run per lane would collide 8-16 way).
 __device__ __forceinline__ void pitch_prefix_warp(const int16_t* s, uint32_t need, unsigned long long* S) {
-    constexpr int PER = 16;  // 32 lanes * 16 = 512 >= PITCH_S
     const int lane = lane_id();
-    const int i0 = lane * PER;
-    int v[PER];
-    unsigned long long loc = 0;
+    int v[4][4];
+    unsigned long long rs[4];
 #pragma unroll
-    for (int k = 0; k < PER; k++) {
-        v[k] = (uint32_t)(i0 + k) < need ? (int)s[i0 + k] : 0;
-        loc += (unsigned long long)(uint32_t)(v[k] * v[k]);
+    for (int q = 0; q < 4; q++) {
+        const uint32_t i0 = 4u * (uint32_t)(lane + 32 * q);
+        rs[q] = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            v[q][c] = i0 + c < need ? (int)s[i0 + c] : 0;
+            rs[q] += (unsigned long long)(uint32_t)(v[q][c] * v[q][c]);
+        }
     }
-    unsigned long long inc = loc;
+    unsigned long long carry = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    unsigned long long run = inc - loc;  // exclusive
+    for (int q = 0; q < 4; q++) {
+        unsigned long long inc = rs[q];
 #pragma unroll
-    for (int k = 0; k < PER; k++) {
-        if (i0 + k < PITCH_S) S[i0 + k] = run;
-        run += (unsigned long long)(uint32_t)(v[k] * v[k]);
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        unsigned long long run = carry + inc - rs[q];   // exclusive prefix at the lane's first sample
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+        ulonglong2 lo, hi;
+        lo.x = run; run += (unsigned long long)(uint32_t)(v[q][0] * v[q][0]);
+        lo.y = run; run += (unsigned long long)(uint32_t)(v[q][1] * v[q][1]);
+        hi.x = run; run += (unsigned long long)(uint32_t)(v[q][2] * v[q][2]);
+        hi.y = run;
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(S + 4 * (lane + 32 * q));
+        dst[0] = lo;
+        dst[1] = hi;
     }
 }
 

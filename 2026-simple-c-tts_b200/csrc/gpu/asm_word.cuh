@@ -160,15 +160,21 @@ __device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t big, 
     // be processed in order with one barrier between a chunk's reads and writes
     for (uint32_t c0 = 0; c0 < len; c0 += ASM_THREADS * 8) {
         uint32_t i0 = c0 + (uint32_t)tid * 8;
-        int16_t v[8];
+        __align__(16) int16_t v[8];
         uint32_t km = 0, d0 = 0;
         if (i0 < len) {
             uint32_t j = i0 >> 5, b = i0 & 31;  // 8 | 32: one word
             uint32_t kw = words[j];
             km = (kw >> b) & 0xffu;
             d0 = woff[j] + __popc(kw & ((1u << b) - 1u));
-#pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = (i0 + k < len) ? reg[i0 + k] : (int16_t)0;
+            // the 8 samples at i0 (a multiple of 8) from the 16-byte grid of the region
+            int4 q = grid[i0 >> 3];
+            if (phase) {
+                int4 hi = make_int4(0, 0, 0, 0);
+                if (i0 + 8 < len + phase) hi = grid[(i0 >> 3) + 1];
+                q = shift_pick(q, hi, phase);
+            }
+            *reinterpret_cast<int4*>(v) = q;
         }
         __syncthreads();
         if (km) {

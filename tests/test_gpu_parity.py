@@ -227,3 +227,44 @@ def test_full_batch_properties(H, gpu):
         _assert_same(solo[k], inside, f"utt {u} alone vs in batch")
         want, _ = orc.synth(prm, plan.utt_ops(u), 1.0)
         _assert_same(inside, want, f"utt {u} vs oracle")
+
+
+def test_forced_hbm_window_and_chunked_batch(H, gpu, small_db, oracle_small, front_small, monkeypatch):
+    """The two rarely taken execution paths, forced: (a) a shared window so small that most regions
+    are assembled in the HBM slot and joins reach back across tasks (CTTS_GPU_WINDOW), (b) the drop-in
+    call cut into many launches whose copies overlap the next launch (CTTS_GPU_CHUNK_SAMPLES)."""
+    prm = front_small.params()
+    texts = H.corpus.batch(24, seed=47, target_chars=120) + ["", "a", ". . .", "olá mundo"]
+    plan = front_small.plan(texts)
+    want = [oracle_small.synth(prm, plan.utt_ops(u), 1.0)[0] for u in range(plan.n_utts)]
+    for env in ({"CTTS_GPU_WINDOW": "2048"}, {"CTTS_GPU_CHUNK_SAMPLES": "300000"},
+                {"CTTS_GPU_WINDOW": "4096", "CTTS_GPU_CHUNK_SAMPLES": "100000", "CTTS_GPU_CTAS_PER_SM": "2"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        g = gpu.GpuSynth(small_db, 0)
+        outs = g.synth_list(plan, prm)
+        for u in range(plan.n_utts):
+            _assert_same(outs[u], want[u], f"{env} utt {u}")
+        rp = g.create_plan(plan, prm)
+        rp.run()
+        for u, got in enumerate(rp.utterances()):
+            _assert_same(got, want[u], f"{env} resident utt {u}")
+        if "CTTS_GPU_WINDOW" in env:
+            assert rp.info().n_global_tasks > 0
+        for k in env:
+            monkeypatch.delenv(k)
+
+
+def test_bounds_are_upper_bounds_and_tighter_than_the_sum(H, synth_small, oracle_small, front_small):
+    """ctts_gpu_plan_bounds subtracts the crossfade overlap every certain join must consume; it must
+    still bound the true counts (pre-stretch and output) for every utterance, at every speed."""
+    prm = front_small.params()
+    texts = H.corpus.batch(40, seed=48, target_chars=90)
+    speeds = [1.0] * 30 + [0.5, 0.7, 0.9, 1.1, 1.3, 1.5, 1.7, 1.9, 2.0, 0.6]
+    plan = front_small.plan(texts, speeds)
+    tight = synth_small.bounds(plan).astype(np.int64)
+    _, loose, _ = front_small.bounds(plan)
+    assert (tight <= loose.astype(np.int64)).all() and (tight[:30] < loose[:30].astype(np.int64)).any()
+    for u in range(plan.n_utts):
+        pcm, st = oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))
+        assert len(pcm) <= tight[u], (u, len(pcm), tight[u])

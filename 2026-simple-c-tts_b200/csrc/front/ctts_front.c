@@ -15,7 +15,9 @@
 
 #include <locale.h>
 #include <math.h>
+#include <pthread.h>
 #include <regex.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -43,6 +45,7 @@ typedef struct {
 
 typedef struct {
     regex_t re;
+    char* pat;   /* the ERE that was compiled (kept so that worker threads can compile their own copy) */
     char replace[MAX_REPLACE];
 } norm_rule;
 
@@ -397,8 +400,11 @@ static int load_rules(ctts_front* f, const char* path) {
         if (!pat) continue;
         norm_rule* r = &f->rules[f->n_rules];
         int bad = regcomp(&r->re, pat, REG_EXTENDED);
-        free(pat);
-        if (bad) continue;
+        if (bad) {
+            free(pat);
+            continue;
+        }
+        r->pat = pat;
         strncpy(r->replace, comma + 1, MAX_REPLACE - 1);
         r->replace[MAX_REPLACE - 1] = '\0';
         f->n_rules++;
@@ -1052,7 +1058,10 @@ int ctts_front_open(ctts_front** out, const void* voice_db, size_t db_size,
 
 void ctts_front_close(ctts_front* f) {
     if (!f) return;
-    for (uint32_t i = 0; i < f->n_rules; i++) regfree(&f->rules[i].re);
+    for (uint32_t i = 0; i < f->n_rules; i++) {
+        regfree(&f->rules[i].re);
+        free(f->rules[i].pat);
+    }
     free(f->rules);
     if (f->c_locale) freelocale(f->c_locale);
     free(f);
@@ -1078,41 +1087,146 @@ int ctts_front_word_end_op(const ctts_front* f, int type_id, int word_index, int
     return CTTS_FRONT_OK;
 }
 
+/* One worker of ctts_front_plan_batch: plans texts [u0, u1) into its own op vector.  glibc's
+ * regexec serialises on a lock inside the compiled pattern, so every worker compiles its own
+ * copy of the rules; everything else in ctts_front is read-only after ctts_front_open. */
+typedef struct {
+    const ctts_front* f;
+    const char* const* texts;
+    uint32_t u0, u1;
+    opvec o;
+    uint32_t* n_ops;  /* per utterance (shared array, disjoint slices) */
+    uint32_t* stats;  /* may be NULL */
+    int err;
+} plan_job;
+
+static void* plan_worker(void* arg) {
+    plan_job* j = arg;
+    ctts_front local = *j->f;
+    norm_rule* rules = NULL;
+    if (local.n_rules) {
+        rules = calloc(local.n_rules, sizeof *rules);
+        if (!rules) {
+            j->err = CTTS_FRONT_ERR_OUT_OF_MEMORY;
+            return NULL;
+        }
+        locale_t prev = uselocale(local.c_locale);
+        for (uint32_t i = 0; i < local.n_rules; i++) {
+            rules[i] = j->f->rules[i];
+            if (regcomp(&rules[i].re, j->f->rules[i].pat, REG_EXTENDED) != 0) j->err = CTTS_FRONT_ERR_INVALID_ARG;
+        }
+        uselocale(prev);
+        local.rules = rules;
+    }
+    for (uint32_t u = j->u0; u < j->u1 && !j->err; u++) {
+        uint32_t before = j->o.n, found = 0, missing = 0;
+        j->err = j->texts[u] ? plan_text(&local, j->texts[u], &j->o, &found, &missing) : CTTS_FRONT_ERR_INVALID_ARG;
+        if (!j->err && j->o.oom) j->err = CTTS_FRONT_ERR_OUT_OF_MEMORY;
+        j->n_ops[u] = j->o.n - before;
+        if (j->stats) {
+            j->stats[2 * u] = found;
+            j->stats[2 * u + 1] = missing;
+        }
+    }
+    if (rules) {
+        for (uint32_t i = 0; i < local.n_rules; i++) regfree(&rules[i].re);
+        free(rules);
+    }
+    return NULL;
+}
+
+static uint32_t plan_threads(uint32_t n) {
+    long t = sysconf(_SC_NPROCESSORS_ONLN);
+    const char* e = getenv("CTTS_FRONT_THREADS");
+    if (e && atoi(e) > 0) t = atoi(e);
+    if (t < 1) t = 1;
+    if (t > 64) t = 64;
+    uint32_t by_work = n / 64; /* below ~64 texts per worker the start-up (rule compilation) dominates */
+    if (by_work < 1) by_work = 1;
+    return (uint32_t)t < by_work ? (uint32_t)t : by_work;
+}
+
 int ctts_front_plan_batch(ctts_front* f, const char* const* texts, const float* speeds,
                           uint32_t n, ctts_batch_plan* out, uint32_t* stats) {
     if (!f || !out || (n && !texts)) return CTTS_FRONT_ERR_INVALID_ARG;
     memset(out, 0, sizeof *out);
     uint32_t* begin = malloc(((size_t)n + 1) * sizeof *begin);
     float* sp = malloc(((size_t)n + 1) * sizeof *sp);
-    opvec o = {NULL, 0, 0, 0};
     if (!begin || !sp) {
         free(begin);
         free(sp);
         return CTTS_FRONT_ERR_OUT_OF_MEMORY;
     }
-    int err = CTTS_FRONT_OK;
-    for (uint32_t u = 0; u < n && !err; u++) {
-        begin[u] = o.n;
-        sp[u] = speeds ? speeds[u] : 1.0f;
-        uint32_t found = 0, missing = 0;
-        err = texts[u] ? plan_text(f, texts[u], &o, &found, &missing) : CTTS_FRONT_ERR_INVALID_ARG;
-        if (stats) {
-            stats[2 * u] = found;
-            stats[2 * u + 1] = missing;
-        }
+    for (uint32_t u = 0; u < n; u++) sp[u] = speeds ? speeds[u] : 1.0f;
+
+    /* utterances are independent: contiguous slices planned by worker threads, then concatenated */
+    const uint32_t T = plan_threads(n);
+    plan_job* jobs = calloc(T, sizeof *jobs);
+    pthread_t* tids = calloc(T, sizeof *tids);
+    if (!jobs || !tids) {
+        free(jobs);
+        free(tids);
+        free(begin);
+        free(sp);
+        return CTTS_FRONT_ERR_OUT_OF_MEMORY;
     }
-    begin[n] = o.n;
+    for (uint32_t t = 0; t < T; t++) {
+        jobs[t].f = f;
+        jobs[t].texts = texts;
+        jobs[t].u0 = (uint32_t)((uint64_t)n * t / T);
+        jobs[t].u1 = (uint32_t)((uint64_t)n * (t + 1) / T);
+        jobs[t].n_ops = begin; /* per-utterance counts first, prefix-summed below */
+        jobs[t].stats = stats;
+    }
+    int err = CTTS_FRONT_OK;
+    if (T == 1) {
+        plan_worker(&jobs[0]);
+    } else {
+        uint32_t started = 0;
+        for (; started < T; started++)
+            if (pthread_create(&tids[started], NULL, plan_worker, &jobs[started]) != 0) break;
+        for (uint32_t t = started; t < T; t++) plan_worker(&jobs[t]); /* could not start: run inline */
+        for (uint32_t t = 0; t < started; t++) pthread_join(tids[t], NULL);
+    }
+    uint64_t total = 0;
+    for (uint32_t t = 0; t < T; t++) {
+        if (jobs[t].err && !err) err = jobs[t].err;
+        total += jobs[t].o.n;
+    }
+    ctts_plan_op* ops = NULL;
+    if (!err && total > 0xffffffffull) err = CTTS_FRONT_ERR_INVALID_ARG;
+    if (!err) {
+        ops = malloc((total ? total : 1) * sizeof *ops);
+        if (!ops) err = CTTS_FRONT_ERR_OUT_OF_MEMORY;
+    }
+    if (!err) {
+        uint64_t at = 0;
+        for (uint32_t t = 0; t < T; t++) {
+            if (jobs[t].o.n) memcpy(ops + at, jobs[t].o.v, (size_t)jobs[t].o.n * sizeof *ops);
+            at += jobs[t].o.n;
+        }
+        uint32_t run = 0;
+        for (uint32_t u = 0; u < n; u++) {
+            uint32_t c = begin[u];
+            begin[u] = run;
+            run += c;
+        }
+        begin[n] = run;
+    }
+    for (uint32_t t = 0; t < T; t++) free(jobs[t].o.v);
+    free(jobs);
+    free(tids);
     if (err) {
         free(begin);
         free(sp);
-        free(o.v);
+        free(ops);
         return err;
     }
     out->n_utts = n;
-    out->n_ops = o.n;
+    out->n_ops = (uint32_t)total;
     out->utt_op_begin = begin;
     out->speed = sp;
-    out->ops = o.v ? o.v : calloc(1, sizeof(ctts_plan_op));
+    out->ops = ops;
     return CTTS_FRONT_OK;
 }
 

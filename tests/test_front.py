@@ -122,3 +122,18 @@ def test_bounds_and_select(H, front_small, small_db):
     sub = plan.select([4, 1])
     assert sub.n_utts == 2 and float(sub.speed[0]) == 2.0
     assert np.array_equal(sub.utt_ops(1), plan.utt_ops(1))
+
+
+def test_threaded_planning_is_identical(H, front_small, monkeypatch):
+    """ctts_front_plan_batch plans contiguous slices on worker threads (each with its own compiled
+    rules): the concatenated plan must be byte-identical to the single-threaded one."""
+    texts = H.corpus.batch(700, seed=11, target_chars=60) + ["", "olá mundo", "12 casas, 3 rios!"]
+    speeds = np.linspace(0.5, 2.0, len(texts)).astype(np.float32)
+    monkeypatch.setenv("CTTS_FRONT_THREADS", "1")
+    a = front_small.plan(texts, speeds)
+    for t in ("3", "8"):
+        monkeypatch.setenv("CTTS_FRONT_THREADS", t)
+        b = front_small.plan(texts, speeds)
+        assert np.array_equal(a.utt_op_begin, b.utt_op_begin) and a.ops.tobytes() == b.ops.tobytes()
+        assert np.array_equal(a.found, b.found) and np.array_equal(a.missing, b.missing)
+        assert np.array_equal(a.speed, b.speed)

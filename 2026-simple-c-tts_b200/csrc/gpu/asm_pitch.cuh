@@ -197,8 +197,8 @@ __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int1
             sc[k] = -1.0f;
             if (lag >= lo && lag <= hi) {
                 const float e2 = (float)(S[lag + len] - S[lag]);
-                const float nrm = sqrtf(e1 * e2);
-                sc[k] = nrm > 0.0f ? c[k] / nrm : 0.0f;
+                const float nn = e1 * e2;   // exact integers >= 1 when nonzero; the filter may use rsqrt.approx (2^-22)
+                sc[k] = nn > 0.0f ? c[k] * rsqrt_approx(nn) : 0.0f;
                 my_max = fmaxf(my_max, sc[k]);
             }
         }

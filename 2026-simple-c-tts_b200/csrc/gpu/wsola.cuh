@@ -372,12 +372,12 @@ __global__ void __launch_bounds__(WS_THREADS, 8) wsola_search_kernel(const Wsola
             const float spc = sidx == 0 ? sp[0] : sidx == 1 ? sp[1] : sidx == 2 ? sp[2] : sp[3];
             if (c >= c_first && c <= c_last) {
                 const float sa = (float)(S[4 * c + WS_OVERLAP] - S[4 * c]);
-                const float den = sqrtf(sa * sb);
+                const float den2 = sa * sb;   // the filter only needs an approximation: rsqrt.approx (2^-22)
                 float a = 0.0f, e = 0.0f;
-                if (den > 1.01f) {
-                    a = spc / den;
+                if (den2 > 1.02f) {
+                    a = spc * rsqrt_approx(den2);
                     e = WS_EPS;
-                } else if (den >= 0.99f) {   // cannot tell which side of 1 the reference's denominator falls
+                } else if (den2 >= 0.98f) {   // cannot tell which side of 1 the reference's denominator falls
                     a = 0.0f;
                     e = 4.0f;
                 }
@@ -430,12 +430,12 @@ __global__ void __launch_bounds__(WS_THREADS, 8) wsola_search_kernel(const Wsola
                 const int slot = 1 + (off - flo) - (best_off >= flo && best_off < off ? 1 : 0);
                 const int xo = off + WS_SHIFT;
                 const float sa = (float)(S[xo + WS_OVERLAP] - S[xo]);
-                const float den = sqrtf(sa * sb);
+                const float den2 = sa * sb;
                 float a = 0.0f, e = 0.0f;
-                if (den > 1.01f) {
-                    a = spf / den;
+                if (den2 > 1.02f) {
+                    a = spf * rsqrt_approx(den2);
                     e = WS_EPS;
-                } else if (den >= 0.99f) {
+                } else if (den2 >= 0.98f) {
                     e = 4.0f;
                 }
                 ca[slot] = a;

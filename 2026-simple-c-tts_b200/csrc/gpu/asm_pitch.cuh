@@ -343,13 +343,18 @@ __device__ void match_energy(const State& s, const Smem& sm, int16_t* us, uint32
     const int tid = threadIdx.x;
     const int16_t* tail = s.w + ((int)s.cnt - (int)len);
     long long sp = sumsq_range(tail, len), sn = sumsq_range(us, len);
-    block_allreduce_add2<ASM_THREADS>(sp, sn, reinterpret_cast<long long*>(sm.red));
-    float pr = (float)sqrt((double)sp / (double)len);
-    float nr = (float)sqrt((double)sn / (double)len);
-    if (pr < 1.0f || nr < 1.0f) return;
-    float ratio = pr / nr;
-    if (ratio > 2.0f) ratio = 2.0f;
-    if (ratio < 0.5f) ratio = 0.5f;
+    // ratio = clamp(prev_rms / next_rms) with both rms values in double (ctts.c:1741-1749): one thread
+    const unsigned long long rr = block_sum2_then<ASM_THREADS>(sp, sn, reinterpret_cast<long long*>(sm.red), [&](long long tp, long long tn) {
+        const float pr = (float)sqrt((double)tp / (double)len);
+        const float nr = (float)sqrt((double)tn / (double)len);
+        if (pr < 1.0f || nr < 1.0f) return 0ull;
+        float ratio = pr / nr;
+        if (ratio > 2.0f) ratio = 2.0f;
+        if (ratio < 0.5f) ratio = 0.5f;
+        return (1ull << 32) | (unsigned long long)__float_as_uint(ratio);
+    });
+    if ((rr >> 32) == 0) return;
+    const float ratio = __uint_as_float((uint32_t)rr);
     // two samples per step (us is 4-byte aligned); t = i / len with the hoisted reciprocal
     const float flen = (float)len, rlen = recip_for_div(flen);
     uint32_t* us2 = reinterpret_cast<uint32_t*>(us);

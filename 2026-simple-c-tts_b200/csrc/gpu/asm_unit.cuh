@@ -137,18 +137,24 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
     // ---- pass 1: sum of squares (normalize_rms, ctts.c:1709; double sum of integers == integer sum)
     long long ss = 0;
     for (uint32_t v = tid; v < nvec; v += ASM_THREADS) ss += sumsq8(__ldg(srcv + v));
-    ss = block_allreduce<ASM_THREADS>(ss, OpAddI64(), reinterpret_cast<long long*>(sm.red));
-    bool scale = false;
-    float g = 1.0f;
-    if (A.prm.target_rms > 0) {
-        float rms = (float)sqrt((double)ss / (double)n);
-        if (!(rms < 1.0f)) {
-            g = A.prm.target_rms / rms;
-            if (g > 3.0f) g = 3.0f;
-            if (g < 0.1f) g = 0.1f;
-            scale = true;
+    // gain = clamp(target / rms), rms = (float)sqrt(sum / n) in double (calculate_rms, ctts.c:1697): one thread
+    const float target_rms = A.prm.target_rms;
+    const unsigned long long gs = block_sum_then<ASM_THREADS>(ss, reinterpret_cast<long long*>(sm.red), [&](long long tot) {
+        float gg = 1.0f;
+        uint32_t sc = 0;
+        if (target_rms > 0) {
+            const float rms = (float)sqrt((double)tot / (double)n);
+            if (!(rms < 1.0f)) {
+                gg = target_rms / rms;
+                if (gg > 3.0f) gg = 3.0f;
+                if (gg < 0.1f) gg = 0.1f;
+                sc = 1;
+            }
         }
-    }
+        return ((unsigned long long)sc << 32) | __float_as_uint(gg);
+    });
+    const bool scale = (gs >> 32) != 0;
+    const float g = __uint_as_float((uint32_t)gs);
 
     // ---- pass 2: scale; head -> hstage, body -> window (aligned vectors of the window)
     for (uint32_t v = tid; v < (hs >> 3); v += ASM_THREADS) {
@@ -201,8 +207,9 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
     int dc = 0;
     if (remove_dc) {
         for (uint32_t i = tid; i < hsn; i += ASM_THREADS) dsum += us[i];
-        long long sum = block_allreduce<ASM_THREADS>((long long)dsum, OpAddI64(), reinterpret_cast<long long*>(sm.red));
-        dc = (int)(int16_t)(sum / (long long)n);
+        dc = (int)block_sum_then<ASM_THREADS>((long long)dsum, reinterpret_cast<long long*>(sm.red), [&](long long sum) {
+            return (unsigned long long)(uint32_t)(int)(int16_t)(sum / (long long)n);
+        });
     }
     // body in place
     if (dc != 0) {

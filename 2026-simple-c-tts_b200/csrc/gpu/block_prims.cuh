@@ -75,6 +75,50 @@ __device__ __forceinline__ void block_allreduce_add2(long long& a, long long& b,
     b = rb;
 }
 
+// Sum of one (or two) 64-bit integers per thread; THREAD 0 ALONE maps the total(s) through fn --
+// the FP64 / 64-bit-division work that follows such a sum would otherwise be repeated by every
+// thread -- and the 64-bit result is broadcast.  Two barriers, like block_allreduce.
+// `red` needs 2 * NT/32 + 1 entries.
+template <int NT, typename F>
+__device__ __forceinline__ unsigned long long block_sum_then(long long a, long long* red, F fn) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane_id() == 0) red[warp_id()] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+#pragma unroll
+        for (int k = 0; k < NT / 32; k++) t += red[k];
+        reinterpret_cast<unsigned long long*>(red)[2 * (NT / 32)] = fn(t);
+    }
+    __syncthreads();
+    return reinterpret_cast<unsigned long long*>(red)[2 * (NT / 32)];
+}
+template <int NT, typename F>
+__device__ __forceinline__ unsigned long long block_sum2_then(long long a, long long b, long long* red, F fn) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane_id() == 0) {
+        red[warp_id()] = a;
+        red[NT / 32 + warp_id()] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long ta = 0, tb = 0;
+#pragma unroll
+        for (int k = 0; k < NT / 32; k++) {
+            ta += red[k];
+            tb += red[NT / 32 + k];
+        }
+        reinterpret_cast<unsigned long long*>(red)[2 * (NT / 32)] = fn(ta, tb);
+    }
+    __syncthreads();
+    return reinterpret_cast<unsigned long long*>(red)[2 * (NT / 32)];
+}
+
 // Exclusive scan of one value per thread in thread order (reverse = suffix scan).
 // Op must be commutative and associative.  Optionally returns the CTA total.
 template <int NT, typename V, typename Op>

@@ -81,9 +81,10 @@ __device__ __forceinline__ uint32_t sub_dc2(uint32_t w, const DcPack& d) {
 __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_plan_op& op) {
     const int tid = threadIdx.x;
     if (op.a >= A.n_units) { s.err = ERR_BAD_OP; return; }
-    const uint32_t n = __ldg(A.unit_cnt + op.a);
+    // the plan compiler stored the unit's length and pool offset in the op's unused float fields
+    const uint32_t n = __float_as_uint(op.f0);
     if (n == 0) return;
-    const int16_t* src = A.pool + __ldg(A.unit_off + op.a);
+    const int16_t* src = A.pool + __float_as_uint(op.f1);
     const int4* srcv = reinterpret_cast<const int4*>(src);
     const uint32_t nvec = (n + 7) >> 3;
     int16_t* us = sm.hstage;

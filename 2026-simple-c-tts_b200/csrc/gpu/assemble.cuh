@@ -70,11 +70,25 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
         __syncthreads();
     }
 
+    // the task's ops in one coalesced load (an op fetched from HBM per step would stall the whole CTA)
+    {
+        const uint32_t n_pref = min(task.op_end - task.op_begin, TASK_OPS_SMEM);
+        if ((uint32_t)tid < 2 * n_pref) sm.ops[tid] = __ldg(reinterpret_cast<const int4*>(A.ops + task.op_begin) + tid);
+        __syncthreads();
+    }
     for (uint32_t k = task.op_begin; k < task.op_end && !s.err; k++) {
         ctts_plan_op op;
         {
-            const int4* p = reinterpret_cast<const int4*>(A.ops + k);
-            int4 lo = __ldg(p), hi = __ldg(p + 1);
+            const uint32_t rel = k - task.op_begin;
+            int4 lo, hi;
+            if (rel < TASK_OPS_SMEM) {
+                lo = sm.ops[2 * rel];
+                hi = sm.ops[2 * rel + 1];
+            } else {
+                const int4* p = reinterpret_cast<const int4*>(A.ops + k);
+                lo = __ldg(p);
+                hi = __ldg(p + 1);
+            }
             *reinterpret_cast<int4*>(&op) = lo;
             *(reinterpret_cast<int4*>(&op) + 1) = hi;
         }
@@ -129,6 +143,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 3) assemble_kernel(const AsmArgs 
     sm.nrm2 = reinterpret_cast<float*>(smem_raw + SMEM_NRM2);
     sm.red = reinterpret_cast<unsigned long long*>(smem_raw + SMEM_RED);
     sm.bcast = reinterpret_cast<uint32_t*>(smem_raw + SMEM_BCAST);
+    sm.ops = reinterpret_cast<int4*>(smem_raw + SMEM_OPS);
     sm.scratch = reinterpret_cast<uint32_t*>(smem_raw + SMEM_SCRATCH);
     sm.hstage = reinterpret_cast<int16_t*>(smem_raw + SMEM_HSTAGE);
     sm.win = sm.hstage + A.hcap;

@@ -54,6 +54,7 @@ struct ctts_gpu_ctx {
     uint32_t n_units = 0;
     uint32_t max_unit = 0;
     std::vector<uint32_t> unit_cnt;
+    std::vector<uint32_t> unit_off;   // offsets into the re-packed pool (samples, multiples of 8)
     int sm_count = 0;
     int smem_per_sm = 0;
     int smem_optin = 0;
@@ -304,7 +305,8 @@ int ctts_gpu_init(ctts_gpu_ctx** out, const void* voice_db, size_t db_size, int 
     const uint8_t* pcm = base + h.audio_offset;  // may be 2-byte misaligned
     ctx->n_units = h.unit_count;
     ctx->unit_cnt.resize(h.unit_count);
-    std::vector<uint32_t> unit_off(h.unit_count);
+    std::vector<uint32_t>& unit_off = ctx->unit_off;
+    unit_off.resize(h.unit_count);
     uint64_t packed = 0;
     for (uint32_t u = 0; u < h.unit_count; u++) {
         DbEntry e;
@@ -734,6 +736,10 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c) {
             switch (op.kind) {
                 case CTTS_OP_UNIT: {
                     const uint32_t cn = ucnt[op.a];
+                    // private copy: the unit's length and pool offset ride in the (unused) float fields,
+                    // so the kernel needs no dependent table look-up before the gather
+                    memcpy(&op.f0, &cn, 4);
+                    memcpy(&op.f1, &ctx->unit_off[op.a], 4);
                     count_ub += cn;
                     p->gather += cn;
                     rb += unit_append_bound(op, cn, L);

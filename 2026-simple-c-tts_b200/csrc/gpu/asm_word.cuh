@@ -15,7 +15,12 @@ __device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t big, 
     const uint32_t phase = (uint32_t)((reinterpret_cast<uintptr_t>(reg) >> 1) & 7u);
     const int4* grid = reinterpret_cast<const int4*>(reg - phase);
     const uint32_t gvec = (phase + len + 7) >> 3;
-    // max |x| over the region, |.| with the reference's int16 wrap (abs16(-32768) < 0 never wins)
+    // max |x| over the region, |.| with the reference's int16 wrap (abs16(-32768) < 0 never wins).
+    // The maximum of every 8-sample grid vector is kept (vm): a silent run long enough to be cut
+    // must contain whole silent vectors, so most regions are cleared below without a second pass.
+    const uint32_t wn = (len + 31) >> 5;
+    const bool have_vm = 2 * wn + (gvec + 1) / 2 + 2 <= SCR_WORDS;
+    uint16_t* vm = reinterpret_cast<uint16_t*>(sm.scratch + 2 * wn);   // after the bit mask arrays
     uint32_t pk2 = 0;
     for (uint32_t j = tid; j < gvec; j += ASM_THREADS) {
         int4 q = grid[j];
@@ -26,10 +31,10 @@ __device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t big, 
             for (int k = 0; k < 8; k++)
                 if (i0 + k < 0 || i0 + k >= (int)len) e[k] = 0;
         }
-        pk2 = __vmaxs2(pk2, absmax0_2((uint32_t)q.x));
-        pk2 = __vmaxs2(pk2, absmax0_2((uint32_t)q.y));
-        pk2 = __vmaxs2(pk2, absmax0_2((uint32_t)q.z));
-        pk2 = __vmaxs2(pk2, absmax0_2((uint32_t)q.w));
+        uint32_t m2 = __vmaxs2(absmax0_2((uint32_t)q.x), absmax0_2((uint32_t)q.y));
+        m2 = __vmaxs2(m2, __vmaxs2(absmax0_2((uint32_t)q.z), absmax0_2((uint32_t)q.w)));
+        pk2 = __vmaxs2(pk2, m2);
+        if (have_vm) vm[j] = (uint16_t)max(m2 & 0xffffu, m2 >> 16);
     }
     int pk = max((int)(pk2 & 0xffffu), (int)(pk2 >> 16));
     pk = block_allreduce<ASM_THREADS>(pk, OpMaxI32(), reinterpret_cast<int*>(sm.red));
@@ -38,7 +43,24 @@ __device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t big, 
     uint32_t keep_n = min_sil / 4;
     if (keep_n < 10) keep_n = 10;
 
-    const uint32_t wn = (len + 31) >> 5;
+    // A run of >= min_sil silent samples covers >= (min_sil - 7) / 8 whole grid vectors, all of them
+    // silent; that many consecutive vectors contain an aligned group of g = 32, 16 or 8 of them
+    // (2g - 1 <= count).  No such group: nothing can be cut (ctts.c:1662-1668 copies every run).
+    if (have_vm && limit >= 0 && min_sil >= 15 + 8 * 14) {
+        const uint32_t needv = (min_sil - 7) / 8;
+        const int g = needv >= 63 ? 32 : needv >= 31 ? 16 : 8;
+        int found = 0;
+        for (uint32_t j0 = 0; j0 < gvec; j0 += ASM_THREADS) {
+            const uint32_t j = j0 + tid;
+            const bool sil = j < gvec && (int)vm[j] <= limit;
+            const uint32_t w = __ballot_sync(0xffffffffu, sil);
+            if (g == 32) found |= w == 0xffffffffu;
+            else if (g == 16) found |= (w & 0xffffu) == 0xffffu || (w >> 16) == 0xffffu;
+            else found |= ((w & (w >> 1) & (w >> 2) & (w >> 3) & (w >> 4) & (w >> 5) & (w >> 6) & (w >> 7)) & 0x01010101u) != 0;
+        }
+        if (!__syncthreads_or(found)) return len;
+    }
+
     uint32_t* words;
     if (2 * wn <= SCR_WORDS) words = sm.scratch;
     else words = A.trim_scratch + (size_t)big * A.trim_scratch_words;   // host sized it for this task

@@ -142,15 +142,6 @@ int fail(ctts_gpu_ctx* c, int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                   \
     } while (0)
 
-template <typename T>
-int upload(ctts_gpu_ctx* ctx, T** dptr, const std::vector<T>& h) {
-    size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
-    CU(ctx, cudaMalloc(reinterpret_cast<void**>(dptr), bytes));
-    if (!h.empty())
-        CU(ctx, cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    return 0;
-}
-
 // speed handling of ctts_synthesize / time_stretch (ctts.c:3907, :3493-3503):
 // returns true when the utterance goes through WSOLA and sets the synthesis hop
 bool needs_stretch(float speed, uint32_t* hop) {
@@ -796,7 +787,7 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c) {
             t.bound = (uint32_t)std::min<uint64_t>(h.bound, 0xffffffffull);
             t.pred = last_index[ui];
             const bool stretched = p->pre_off[u] != ~0ull;
-            t.flags = (k + 1 == ht_begin[ui + 1] - ht_begin[ui] ? ctts::TASK_LAST : 0u) | (stretched ? ctts::TASK_TO_PRE : 0u);
+            t.flags = (k + 1 == ht_begin[ui + 1] - ht_begin[ui] ? (uint32_t)ctts::TASK_LAST : 0u) | (stretched ? (uint32_t)ctts::TASK_TO_PRE : 0u);
             if (h.bound > wcap) { t.flags |= ctts::TASK_GLOBAL; p->n_global_tasks++; }
             t.dst_cap = stretched ? (uint32_t)p->pre_cap[u] : (uint32_t)(p->offsets[u + 1] - p->offsets[u]);
             t.dst_off = stretched ? p->pre_off[u] : p->offsets[u];

@@ -473,13 +473,16 @@ __global__ void __launch_bounds__(OLA_THREADS) wsola_ola_kernel(const WsolaArgs 
     int16_t* out = A.out + task.out_off;
     const uint32_t first = A.ola_block_first[blockIdx.x];
     int last_nz = -1;
+    // j / hop by multiplication: exact for j < 2^24 and hop <= 256 (hop = (size_t)(128 / speed), speed >= 0.5)
+    const bool mulhi_ok = used < (1u << 24) && hop <= 256;
+    const uint32_t magic = (uint32_t)((0x100000000ull + hop - 1) / hop);
 #pragma unroll
     for (int r = 0; r < OLA_SPT; r++) {
         uint32_t j = first + (uint32_t)r * OLA_THREADS + (uint32_t)tid;
         if (j >= used || j >= task.out_cap) continue;
-        uint32_t k_hi = j / hop;
+        uint32_t k_hi = mulhi_ok ? __umulhi(j, magic) : j / hop;
         if (k_hi > frames - 1) k_hi = frames - 1;
-        uint32_t k_lo = j < WS_FRAME ? 0u : (j - WS_FRAME) / hop + 1u;
+        uint32_t k_lo = j < WS_FRAME ? 0u : (mulhi_ok ? __umulhi(j - WS_FRAME, magic) : (j - WS_FRAME) / hop) + 1u;
         int16_t acc = 0;
         float norm = 0.0f;
         for (uint32_t k = k_lo; k <= k_hi; k++) {

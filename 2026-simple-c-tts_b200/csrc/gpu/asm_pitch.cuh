@@ -23,7 +23,7 @@ namespace ctts {
 //     For 220 terms |a - r| <= 4.0e-5 where r is the reference's score (standard
 //     summation error bound, gamma_n * sum|x_i*y_i| <= gamma_n * sqrt(e1*e2) by
 //     Cauchy-Schwarz; DESIGN.md derives it).
-//  2. DECIDE: with eps = 2.5e-4 (6 x the bound) a signal is unvoiced if
+//  2. DECIDE: with eps = 1e-4 (3 x the rigorous worst-case bound 3.4e-5) a signal is unvoiced if
 //     max a <= 0.3 - eps.  Otherwise only lags with a >= max a - 2*eps can be the
 //     reference's arg max.  If that is a single lag and its score exceeds
 //     0.3 + eps, the answer is known.  Else the candidates (typically 2-3) are
@@ -40,7 +40,7 @@ constexpr int PITCH_TPS = 64;         // threads per signal and half (57 used)
 constexpr int PITCH_Y = 512;          // staged floats per signal (zero padded)
 constexpr int PITCH_S = 512;          // prefix entries per signal
 constexpr int PITCH_MAX_CAND = 64;    // per signal, beyond that: every lag is evaluated exactly
-constexpr float PITCH_EPS = 2.5e-4f;
+constexpr float PITCH_EPS = 1e-4f;
 constexpr int PITCH_SCRATCH_WORDS = 2 * PITCH_Y + 2 * 2 * PITCH_S + 4 + 2 * (PITCH_MAX_CAND + 2) + 16 + 4 * 2 * PITCH_TPS;
 static_assert(ASM_THREADS == 4 * PITCH_TPS, "2 signals x 2 halves x PITCH_TPS threads");
 static_assert(PITCH_LAG0 % 4 == 1 && PITCH_LAG0 <= PITCH_LO, "lag tiling");

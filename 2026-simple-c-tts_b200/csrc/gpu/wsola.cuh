@@ -16,8 +16,9 @@
 //              are evaluated with the reference's exact loop, one thread each, and compared
 //              exactly (largest score, first in scan order on ties).  A score whose
 //              denominator is clearly < 1 is exactly 0 (ctts.c:3426) and needs no evaluation.
-//    The 640-sample view of frame k+1 does not depend on the decision for frame k, so it is
-//    prefetched while frame k is decided.  Output: the analysis position of every frame.
+//    Consecutive views overlap by 512 samples: the samples (as floats) and the prefix sums live
+//    in rings, a frame appends only its 128 new samples, prefetched while the previous frame is
+//    decided.  Output: the analysis position of every frame.
 // 2. wsola_ola_kernel: embarrassingly parallel gather-form overlap-add.  Each
 //    output sample adds its <= 8 windowed frame contributions in frame order
 //    into an int16 accumulator that wraps exactly like the reference's `+=`
@@ -36,11 +37,11 @@ constexpr int WS_HOP = 128;      // analysis hop
 constexpr int WS_OVERLAP = 384;  // correlation length
 constexpr int WS_SHIFT = 128;    // +-search range
 constexpr int WS_RANGE = 2 * WS_SHIFT + WS_OVERLAP;  // 640 samples visible to the candidates
-constexpr int WS_THREADS = 192;  // 17 candidate groups x 8 splits = 136 filter threads, 1 prefix warp
-constexpr int WS_GROUPS = 17;    // groups of 4 coarse candidates (65 candidates, the last group holds 1)
+constexpr int WS_THREADS = 128;  // 16 candidate groups x 8 splits; the 65th candidate is spread over all threads
+constexpr int WS_GROUPS = 16;    // groups of 4 coarse candidates (offsets -128 .. 124)
 constexpr int WS_SPLITS = 8;     // threads sharing the 384 terms of a group
 constexpr int WS_FINE_SPLITS = 16;
-constexpr int WS_XPAD = 672;     // staged floats (640 + what the partial last group reads past the end)
+constexpr int WS_RING = 1024;    // samples kept: a double-mapped ring makes every 640-sample view contiguous
 constexpr int WS_MAXC = 72;      // candidates of one decision
 constexpr float WS_EPS = 1e-4f;
 constexpr int OLA_THREADS = 256;
@@ -215,12 +216,24 @@ __device__ int ws_decide(const WsDecide& D, int cnt, const float* xin, const flo
     return w;
 }
 
-__global__ void __launch_bounds__(WS_THREADS, 8) wsola_search_kernel(const WsolaArgs A) {
-    __shared__ __align__(16) float xbuf[2][WS_XPAD];   // input[nominal-128 .. nominal+512), zero padded
-    __shared__ __align__(16) float tgt[WS_OVERLAP];    // previous frame's last 384 samples
-    __shared__ __align__(16) unsigned long long S[WS_RANGE + 8];     // S[i] = sum_{j<i} xin[j]^2 (exact)
+// exact integer (< 2^40) -> float, two conversions instead of the 64-bit library path; the two
+// roundings (<= 2^-24 each) are inside the filter's error budget
+__device__ __forceinline__ float ws_u64_to_float(unsigned long long v) {
+    return __fmaf_rn((float)(uint32_t)(v >> 32), 4294967296.0f, (float)(uint32_t)v);
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 10) wsola_search_kernel(const WsolaArgs A) {
+    // ring of the last 1024 input samples as floats, stored twice (i and i + 1024): the view of a
+    // frame, input[nominal-128 .. nominal+512), is 640 contiguous floats at a 16-byte aligned offset
+    __shared__ __align__(16) float xr[2 * WS_RING];
+    // Pr[p & 1023] = sum_{j<p} input[j]^2 (exact, 64-bit): every window energy is a difference
+    __shared__ __align__(16) unsigned long long Pr[WS_RING];
+    __shared__ __align__(16) float tgt[WS_OVERLAP];    // previous frame's last 384 samples (aligned copy)
+    __shared__ unsigned long long s_wtot[WS_THREADS / 32];
+    __shared__ unsigned long long s_ptotal;
     __shared__ float ca[WS_MAXC], ce[WS_MAXC];
     __shared__ int xoff[WS_MAXC], list[WS_MAXC], coff[WS_MAXC];
+    __shared__ float s_c64[WS_GROUPS];                 // partial cross terms of the 65th candidate
     __shared__ int s_cnt[4], s_sb_valid;
     __shared__ float s_sb;
 
@@ -236,6 +249,8 @@ __global__ void __launch_bounds__(WS_THREADS, 8) wsola_search_kernel(const Wsola
     if (tid == 0) {
         A.n_frames[blockIdx.x] = frames;
         *exact_count = 0;
+        s_ptotal = 0ull;
+        Pr[0] = 0ull;
     }
     if (frames == 0) return;
     if (tid == 0) fpos[0] = 0;
@@ -243,43 +258,51 @@ __global__ void __launch_bounds__(WS_THREADS, 8) wsola_search_kernel(const Wsola
 
     WsDecide D{ca, ce, xoff, list, s_cnt, &s_sb, &s_sb_valid, exact_count};
 
-    // the view of frame k: xin[i] = in[k*128 - 128 + i]; loaded one frame ahead into registers
-    constexpr int PER = (WS_XPAD + WS_THREADS - 1) / WS_THREADS;   // 4
-    float pre_v[PER];
-    auto fetch = [&](uint32_t k) {
-        const int p0 = (int)(k * WS_HOP) - WS_SHIFT;   // first sample of the view (>= 0 for k >= 1)
-        if (p0 >= 0 && (uint32_t)(p0 + WS_RANGE) <= n) {
-            // interior frame (all but the last few): no bounds checks
+    // append 128 samples (one per thread) at absolute positions base .. base+127 to both rings.
+    // Two barriers inside; the caller synchronises before anything reads the rings.
+    auto append = [&](uint32_t base, float v) {
+        const uint32_t p = base + (uint32_t)tid;
+        xr[p & (WS_RING - 1)] = v;
+        xr[(p & (WS_RING - 1)) + WS_RING] = v;
+        const int iv = (int)v;
+        const unsigned long long q = (unsigned long long)(uint32_t)(iv * iv);
+        unsigned long long inc = q;
 #pragma unroll
-            for (int r = 0; r < PER; r++) {
-                const int i = tid + r * WS_THREADS;
-                pre_v[r] = i < WS_RANGE ? (float)in[p0 + i] : 0.0f;
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < PER; r++) {
-                const int i = tid + r * WS_THREADS;
-                const int pidx = p0 + i;
-                pre_v[r] = (i < WS_RANGE && pidx >= 0 && (uint32_t)pidx < n) ? (float)in[pidx] : 0.0f;
-            }
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
         }
-    };
-    auto commit = [&](float* xin) {
+        if (lane == 31) s_wtot[warp] = inc;
+        __syncthreads();
+        unsigned long long carry = s_ptotal;
 #pragma unroll
-        for (int r = 0; r < PER; r++) {
-            const int i = tid + r * WS_THREADS;
-            if (i < WS_XPAD) xin[i] = pre_v[r];
-        }
+        for (int w = 0; w < WS_THREADS / 32; w++)
+            if (w < warp) carry += s_wtot[w];
+        Pr[(p + 1) & (WS_RING - 1)] = carry + inc;
+        __syncthreads();
+        if (tid == WS_THREADS - 1) s_ptotal = carry + inc;
     };
-    if (frames > 1) fetch(1);
+    auto load = [&](uint32_t base) {
+        const uint32_t p = base + (uint32_t)tid;
+        return p < n ? (float)in[p] : 0.0f;
+    };
+    // frame 1 sees input[0 .. 640)
+    for (uint32_t b = 0; b < WS_RANGE; b += WS_THREADS) {
+        append(b, load(b));
+        __syncthreads();
+    }
+    float next_v = frames > 2 ? load(WS_RANGE) : 0.0f;   // frame 2 adds input[640 .. 768)
 
     for (uint32_t k = 1; k < frames; k++) {
-        float* xin = xbuf[k & 1];
         const int nominal = (int)(k * WS_HOP);
-        commit(xin);
+        const uint32_t vstart = (uint32_t)(nominal - WS_SHIFT);           // absolute position of the view
+        if (k >= 2) {
+            append(vstart + WS_RANGE - WS_THREADS, next_v);              // the 128 samples this view adds
+            if (k + 1 < frames) next_v = load(vstart + WS_RANGE);       // in flight while this frame is decided
+        }
+        const float* xin = xr + (vstart & (WS_RING - 1));
         if (tid == 0) s_sb_valid = 0;
         __syncthreads();
-        if (k + 1 < frames) fetch(k + 1);   // in flight while this frame is decided
         // the target inside the view: in[prev_pos + 128 ..) = xin[ti ..], ti in [0, 256]
         const int ti = (int)prev_pos + (WS_FRAME - WS_OVERLAP) - (nominal - WS_SHIFT);
         int tgt_nz = 0;
@@ -290,7 +313,7 @@ __global__ void __launch_bounds__(WS_THREADS, 8) wsola_search_kernel(const Wsola
         }
         // scan order of the coarse stage: ascending offset, candidates out of bounds skipped (ctts.c:3452)
         // candidate c (offset -128 + 4c) is in bounds iff cpos >= 0 && cpos + 512 <= n
-        const int c_first = nominal >= WS_SHIFT ? 0 : (WS_SHIFT - nominal + 3) / 4;
+        const int c_first = 0;                                             // nominal >= 128 for k >= 1
         int c_last = 2 * WS_SHIFT / 4;
         const long long room = (long long)n - WS_FRAME - nominal;   // largest offset in bounds (>= 0)
         if (room < WS_SHIFT) c_last = (int)((room + WS_SHIFT) / 4);
@@ -302,10 +325,11 @@ __global__ void __launch_bounds__(WS_THREADS, 8) wsola_search_kernel(const Wsola
             prev_pos = pos;
             continue;
         }
-        // ---- FILTER, coarse: group g = candidates 4g..4g+3 (window starts 16g + 4j), split s = terms [48s, 48s+48)
+
+        // ---- FILTER, coarse: group g = candidates 4g..4g+3 (window starts 16g + 4j), split s
         float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         const int g = tid >> 3, sidx = tid & 7;
-        if (g < WS_GROUPS) {
+        {
             // split s takes terms [52 s, 52 s + 52) (the last one 20): starts 13 float4 apart put the
             // eight lanes of a quarter warp on eight different bank groups (12 would collide 4-way)
             const int m_cnt = sidx == WS_SPLITS - 1 ? WS_OVERLAP / 4 - 13 * (WS_SPLITS - 1) : 13;
@@ -325,53 +349,41 @@ __global__ void __launch_bounds__(WS_THREADS, 8) wsola_search_kernel(const Wsola
                 sp[3] = __fmaf_rn(x.z, y3.z, sp[3]); sp[3] = __fmaf_rn(x.w, y3.w, sp[3]);
                 y0 = y1; y1 = y2; y2 = y3;
             }
-        } else if (warp == WS_THREADS / 32 - 1) {
-            // exact prefix sums of squares of the view (20 values per lane, 640 * 2^30 < 2^64)
-            constexpr int P = WS_RANGE / 32;   // 20: five float4 loads, ten 16-byte stores per lane
-            const int i0 = lane * P;
-            int v[P];
-            unsigned long long loc = 0;
-#pragma unroll
-            for (int q = 0; q < P / 4; q++) {
-                const float4 f = *reinterpret_cast<const float4*>(xin + i0 + 4 * q);
-                v[4 * q] = (int)f.x; v[4 * q + 1] = (int)f.y; v[4 * q + 2] = (int)f.z; v[4 * q + 3] = (int)f.w;
-            }
-#pragma unroll
-            for (int q = 0; q < P; q++) loc += (unsigned long long)(uint32_t)(v[q] * v[q]);
-            unsigned long long inc = loc;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            unsigned long long run = inc - loc;
-#pragma unroll
-            for (int q = 0; q < P; q += 2) {
-                ulonglong2 two;
-                two.x = run;
-                run += (unsigned long long)(uint32_t)(v[q] * v[q]);
-                two.y = run;
-                run += (unsigned long long)(uint32_t)(v[q + 1] * v[q + 1]);
-                *reinterpret_cast<ulonglong2*>(S + i0 + q) = two;
-            }
-            if (lane == 31) S[WS_RANGE] = run;
         }
+        // the 65th candidate (offset +128, window xin[256 ..)): three terms per thread
+        float s64 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < WS_OVERLAP / WS_THREADS; q++)
+            s64 = __fmaf_rn(tgt[tid + WS_THREADS * q], xin[2 * WS_SHIFT + tid + WS_THREADS * q], s64);
         // reduce the 8 splits of a group (adjacent lanes)
-        if (warp < WS_THREADS / 32 - 1) {
 #pragma unroll
-            for (int o = 1; o < WS_SPLITS; o <<= 1) {
+        for (int o = 1; o < WS_SPLITS; o <<= 1) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) sp[j] += __shfl_xor_sync(0xffffffffu, sp[j], o);
-            }
+            for (int j = 0; j < 4; j++) sp[j] += __shfl_xor_sync(0xffffffffu, sp[j], o);
+            s64 += __shfl_xor_sync(0xffffffffu, s64, o);
         }
-        __syncthreads();   // S
-        const float sb = (float)(S[ti + WS_OVERLAP] - S[ti]);
-        if (g < WS_GROUPS && sidx < 4) {
-            // every lane of a group holds the four sums: lane j scores candidate j
-            const int c = 4 * g + sidx;
-            const float spc = sidx == 0 ? sp[0] : sidx == 1 ? sp[1] : sidx == 2 ? sp[2] : sp[3];
+        if (sidx == 0) s_c64[g] = s64;
+        const unsigned long long* Pv = Pr;   // window energy of view index a: P[vstart + a + 384] - P[vstart + a]
+        auto energy = [&](int a) {
+            const uint32_t p0 = vstart + (uint32_t)a;
+            return ws_u64_to_float(Pv[(p0 + WS_OVERLAP) & (WS_RING - 1)] - Pv[p0 & (WS_RING - 1)]);
+        };
+        const float sb = energy(ti);
+        __syncthreads();   // s_c64
+        {
+            // lanes 0..3 of a group score its four candidates; lane 4 of group 0 scores the 65th
+            int c = -1;
+            float spc = 0.0f;
+            if (sidx < 4) {
+                c = 4 * g + sidx;
+                spc = sidx == 0 ? sp[0] : sidx == 1 ? sp[1] : sidx == 2 ? sp[2] : sp[3];
+            } else if (tid == 4) {
+                c = 2 * WS_SHIFT / 4;
+#pragma unroll
+                for (int q = 0; q < WS_GROUPS; q++) spc += s_c64[q];
+            }
             if (c >= c_first && c <= c_last) {
-                const float sa = (float)(S[4 * c + WS_OVERLAP] - S[4 * c]);
+                const float sa = energy(4 * c);
                 const float den2 = sa * sb;   // the filter only needs an approximation: rsqrt.approx (2^-22)
                 float a = 0.0f, e = 0.0f;
                 if (den2 > 1.02f) {
@@ -412,10 +424,8 @@ __global__ void __launch_bounds__(WS_THREADS, 8) wsola_search_kernel(const Wsola
                 for (int q = 0; q < WS_OVERLAP / WS_FINE_SPLITS; q++)
                     spf = __fmaf_rn(x[WS_FINE_SPLITS * q], y[WS_FINE_SPLITS * q], spf);
             }
-            if (tid < 128) {   // whole warps; f <= 7
 #pragma unroll
-                for (int o = 1; o < WS_FINE_SPLITS; o <<= 1) spf += __shfl_xor_sync(0xffffffffu, spf, o);
-            }
+            for (int o = 1; o < WS_FINE_SPLITS; o <<= 1) spf += __shfl_xor_sync(0xffffffffu, spf, o);
             if (tid == 0) {   // scan order: the coarse winner first (it is `best`), then the fine candidates ascending
                 ca[0] = best_a;
                 ce[0] = best_e;
@@ -429,7 +439,7 @@ __global__ void __launch_bounds__(WS_THREADS, 8) wsola_search_kernel(const Wsola
             if (live && fs == 0 && off >= flo && off <= fhi) {
                 const int slot = 1 + (off - flo) - (best_off >= flo && best_off < off ? 1 : 0);
                 const int xo = off + WS_SHIFT;
-                const float sa = (float)(S[xo + WS_OVERLAP] - S[xo]);
+                const float sa = energy(xo);
                 const float den2 = sa * sb;
                 float a = 0.0f, e = 0.0f;
                 if (den2 > 1.02f) {

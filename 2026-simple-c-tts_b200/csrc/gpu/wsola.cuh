@@ -115,39 +115,38 @@ __device__ int ws_decide(const WsDecide& D, int cnt, const float* xin, const flo
     //      survivor's score is already exact, or there is only one -- the winner
     if (tid < 32) {
         float a[3], e[3];
-        float lb = -3.0f;
+        uint32_t lbk = 0;   // sortable key of the best lower bound
 #pragma unroll
         for (int r = 0; r < 3; r++) {
             const int i = tid + 32 * r;
             a[r] = i < cnt ? D.ca[i] : -3.0f;
             e[r] = i < cnt ? D.ce[i] : 0.0f;
-            lb = fmaxf(lb, a[r] - e[r]);
+            lbk = max(lbk, ws_sortable(a[r] - e[r]));
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+        lbk = __reduce_max_sync(0xffffffffu, lbk);
         int ns = 0, inexact = 0;
-        unsigned long long key = 0ull;   // (score, scan position reversed): max = best score, first in scan order
+        uint32_t best_k = 0;      // best score among this lane's survivors
+        uint32_t best_i = 0xffffu;
 #pragma unroll
         for (int r = 0; r < 3; r++) {
             const int i = tid + 32 * r;
-            const bool in = i < cnt && a[r] + e[r] >= lb;
+            const bool in = i < cnt && ws_sortable(a[r] + e[r]) >= lbk;
             ns += __popc(__ballot_sync(0xffffffffu, in));
             inexact += __popc(__ballot_sync(0xffffffffu, in && e[r] != 0.0f));
-            if (in) {
-                const unsigned long long k2 = ((unsigned long long)ws_sortable(a[r]) << 32) | (uint32_t)(0xffff - i);
-                key = k2 > key ? k2 : key;
+            const uint32_t sk = ws_sortable(a[r]);
+            if (in && sk > best_k) {   // ascending i inside a lane: strict > keeps the first
+                best_k = sk;
+                best_i = (uint32_t)i;
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-            key = other > key ? other : key;
-        }
+        // (score, scan position): the best score, first in scan order among equals
+        const uint32_t top = __reduce_max_sync(0xffffffffu, best_k);
+        const uint32_t first = __reduce_min_sync(0xffffffffu, best_k == top ? best_i : 0xffffu);
         if (tid == 0) {
             D.cnt_s[0] = ns;
             D.cnt_s[1] = inexact;
-            D.cnt_s[2] = 0xffff - (int)(uint32_t)(key & 0xffffu);
-            D.cnt_s[3] = __float_as_int(lb);
+            D.cnt_s[2] = (int)first;
+            D.cnt_s[3] = (int)lbk;
         }
     }
     __syncthreads();
@@ -158,12 +157,12 @@ __device__ int ws_decide(const WsDecide& D, int cnt, const float* xin, const flo
         return w;
     }
     // ---- several possible winners, not all exact: the reference's loop for those, one thread each
-    const float lb = __int_as_float(D.cnt_s[3]);
+    const uint32_t lbk = (uint32_t)D.cnt_s[3];
     if (tid < 32) {   // survivors in scan order (a warp-ordered compaction keeps the order)
         int base = 0;
         for (int i0 = 0; i0 < cnt; i0 += 32) {
             const int i = i0 + tid;
-            const bool in = i < cnt && D.ca[i] + D.ce[i] >= lb;
+            const bool in = i < cnt && ws_sortable(D.ca[i] + D.ce[i]) >= lbk;
             const uint32_t m = __ballot_sync(0xffffffffu, in);
             if (in) D.list[base + __popc(m & ((1u << tid) - 1u))] = i;
             base += __popc(m);
@@ -291,14 +290,17 @@ __global__ void __launch_bounds__(WS_THREADS, 10) wsola_search_kernel(const Wsol
         append(b, load(b));
         __syncthreads();
     }
-    float next_v = frames > 2 ? load(WS_RANGE) : 0.0f;   // frame 2 adds input[640 .. 768)
+    // frame k >= 2 adds input[128 k + 384 .. 128 k + 512); loaded two frames ahead (the buffer is in HBM)
+    float next_v = frames > 2 ? load(WS_RANGE) : 0.0f;
+    float next_v2 = frames > 3 ? load(WS_RANGE + WS_THREADS) : 0.0f;
 
     for (uint32_t k = 1; k < frames; k++) {
         const int nominal = (int)(k * WS_HOP);
         const uint32_t vstart = (uint32_t)(nominal - WS_SHIFT);           // absolute position of the view
         if (k >= 2) {
             append(vstart + WS_RANGE - WS_THREADS, next_v);              // the 128 samples this view adds
-            if (k + 1 < frames) next_v = load(vstart + WS_RANGE);       // in flight while this frame is decided
+            next_v = next_v2;
+            if (k + 2 < frames) next_v2 = load(vstart + WS_RANGE + WS_THREADS);   // two frames ahead
         }
         const float* xin = xr + (vstart & (WS_RING - 1));
         if (tid == 0) s_sb_valid = 0;

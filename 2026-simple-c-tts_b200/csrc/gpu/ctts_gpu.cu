@@ -290,6 +290,8 @@ int ctts_gpu_init(ctts_gpu_ctx** out, const void* voice_db, size_t db_size, int 
     CUI(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal));
     CUI(cudaDeviceGetAttribute(&ctx->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device_ordinal));
     CUI(cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_ordinal));
+    // once per device: plans of different window sizes may be alive at the same time
+    CUI(cudaFuncSetAttribute(ctts::assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
 
     // re-pack: every unit starts on a 16-byte boundary, zero padded (int16x8 loads)
     const uint8_t* base = static_cast<const uint8_t*>(voice_db);
@@ -659,7 +661,6 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
         CUP(cudaMemcpyAsync(p->d_ola_first, ola_first.data(), ola_first.size() * 4, cudaMemcpyHostToDevice, st));
         CUP(cudaStreamSynchronize(st));   // the vectors above are about to go out of scope
     }
-    CUP(cudaFuncSetAttribute(ctts::assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctts::assemble_kernel, ctts::ASM_THREADS, p->smem_bytes) != cudaSuccess || occ < 1)
         occ = 1;

@@ -291,3 +291,19 @@ def test_cli_synth_writes_the_reference_wav(H, small_db, golden, tmp_path, monke
     (tmp_path / "t.tsv").write_text("1.0\tolá mundo\n1.5\tolá mundo\n", encoding="utf-8")
     assert cli.main(["synth-batch", "voice.db", "t.tsv", "out"]) == 0
     assert (tmp_path / "out" / "000001.wav").read_bytes() == (tmp_path / "o1.wav").read_bytes()
+
+
+def test_two_resident_plans_with_different_windows(H, gpu, synth_small, oracle_small, front_small):
+    """Plans whose shared-memory windows differ (a tiny batch next to a large region) stay runnable in
+    any order: the dynamic shared-memory limit is a per-device setting, not a per-plan one."""
+    prm = front_small.params()
+    small = front_small.plan(["a", "olá"])
+    big = front_small.plan([",".join(["casa"] * 12), "bom dia mundo"])
+    ra = synth_small.create_plan(big, prm)
+    rb = synth_small.create_plan(small, prm)
+    assert ra.info().smem_bytes != rb.info().smem_bytes
+    for rp, plan in ((ra, big), (rb, small), (ra, big)):
+        rp.run()
+        for u, got in enumerate(rp.utterances()):
+            want, _ = oracle_small.synth(prm, plan.utt_ops(u), 1.0)
+            _assert_same(got, want, f"utt {u}")

@@ -307,3 +307,35 @@ def test_two_resident_plans_with_different_windows(H, gpu, synth_small, oracle_s
         for u, got in enumerate(rp.utterances()):
             want, _ = oracle_small.synth(prm, plan.utt_ops(u), 1.0)
             _assert_same(got, want, f"utt {u}")
+
+
+def test_mixed_speed_batch_properties(H, gpu):
+    """BASELINE configs[3] at a size the oracle cannot cover exhaustively (512 utterances, speeds
+    0.5-2.0): counts within bounds, idempotence, known-answer WSOLA lengths (frames, hop and the
+    trailing-zero trim of ctts.c:3515-3517, :3611), and a sampled bit-exact oracle check."""
+    db = H.synthetic_db()
+    fr = H.front.Front(db, H.shipped_config(), H.NORM_CSV)
+    prm = fr.params()
+    g = gpu.GpuSynth(db, 0)
+    texts = H.corpus.batch(512, seed=4321, target_chars=120)
+    speeds = H.corpus.mixed_speeds(512, seed=5)
+    plan = fr.plan(texts, speeds)
+    rp = g.create_plan(plan, prm)
+    rp.run()
+    cnt = rp.counts().astype(np.int64)
+    off = rp.out_offsets().astype(np.int64)
+    assert (cnt <= g.bounds(plan).astype(np.int64)).all() and (cnt > 0).all()
+    pcm1 = rp.read_pcm(0, rp.out_samples)
+    rp.run()
+    assert np.array_equal(cnt, rp.counts().astype(np.int64))
+    assert np.array_equal(pcm1, rp.read_pcm(0, rp.out_samples))
+    frames, exact = rp.wsola_stats()
+    assert frames > 0 and exact < 0.05 * 2 * frames      # the filter decides almost every frame
+    orc = H.Oracle(db)
+    for u in range(0, 512, 37):
+        want, st, pre = orc.synth(prm, plan.utt_ops(u), float(speeds[u]), want_pre=True)
+        # length known-answer: (frames-1)*hop + 512 minus trailing zeros
+        n_frames = (len(pre) - 512) // 128 + 1
+        hop = int(128 / np.float32(speeds[u]))
+        assert st.wsola_frames == n_frames and len(want) <= (n_frames - 1) * hop + 512
+        _assert_same(pcm1[off[u]:off[u] + cnt[u]], want, f"utt {u} speed {float(speeds[u])}")

@@ -13,7 +13,16 @@ rng = np.random.default_rng(seed)
 db = H.synthetic_db()
 bad = 0
 t0 = time.time()
-for variant, cfg in enumerate((H.shipped_config(), H.front.load_config(None))):
+def variants():
+    yield H.shipped_config()
+    yield H.front.load_config(None)
+    c = H.shipped_config(); c.remove_dc_offset = 0; c.min_silence_ms = 12.0; c.silence_threshold = 0.1; yield c
+    c = H.front.load_config(None); c.remove_word_silence = 0; c.crossfade_ms = 0.0; c.max_pitch_change = 0.3; yield c
+    c = H.shipped_config(); c.crossfade_ms = 150.0; c.crossfade_vowel_ms = 200.0; c.word_pause_ms = 5.0; c.fade_out_ms = 20.0; yield c
+    c = H.shipped_config(); c.word_pause_ms = 0.0; c.unknown_silence_ms = 0.0; c.fade_in_ms = 0.0; c.fade_out_ms = 0.0; yield c
+
+
+for variant, cfg in enumerate(variants()):
     fr = H.front.Front(db, cfg, H.NORM_CSV)
     prm = fr.params()
     orc = H.Oracle(db)

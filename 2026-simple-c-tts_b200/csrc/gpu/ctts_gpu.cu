@@ -14,6 +14,7 @@
 #include <cstring>
 #include <chrono>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -190,12 +191,11 @@ struct PlanScan {
 };
 
 // pass A over the plan: validation, upper bounds, global maxima
-int scan_plan(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, uint64_t big_threshold, PlanScan* sc, uint32_t* bad_utt) {
-    const uint32_t n = plan->n_utts;
-    sc->pre.assign(n, 0);
-    sc->bound.assign(n, 0);
+// (utterances [u0, u1); pre / bound are written through `sc`, the scalars into `sc` too)
+int scan_range(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, uint64_t big_threshold, PlanScan* sc, uint32_t* bad_utt,
+               uint32_t u0, uint32_t u1, uint64_t* pre_out, uint64_t* bound_out) {
     const std::vector<uint32_t>& ucnt = ctx->unit_cnt;
-    for (uint32_t u = 0; u < n; u++) {
+    for (uint32_t u = u0; u < u1; u++) {
         const uint32_t b = plan->utt_op_begin[u], e = plan->utt_op_begin[u + 1];
         *bad_utt = u;
         if (b > e || e > plan->n_ops) return CTTS_GPU_ERR_INVALID_ARG;
@@ -242,11 +242,49 @@ int scan_plan(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, uint64_t big
             }
         }
         close_region();
-        sc->pre[u] = total;
+        pre_out[u] = total;
         uint32_t hop = 0;
         const bool st = needs_stretch(plan->speed[u], &hop);
         sc->any_stretch |= st;
-        sc->bound[u] = st ? stretch_bound(total, hop) : total;
+        bound_out[u] = st ? stretch_bound(total, hop) : total;
+    }
+    return 0;
+}
+
+// pass A, on a few host threads for large plans (it is serial work in front of the first launch)
+int scan_plan(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, uint64_t big_threshold, PlanScan* sc, uint32_t* bad_utt) {
+    const uint32_t n = plan->n_utts;
+    sc->pre.assign(n, 0);
+    sc->bound.assign(n, 0);
+    uint32_t T = 1;
+    if (plan->n_ops > (1u << 17)) {
+        T = std::min<uint32_t>(4, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char* e = getenv("CTTS_GPU_HOST_THREADS")) T = (uint32_t)std::max(1, std::min(16, atoi(e)));
+    }
+    if (T <= 1) return scan_range(ctx, plan, big_threshold, sc, bad_utt, 0, n, sc->pre.data(), sc->bound.data());
+    std::vector<PlanScan> part(T);
+    std::vector<int> rc(T, 0);
+    std::vector<uint32_t> bad(T, 0);
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < T; t++) {
+        const uint32_t u0 = (uint32_t)((uint64_t)n * t / T), u1 = (uint32_t)((uint64_t)n * (t + 1) / T);
+        th.emplace_back([&, t, u0, u1] {
+            rc[t] = scan_range(ctx, plan, big_threshold, &part[t], &bad[t], u0, u1, sc->pre.data(), sc->bound.data());
+        });
+    }
+    for (auto& x : th) x.join();
+    for (uint32_t t = 0; t < T; t++) {
+        if (rc[t]) {
+            *bad_utt = bad[t];
+            return rc[t];
+        }
+        sc->xf_max = std::max(sc->xf_max, part[t].xf_max);
+        sc->region_max = std::max(sc->region_max, part[t].region_max);
+        sc->big_region_max = std::max(sc->big_region_max, part[t].big_region_max);
+        sc->n_regions += part[t].n_regions;
+        sc->n_big_regions += part[t].n_big_regions;
+        sc->bad_factor |= part[t].bad_factor;
+        sc->any_stretch |= part[t].any_stretch;
     }
     return 0;
 }

@@ -67,6 +67,8 @@ struct ctts_gpu_ctx {
     char* h_arena = nullptr;         // pinned staging for the plan upload
     size_t h_arena_cap = 0;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;   // second compute stream: chunks with WSOLA alternate between the two
+    cudaEvent_t fence[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> events;
     char err[512] = {0};
 };
@@ -76,6 +78,8 @@ struct PlanChunk {
     uint32_t utt_begin = 0, utt_end = 0;
     uint32_t task_begin = 0, n_tasks = 0;
     uint32_t grid = 0;
+    uint32_t st_begin = 0, st_count = 0;     // stretched utterances of the chunk (WSOLA tasks)
+    uint32_t ola_begin = 0, ola_count = 0;   // their overlap-add blocks
 };
 
 struct ctts_gpu_plan {
@@ -393,6 +397,8 @@ void ctts_gpu_free(ctts_gpu_ctx* ctx) {
     if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    for (cudaEvent_t e : ctx->fence) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -568,58 +574,40 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
     p->hcap = hcap;
     p->smem_bytes = smem_for(wcap);
 
-    // ---- slots of stretched utterances (longest first) and WSOLA tasks
-    std::vector<ctts::StretchTask> stasks;
-    std::vector<uint32_t> ola_task, ola_first;
-    p->pre_off.assign(n, ~0ull);
-    p->pre_cap.assign(n, 0);
-    uint64_t pre_total = 0, pos_total = 0;
-    if (sc.any_stretch) {
-        std::vector<uint32_t> order(n);
-        std::iota(order.begin(), order.end(), 0u);
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pre[a] > pre[b]; });
-        for (uint32_t i = 0; i < n; i++) {
-            const uint32_t u = order[i];
+    // ---- chunks: contiguous utterance ranges.  Without WSOLA a chunk is about chunk_samples
+    // output samples.  The WSOLA search is one CTA per utterance walking a long dependent chain
+    // (10 resident CTAs per SM); consecutive chunks run on two streams, so a chunk holds about half
+    // a wave of stretched utterances and the tail of one chunk's chains overlaps the next chunk
+    // (measured on the 4096-utterance mixed batch: 6 chunks 171 ms, 3 chunks 173 ms, 11 chunks 219 ms,
+    // one launch and one copy 238 ms).
+    uint32_t n_stretched = 0;
+    if (sc.any_stretch)
+        for (uint32_t u = 0; u < n; u++) {
             uint32_t hop = 0;
-            if (!needs_stretch(plan->speed[u], &hop)) continue;
-            if (pre[u] + 16 > 0xffffffffull) {
-                delete p;
-                return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "utterance %u too long", u);
-            }
-            p->pre_off[u] = pre_total;
-            p->pre_cap[u] = (uint32_t)(up8(pre[u]) + 8);
-            ctts::StretchTask st;
-            st.utt = u;
-            st.hop = hop;
-            st.pre_off = pre_total;
-            st.out_off = p->offsets[u];
-            st.out_cap = (uint32_t)(p->offsets[u + 1] - p->offsets[u]);
-            st.pos_off = (uint32_t)pos_total;
-            st.max_frames = (uint32_t)(pre[u] > 512 ? (pre[u] - 512) / 128 + 1 : 1);
-            const uint64_t used_max = (uint64_t)st.max_frames * hop + 512;
-            const uint32_t per_block = ctts::OLA_THREADS * ctts::OLA_SPT;
-            for (uint64_t f = 0; f < used_max; f += per_block) {
-                ola_task.push_back((uint32_t)stasks.size());
-                ola_first.push_back((uint32_t)f);
-            }
-            stasks.push_back(st);
-            pre_total += p->pre_cap[u];
-            pos_total += st.max_frames;
-            if (pos_total > 0xffffffffull) {
-                delete p;
-                return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "too many WSOLA frames in one batch");
-            }
+            n_stretched += needs_stretch(plan->speed[u], &hop);
         }
-    }
-    p->n_stretch = (uint32_t)stasks.size();
-    p->n_ola_blocks = (uint32_t)ola_task.size();
-    if (p->n_stretch) chunk_samples = 0;   // the stretch kernels run over the whole batch
-
-    // ---- chunks: contiguous utterance ranges of about chunk_samples output samples
     if (chunk_samples == 0 || n == 0) {
         PlanChunk ch;
         ch.utt_end = n;
         p->chunks.push_back(ch);
+    } else if (n_stretched) {
+        uint32_t wave = (uint32_t)ctx->sm_count * ctts::WS_CTAS_PER_SM / 2;
+        if (const char* e = getenv("CTTS_GPU_STRETCH_WAVE")) wave = (uint32_t)std::max(1, atoi(e));
+        const uint32_t k = std::max<uint32_t>(1, (n_stretched + wave / 2) / wave);
+        const uint32_t share = (n_stretched + k - 1) / k;
+        uint32_t u0 = 0, cnt = 0;
+        for (uint32_t u = 0; u < n; u++) {
+            uint32_t hop = 0;
+            cnt += needs_stretch(plan->speed[u], &hop);
+            if ((cnt >= share && p->chunks.size() + 1 < k) || u + 1 == n) {
+                PlanChunk ch;
+                ch.utt_begin = u0;
+                ch.utt_end = u + 1;
+                p->chunks.push_back(ch);
+                u0 = u + 1;
+                cnt = 0;
+            }
+        }
     } else {
         uint64_t acc = 0;
         uint32_t u0 = 0;
@@ -635,6 +623,58 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
             }
         }
     }
+
+    // ---- slots of stretched utterances and WSOLA tasks, chunk by chunk, longest first inside a chunk
+    std::vector<ctts::StretchTask> stasks;
+    std::vector<uint32_t> ola_task, ola_first;
+    p->pre_off.assign(n, ~0ull);
+    p->pre_cap.assign(n, 0);
+    uint64_t pre_total = 0, pos_total = 0;
+    if (n_stretched) {
+        std::vector<uint32_t> order;
+        for (PlanChunk& ch : p->chunks) {
+            ch.st_begin = (uint32_t)stasks.size();
+            ch.ola_begin = (uint32_t)ola_task.size();
+            order.resize(ch.utt_end - ch.utt_begin);
+            std::iota(order.begin(), order.end(), ch.utt_begin);
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pre[a] > pre[b]; });
+            for (const uint32_t u : order) {
+                uint32_t hop = 0;
+                if (!needs_stretch(plan->speed[u], &hop)) continue;
+                if (pre[u] + 16 > 0xffffffffull) {
+                    delete p;
+                    return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "utterance %u too long", u);
+                }
+                p->pre_off[u] = pre_total;
+                p->pre_cap[u] = (uint32_t)(up8(pre[u]) + 8);
+                ctts::StretchTask st;
+                st.utt = u;
+                st.hop = hop;
+                st.pre_off = pre_total;
+                st.out_off = p->offsets[u];
+                st.out_cap = (uint32_t)(p->offsets[u + 1] - p->offsets[u]);
+                st.pos_off = (uint32_t)pos_total;
+                st.max_frames = (uint32_t)(pre[u] > 512 ? (pre[u] - 512) / 128 + 1 : 1);
+                const uint64_t used_max = (uint64_t)st.max_frames * hop + 512;
+                const uint32_t per_block = ctts::OLA_THREADS * ctts::OLA_SPT;
+                for (uint64_t f = 0; f < used_max; f += per_block) {
+                    ola_task.push_back((uint32_t)stasks.size());
+                    ola_first.push_back((uint32_t)f);
+                }
+                stasks.push_back(st);
+                pre_total += p->pre_cap[u];
+                pos_total += st.max_frames;
+                if (pos_total > 0xffffffffull) {
+                    delete p;
+                    return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "too many WSOLA frames in one batch");
+                }
+            }
+            ch.st_count = (uint32_t)stasks.size() - ch.st_begin;
+            ch.ola_count = (uint32_t)ola_task.size() - ch.ola_begin;
+        }
+    }
+    p->n_stretch = (uint32_t)stasks.size();
+    p->n_ola_blocks = (uint32_t)ola_task.size();
     const uint32_t n_chunks = (uint32_t)p->chunks.size();
     if (sc.n_regions + 1 > 0x7fffffffull) {
         delete p;
@@ -704,7 +744,8 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
         occ = 1;
     p->occ = (uint32_t)occ;
 
-    p->info.kernel_launches = n_chunks + (p->n_stretch ? 2 : 0);
+    p->info.kernel_launches = n_chunks;
+    for (const PlanChunk& ch : p->chunks) p->info.kernel_launches += ch.st_count ? 2 : 0;
     p->info.n_stretch = p->n_stretch;
     p->info.bound_samples = std::accumulate(bound.begin(), bound.end(), (uint64_t)0);
     p->info.smem_bytes = p->smem_bytes;
@@ -718,7 +759,7 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
 
 // The plan compiler, part 2: private op copy (with provably dead fade-outs turned into
 // no-ops), regions -> tasks, ticket order, upload -- for chunk c.  Chunks are built in order.
-int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c) {
+int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st) {
     if (c != p->built_chunks || c >= p->chunks.size() || !p->src) return CTTS_GPU_ERR_INVALID_ARG;
     const ctts_batch_plan* plan = p->src;
     PlanChunk& ch = p->chunks[c];
@@ -843,7 +884,6 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c) {
     p->n_tasks = nt;
     ch.grid = (uint32_t)std::min<uint64_t>((uint64_t)p->occ * (uint64_t)ctx->sm_count, std::max<uint32_t>(ch.n_tasks, 1));
 
-    cudaStream_t st = ctx->stream;
     if (op_hi > op_lo)
         CU(ctx, cudaMemcpyAsync(p->d_ops + op_lo, h_ops + op_lo, (size_t)(op_hi - op_lo) * sizeof(ctts_plan_op), cudaMemcpyHostToDevice, st));
     if (ch.n_tasks)
@@ -868,7 +908,7 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c) {
 #undef CUP
 
 // Enqueue one chunk's assembly kernel on the context stream.
-int launch_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, int16_t* d_pcm_out) {
+int launch_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, int16_t* d_pcm_out, cudaStream_t st) {
     const PlanChunk& ch = p->chunks[c];
     if (ch.n_tasks == 0) return CTTS_GPU_OK;
     ctts::AsmArgs a{};
@@ -898,7 +938,7 @@ int launch_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, int16_t* d_pcm
     a.prm = p->prm;
     a.wcap = p->wcap;
     a.hcap = p->hcap;
-    ctts::assemble_kernel<<<ch.grid, ctts::ASM_THREADS, p->smem_bytes, ctx->stream>>>(a);
+    ctts::assemble_kernel<<<ch.grid, ctts::ASM_THREADS, p->smem_bytes, st>>>(a);
     CU(ctx, cudaGetLastError());
     return CTTS_GPU_OK;
 }
@@ -914,12 +954,14 @@ int begin_run(ctts_gpu_ctx* ctx, ctts_gpu_plan* p) {
     return CTTS_GPU_OK;
 }
 
-int launch_stretch(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, int16_t* d_pcm_out) {
-    if (!p->n_stretch) return CTTS_GPU_OK;
-    cudaStream_t st = ctx->stream;
+// Enqueue the WSOLA kernels of one chunk's stretched utterances (after its assembly kernel).
+int launch_stretch(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, int16_t* d_pcm_out, cudaStream_t st) {
+    const PlanChunk& ch = p->chunks[c];
+    if (!ch.st_count) return CTTS_GPU_OK;
     ctts::WsolaArgs w{};
     w.tasks = p->d_stasks;
     w.n_tasks = p->n_stretch;
+    w.task_first = ch.st_begin;
     w.pre = p->d_pre;
     w.pre_counts = p->d_pre_counts;
     w.out = d_pcm_out;
@@ -927,12 +969,14 @@ int launch_stretch(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, int16_t* d_pcm_out) {
     w.frame_pos = p->d_frame_pos;
     w.n_frames = p->d_n_frames;
     w.hann512 = ctx->d_tables + 3328;
-    w.ola_block_task = p->d_ola_task;
-    w.ola_block_first = p->d_ola_first;
-    ctts::wsola_search_kernel<<<p->n_stretch, ctts::WS_THREADS, 0, st>>>(w);
+    w.ola_block_task = p->d_ola_task + ch.ola_begin;
+    w.ola_block_first = p->d_ola_first + ch.ola_begin;
+    ctts::wsola_search_kernel<<<ch.st_count, ctts::WS_THREADS, 0, st>>>(w);
     CU(ctx, cudaGetLastError());
-    ctts::wsola_ola_kernel<<<p->n_ola_blocks, ctts::OLA_THREADS, 0, st>>>(w);
-    CU(ctx, cudaGetLastError());
+    if (ch.ola_count) {
+        ctts::wsola_ola_kernel<<<ch.ola_count, ctts::OLA_THREADS, 0, st>>>(w);
+        CU(ctx, cudaGetLastError());
+    }
     return CTTS_GPU_OK;
 }
 
@@ -944,7 +988,7 @@ int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
                          const uint64_t* out_offsets, ctts_gpu_plan** out) {
     ctts_gpu_plan* p = nullptr;
     int rc = prepare_plan(ctx, plan, params, out_offsets, 0, false, &p);
-    for (uint32_t c = 0; !rc && c < p->chunks.size(); c++) rc = build_chunk(ctx, p, c);
+    for (uint32_t c = 0; !rc && c < p->chunks.size(); c++) rc = build_chunk(ctx, p, c, ctx->stream);
     if (rc) {
         ctts_gpu_plan_destroy(p);
         return rc;
@@ -979,8 +1023,10 @@ int ctts_gpu_plan_run(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, int16_t* d_pcm_out) {
     p->d_out_last = d_pcm_out;
     if (p->n_utts == 0) return CTTS_GPU_OK;
     int rc = begin_run(ctx, p);
-    for (uint32_t c = 0; !rc && c < p->chunks.size(); c++) rc = launch_chunk(ctx, p, c, d_pcm_out);
-    if (!rc) rc = launch_stretch(ctx, p, d_pcm_out);
+    for (uint32_t c = 0; !rc && c < p->chunks.size(); c++) {
+        rc = launch_chunk(ctx, p, c, d_pcm_out, ctx->stream);
+        if (!rc) rc = launch_stretch(ctx, p, c, d_pcm_out, ctx->stream);
+    }
     return rc;
 }
 
@@ -1065,6 +1111,7 @@ int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
     auto cu_fail = [&](cudaError_t e, const char* what) {
         cudaStreamSynchronize(ctx->stream);
         if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
         ctts_gpu_plan_destroy(p);
         return fail(ctx, CTTS_GPU_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     };
@@ -1078,30 +1125,53 @@ int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
         if (e != cudaSuccess) return cu_fail(e, "event");
         ctx->events.push_back(ev);
     }
+    std::vector<cudaEvent_t> tev;   // trace only: timing events around each chunk's kernels
+    auto mark = [&](cudaStream_t s_) {
+        if (!trace) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, s_);
+        tev.push_back(ev);
+    };
+    // Chunks with WSOLA alternate between two compute streams: the search kernel is a wave of long
+    // dependent chains whose tail leaves SMs idle, and the other stream's chunk fills them.
+    const bool two = p->n_stretch && nc > 1 && !getenv("CTTS_GPU_ONE_STREAM");
+    if (two && !ctx->aux_stream) {
+        cudaError_t e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->fence[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) return cu_fail(e, "aux stream");
+    }
     if (p->n_utts) {
         rc = begin_run(ctx, p);
+        if (two) {   // the aux stream starts after the memsets / uploads enqueued so far
+            cudaError_t e = cudaEventRecord(ctx->fence[0], ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux_stream, ctx->fence[0], 0);
+            if (e != cudaSuccess) return cu_fail(e, "fence");
+        }
+        mark(ctx->stream);
         for (uint32_t c = 0; !rc && c < nc; c++) {
             // compile + upload chunk c on the host while the device assembles chunk c-1
-            rc = build_chunk(ctx, p, c);
-            if (!rc) rc = launch_chunk(ctx, p, c, d_out);
+            cudaStream_t cs = (two && (c & 1)) ? ctx->aux_stream : ctx->stream;
+            rc = build_chunk(ctx, p, c, cs);
+            if (!rc) rc = launch_chunk(ctx, p, c, d_out, cs);
+            mark(cs);
+            if (!rc) rc = launch_stretch(ctx, p, c, d_out, cs);
+            mark(cs);
             if (rc) break;
-            if (p->n_stretch) continue;   // single chunk: copied after the stretch kernels below
             // the chunk's slots are one contiguous span; copy it while the next chunk is assembled
             const PlanChunk& ch = p->chunks[c];
             const uint64_t lo = p->offsets[ch.utt_begin], hi = p->offsets[ch.utt_end];
-            cudaError_t e = cudaEventRecord(ctx->events[c], ctx->stream);
+            cudaError_t e = cudaEventRecord(ctx->events[c], cs);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->events[c], 0);
             if (e == cudaSuccess && hi > lo)
                 e = cudaMemcpyAsync(pcm_out + lo, d_out + lo, (hi - lo) * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
             if (e != cudaSuccess) return cu_fail(e, "D2H");
+            mark(ctx->copy_stream);
         }
-        if (!rc && p->n_stretch) {
-            rc = launch_stretch(ctx, p, d_out);
-            if (!rc && total > out_offsets[0]) {
-                cudaError_t e = cudaMemcpyAsync(pcm_out + out_offsets[0], d_out + out_offsets[0],
-                                                (total - out_offsets[0]) * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream);
-                if (e != cudaSuccess) return cu_fail(e, "D2H");
-            }
+        if (two) {   // everything the aux stream did is ordered before what follows on the context stream
+            cudaError_t e = cudaEventRecord(ctx->fence[1], ctx->aux_stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->fence[1], 0);
+            if (e != cudaSuccess) return cu_fail(e, "fence");
         }
     }
     auto t2 = now();
@@ -1111,6 +1181,17 @@ int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
     if (e != cudaSuccess && !rc) rc = fail(ctx, CTTS_GPU_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
     auto t4 = now();
     ctts_gpu_plan_destroy(p);
+    if (trace && !tev.empty()) {
+        // per chunk, relative to the start of the run: assembly done, WSOLA done, copy done
+        for (size_t i = 1; i + 2 < tev.size(); i += 3) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, tev[0], tev[i]);
+            cudaEventElapsedTime(&b, tev[0], tev[i + 1]);
+            cudaEventElapsedTime(&c, tev[0], tev[i + 2]);
+            fprintf(stderr, "  chunk %zu: assembled at %.1f ms, stretched at %.1f ms, on the host at %.1f ms\n", (i - 1) / 3, a, b, c);
+        }
+        for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
+    }
     if (trace)
         fprintf(stderr, "ctts_gpu_synth_batch: compile+upload %.1f ms, enqueue %u chunks %.1f ms, kernels done +%.1f ms, copies done +%.1f ms\n",
                 ms(t0, t1), nc, ms(t1, t2), ms(t2, t3), ms(t3, t4));

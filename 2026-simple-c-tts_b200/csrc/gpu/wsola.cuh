@@ -37,6 +37,7 @@ constexpr int WS_HOP = 128;      // analysis hop
 constexpr int WS_OVERLAP = 384;  // correlation length
 constexpr int WS_SHIFT = 128;    // +-search range
 constexpr int WS_RANGE = 2 * WS_SHIFT + WS_OVERLAP;  // 640 samples visible to the candidates
+constexpr int WS_CTAS_PER_SM = 10;   // resident search CTAs per SM (registers and shared memory allow 10)
 constexpr int WS_THREADS = 128;  // 16 candidate groups x 8 splits; the 65th candidate is spread over all threads
 constexpr int WS_GROUPS = 16;    // groups of 4 coarse candidates (offsets -128 .. 124)
 constexpr int WS_SPLITS = 8;     // threads sharing the 384 terms of a group
@@ -59,7 +60,8 @@ struct StretchTask {
 
 struct WsolaArgs {
     const StretchTask* tasks;
-    uint32_t n_tasks;
+    uint32_t n_tasks;      // of the whole plan
+    uint32_t task_first;   // search launch: CTA b works on task task_first + b
     const int16_t* pre;
     const uint32_t* pre_counts;
     int16_t* out;
@@ -67,7 +69,7 @@ struct WsolaArgs {
     uint32_t* frame_pos;
     uint32_t* n_frames;   // per task; [n_tasks + task] = decisions that needed an exact evaluation
     const float* hann512;
-    const uint32_t* ola_block_task;   // per OLA block: task index
+    const uint32_t* ola_block_task;   // per OLA block of this launch: task index (plan-wide)
     const uint32_t* ola_block_first;  // per OLA block: first output sample
 };
 
@@ -221,7 +223,7 @@ __device__ __forceinline__ float ws_u64_to_float(unsigned long long v) {
     return __fmaf_rn((float)(uint32_t)(v >> 32), 4294967296.0f, (float)(uint32_t)v);
 }
 
-__global__ void __launch_bounds__(WS_THREADS, 10) wsola_search_kernel(const WsolaArgs A) {
+__global__ void __launch_bounds__(WS_THREADS, WS_CTAS_PER_SM) wsola_search_kernel(const WsolaArgs A) {
     // ring of the last 1024 input samples as floats, stored twice (i and i + 1024): the view of a
     // frame, input[nominal-128 .. nominal+512), is 640 contiguous floats at a 16-byte aligned offset
     __shared__ __align__(16) float xr[2 * WS_RING];
@@ -236,17 +238,18 @@ __global__ void __launch_bounds__(WS_THREADS, 10) wsola_search_kernel(const Wsol
     __shared__ int s_cnt[4], s_sb_valid;
     __shared__ float s_sb;
 
-    const StretchTask task = A.tasks[blockIdx.x];
+    const uint32_t ti = A.task_first + blockIdx.x;
+    const StretchTask task = A.tasks[ti];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = A.pre_counts[task.utt];
     const int16_t* in = A.pre + task.pre_off;
     uint32_t* fpos = A.frame_pos + task.pos_off;
-    uint32_t* exact_count = A.n_frames + A.n_tasks + blockIdx.x;
+    uint32_t* exact_count = A.n_frames + A.n_tasks + ti;
 
     uint32_t frames = n >= WS_FRAME ? (n - WS_FRAME) / WS_HOP + 1 : 0;
     if (frames > task.max_frames) frames = task.max_frames;
     if (tid == 0) {
-        A.n_frames[blockIdx.x] = frames;
+        A.n_frames[ti] = frames;
         *exact_count = 0;
         s_ptotal = 0ull;
         Pr[0] = 0ull;

@@ -339,3 +339,22 @@ def test_mixed_speed_batch_properties(H, gpu):
         hop = int(128 / np.float32(speeds[u]))
         assert st.wsola_frames == n_frames and len(want) <= (n_frames - 1) * hop + 512
         _assert_same(pcm1[off[u]:off[u] + cnt[u]], want, f"utt {u} speed {float(speeds[u])}")
+
+
+def test_chunked_stretch_batch(H, gpu, small_db, oracle_small, front_small, monkeypatch):
+    """ctts_gpu_synth_batch on a batch that mixes stretched and plain utterances, cut into several
+    launches of assemble -> WSOLA search -> overlap-add whose device->host copies overlap the next
+    chunk (CTTS_GPU_STRETCH_WAVE forces small waves); the result must not depend on the cut."""
+    prm = front_small.params()
+    texts = H.corpus.batch(22, seed=53, target_chars=100) + ["", "olá mundo", "a"]
+    speeds = [1.5, 1.0, 0.5, 2.0, 1.0, 0.7, 1.3, 1.0, 0.9, 1.1, 1.0, 1.7, 0.6, 1.0, 1.9, 0.8,
+              1.0, 1.2, 1.4, 1.0, 1.6, 0.5, 1.5, 1.5, 1.0]
+    plan = front_small.plan(texts, speeds)
+    want = [oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))[0] for u in range(plan.n_utts)]
+    for wave in ("1", "3", "5", "1000"):
+        monkeypatch.setenv("CTTS_GPU_STRETCH_WAVE", wave)
+        g = gpu.GpuSynth(small_db, 0)
+        outs = g.synth_list(plan, prm)
+        for u in range(plan.n_utts):
+            _assert_same(outs[u], want[u], f"wave {wave} utt {u} speed {speeds[u]}")
+    monkeypatch.delenv("CTTS_GPU_STRETCH_WAVE")

@@ -1,4 +1,4 @@
-// asm_unit.cuh -- the UNIT op: gather, normalize_rms, join, buffer_append_crossfade.
+// asm_unit.cuh -- the normalized pool (normalize_rms) and the UNIT op: gather, join, buffer_append_crossfade.
 #pragma once
 #include "asm_common.cuh"
 #include "asm_pitch.cuh"
@@ -71,19 +71,76 @@ __device__ __forceinline__ uint32_t sub_dc2(uint32_t w, const DcPack& d) {
     return __vadd2(__vmins2(__vmaxs2(w, d.lo2), d.hi2), d.neg2);
 }
 
+// normalize_rms (ctts.c:1709, target 3000 at :3684) is the first thing the reference does to
+// its private copy of a unit, so its result is a function of the unit and target_rms alone.  It is
+// evaluated once per unit when a context first sees a target_rms -- the NORMALIZED POOL, same
+// layout as the PCM pool -- instead of once per use (331 000 times per 4096-utterance batch).
+// meta[u] = {sum of the normalized samples (lo, hi), (int16)(sum / n) = the DC offset
+// remove_dc_offset (ctts.c:1568) finds on the untouched unit, 0}.
+__global__ void __launch_bounds__(ASM_THREADS) normalize_pool_kernel(const int16_t* __restrict__ pool, int16_t* __restrict__ out,
+                                                                     const uint32_t* __restrict__ unit_off,
+                                                                     const uint32_t* __restrict__ unit_cnt, int4* __restrict__ meta,
+                                                                     float target_rms) {
+    __shared__ long long red[2 * ASM_WARPS + 2];
+    const uint32_t u = blockIdx.x;
+    const uint32_t n = unit_cnt[u];
+    const int tid = threadIdx.x;
+    if (n == 0) {
+        if (tid == 0) meta[u] = make_int4(0, 0, 0, 0);
+        return;
+    }
+    const int4* srcv = reinterpret_cast<const int4*>(pool + unit_off[u]);
+    int4* dstv = reinterpret_cast<int4*>(out + unit_off[u]);
+    const uint32_t nvec = (n + 7) >> 3;   // the pool is zero padded to whole vectors; scaling keeps zeros
+    // sum of squares: the reference's double sum of integers is the integer sum (< 2^53)
+    long long ss = 0;
+    for (uint32_t v = tid; v < nvec; v += ASM_THREADS) ss += sumsq8(__ldg(srcv + v));
+    // gain = clamp(target / rms), rms = (float)sqrt(sum / n) in double (calculate_rms, ctts.c:1697)
+    const unsigned long long gs = block_sum_then<ASM_THREADS>(ss, red, [&](long long tot) {
+        float gg = 1.0f;
+        uint32_t sc = 0;
+        if (target_rms > 0) {
+            const float rms = (float)sqrt((double)tot / (double)n);
+            if (!(rms < 1.0f)) {
+                gg = target_rms / rms;
+                if (gg > 3.0f) gg = 3.0f;
+                if (gg < 0.1f) gg = 0.1f;
+                sc = 1;
+            }
+        }
+        return ((unsigned long long)sc << 32) | __float_as_uint(gg);
+    });
+    const bool scale = (gs >> 32) != 0;
+    const float g = __uint_as_float((uint32_t)gs);
+    long long dsum = 0;
+    for (uint32_t v = tid; v < nvec; v += ASM_THREADS) {
+        int4 q = __ldg(srcv + v);
+        if (scale) q = scale8(q, g);
+        dstv[v] = q;
+        dsum += sum8_s16(q, 0);
+    }
+    (void)block_sum_then<ASM_THREADS>(dsum, red, [&](long long sum) {
+        meta[u] = make_int4((int)(uint32_t)(unsigned long long)sum, (int)(uint32_t)((unsigned long long)sum >> 32),
+                            (int)(int16_t)(sum / (long long)n), 0);
+        return 0ull;
+    });
+}
+
 // ctts.c:3785-3846: gather -> normalize_rms -> [smooth, match] -> buffer_append_crossfade.
 //
-// The unit's first `hs` samples (everything the join may rewrite, and what the pitch analysis
-// reads) are staged in `hstage`; the rest is written straight to its final place in the window,
-// on the window's own 16-byte grid (the pool side is re-aligned with a funnel shift), and
-// revisited once in place to subtract the DC offset -- which is only known after the head has
-// been smoothed and energy matched.
+// The gather reads the normalized pool (see normalize_pool_kernel).  The unit's first `hs`
+// samples (everything the join may rewrite, and what the pitch analysis reads) are staged in
+// `hstage` and joined there; that settles the DC offset (table sum - staged head as gathered +
+// staged head as joined), and the rest of the unit then goes from the pool straight to its final
+// place in the window, minus the offset, on the window's own 16-byte grid (the pool side is
+// re-aligned with a funnel shift): every window sample of the body is written exactly once.
 __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_plan_op& op) {
     const int tid = threadIdx.x;
     if (op.a >= A.n_units) { s.err = ERR_BAD_OP; return; }
     // the plan compiler stored the unit's length and pool offset in the op's unused float fields
     const uint32_t n = __float_as_uint(op.f0);
     if (n == 0) return;
+    const int4 meta = __ldg(A.unit_meta + op.a);   // needed only after the join
     const int16_t* src = A.pool + __float_as_uint(op.f1);
     const int4* srcv = reinterpret_cast<const int4*>(src);
     const uint32_t nvec = (n + 7) >> 3;
@@ -135,34 +192,6 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
     }
     const uint32_t hsn = hs < n ? hs : n;   // staged samples that exist
 
-    // ---- pass 1: sum of squares (normalize_rms, ctts.c:1709; double sum of integers == integer sum)
-    long long ss = 0;
-    for (uint32_t v = tid; v < nvec; v += ASM_THREADS) ss += sumsq8(__ldg(srcv + v));
-    // gain = clamp(target / rms), rms = (float)sqrt(sum / n) in double (calculate_rms, ctts.c:1697): one thread
-    const float target_rms = A.prm.target_rms;
-    const unsigned long long gs = block_sum_then<ASM_THREADS>(ss, reinterpret_cast<long long*>(sm.red), [&](long long tot) {
-        float gg = 1.0f;
-        uint32_t sc = 0;
-        if (target_rms > 0) {
-            const float rms = (float)sqrt((double)tot / (double)n);
-            if (!(rms < 1.0f)) {
-                gg = target_rms / rms;
-                if (gg > 3.0f) gg = 3.0f;
-                if (gg < 0.1f) gg = 0.1f;
-                sc = 1;
-            }
-        }
-        return ((unsigned long long)sc << 32) | __float_as_uint(gg);
-    });
-    const bool scale = (gs >> 32) != 0;
-    const float g = __uint_as_float((uint32_t)gs);
-
-    // ---- pass 2: scale; head -> hstage, body -> window (aligned vectors of the window)
-    for (uint32_t v = tid; v < (hs >> 3); v += ASM_THREADS) {
-        int4 q = __ldg(srcv + v);
-        if (scale) q = scale8(q, g);
-        *(reinterpret_cast<int4*>(us) + v) = q;
-    }
     // unit sample i lands at tail[i]; the body is [hs, n)
     int16_t* tail = s.w + ((int)s.cnt - (int)a);
     const uint32_t phase = (uint32_t)((reinterpret_cast<uintptr_t>(tail + hs) >> 1) & 7u);
@@ -170,68 +199,65 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
     const uint32_t body = n - hsn;                            // may be 0
     const uint32_t gvec = body ? (phase + body + 7) >> 3 : 0; // window vectors that hold body samples
     const uint32_t pv0 = hs >> 3;                             // pool vector of unit sample hs
-    int dsum = 0;
-    for (uint32_t j = tid; j < gvec; j += ASM_THREADS) {
-        // window vector j holds unit samples i0 .. i0+7, i0 = hs - phase + 8j
-        int4 q;
-        if (phase == 0) {
-            q = __ldg(srcv + pv0 + j);
-        } else {
-            int4 lo = make_int4(0, 0, 0, 0), hi = make_int4(0, 0, 0, 0);
-            if (pv0 + j >= 1) lo = __ldg(srcv + pv0 + j - 1);
-            if (pv0 + j < nvec) hi = __ldg(srcv + pv0 + j);
-            q = shift_pick(lo, hi, 8u - phase);
-        }
-        if (scale) q = scale8(q, g);
-        const int i0 = (int)hs - (int)phase + 8 * (int)j;
-        if (i0 >= (int)hs && i0 + 8 <= (int)n) {
-            dsum = sum8_s16(q, dsum);
-            *(reinterpret_cast<int4*>(grid) + j) = q;
-        } else {   // the (at most two) partial vectors at the ends of the body
-            const int16_t* e = reinterpret_cast<const int16_t*>(&q);
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (i0 + k >= (int)hs && i0 + k < (int)n) {
-                    dsum += (int)e[k];
-                    grid[8 * j + k] = e[k];
-                }
-        }
-    }
-    __syncthreads();
 
-    if (join) {
+    // ---- head -> hstage, join there (smooth_pitch_boundary, match_boundary_energy)
+    int dc = 0;
+    if (hs) {
+        int hsum = 0;   // the staged head as gathered (the pool's zero padding adds nothing)
+        for (uint32_t v = tid; v < (hs >> 3); v += ASM_THREADS) {
+            const int4 q = __ldg(srcv + v);
+            *(reinterpret_cast<int4*>(us) + v) = q;
+            hsum = sum8_s16(q, hsum);
+        }
+        __syncthreads();
         smooth_pitch(s, sm, us, n, xf, reg);
         match_energy(s, sm, us, a);
+        // remove_dc_offset (ctts.c:1568) inside buffer_append_crossfade (ctts.c:3279): the sum over the
+        // joined unit = table sum - head as gathered + head as joined
+        if (remove_dc) {
+            int d = -hsum;
+            for (uint32_t i = tid; i < hsn; i += ASM_THREADS) d += us[i];
+            const long long unit_sum = (long long)(((unsigned long long)(uint32_t)meta.y << 32) | (uint32_t)meta.x);
+            dc = (int)block_sum_then<ASM_THREADS>((long long)d, reinterpret_cast<long long*>(sm.red), [&](long long delta) {
+                return (unsigned long long)(uint32_t)(int)(int16_t)((unit_sum + delta) / (long long)n);
+            });
+        }
+    } else if (remove_dc) {
+        dc = meta.z;   // untouched unit: its DC offset is a table entry
     }
 
-    // ---- remove_dc_offset (ctts.c:1568) inside buffer_append_crossfade (ctts.c:3279)
-    int dc = 0;
-    if (remove_dc) {
-        for (uint32_t i = tid; i < hsn; i += ASM_THREADS) dsum += us[i];
-        dc = (int)block_sum_then<ASM_THREADS>((long long)dsum, reinterpret_cast<long long*>(sm.red), [&](long long sum) {
-            return (unsigned long long)(uint32_t)(int)(int16_t)(sum / (long long)n);
-        });
-    }
-    // body in place
-    if (dc != 0) {
+    // ---- body: pool -> minus DC -> window, once
+    {
         const DcPack dp = dc_pack(dc);
         for (uint32_t j = tid; j < gvec; j += ASM_THREADS) {
-            const int i0 = (int)hs - (int)phase + 8 * (int)j;
-            if (i0 >= (int)hs && i0 + 8 <= (int)n) {
-                int4 q = *(reinterpret_cast<int4*>(grid) + j);
+            // window vector j holds unit samples i0 .. i0+7, i0 = hs - phase + 8j
+            int4 q;
+            if (phase == 0) {
+                q = __ldg(srcv + pv0 + j);
+            } else {
+                int4 lo = make_int4(0, 0, 0, 0), hi = make_int4(0, 0, 0, 0);
+                if (pv0 + j >= 1) lo = __ldg(srcv + pv0 + j - 1);
+                if (pv0 + j < nvec) hi = __ldg(srcv + pv0 + j);
+                q = shift_pick(lo, hi, 8u - phase);
+            }
+            if (dc != 0) {
                 q.x = (int)sub_dc2((uint32_t)q.x, dp);
                 q.y = (int)sub_dc2((uint32_t)q.y, dp);
                 q.z = (int)sub_dc2((uint32_t)q.z, dp);
                 q.w = (int)sub_dc2((uint32_t)q.w, dp);
+            }
+            const int i0 = (int)hs - (int)phase + 8 * (int)j;
+            if (i0 >= (int)hs && i0 + 8 <= (int)n) {
                 *(reinterpret_cast<int4*>(grid) + j) = q;
-            } else {
+            } else {   // the (at most two) partial vectors at the ends of the body
+                const int16_t* e = reinterpret_cast<const int16_t*>(&q);
 #pragma unroll
                 for (int k = 0; k < 8; k++)
-                    if (i0 + k >= (int)hs && i0 + k < (int)n) grid[8 * j + k] = (int16_t)sub_dc((int)grid[8 * j + k], dc);
+                    if (i0 + k >= (int)hs && i0 + k < (int)n) grid[8 * j + k] = e[k];
             }
         }
     }
-    if (join) {
+    if (hs) {
         // staged head: crossfade mix (ctts.c:3328-3344) over [0, a), plain copy over [a, hsn)
         const float inv = a ? 1.0f / (float)a : 0.0f;
         for (uint32_t i = tid; i < hsn; i += ASM_THREADS) {
@@ -246,7 +272,7 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
             }
             tail[i] = (int16_t)v;
         }
-    } else {
+    } else if (!join) {
         // fade-in of a word-initial unit (apply_fade_in, ctts.c:3015), after the DC removal
         const uint32_t pre = A.prm.fade_in_samples < n ? A.prm.fade_in_samples : n;
         if (pre) {

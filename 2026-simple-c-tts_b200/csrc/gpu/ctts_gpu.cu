@@ -52,6 +52,15 @@ struct ctts_gpu_ctx {
     uint32_t* d_unit_off = nullptr;
     uint32_t* d_unit_cnt = nullptr;
     float* d_tables = nullptr;  // fade_out, fade_in, sine (1024 each), hann256, hann512, xfade4 (4096)
+    // normalize_rms applied to every unit, once per target_rms this context has seen
+    // (normalize_pool_kernel); plans keep pointers into these, they live as long as the context
+    struct NormPool {
+        float target_rms;
+        int16_t* d_pool;
+        int4* d_meta;
+    };
+    std::vector<NormPool> norm_pools;
+    uint64_t pool_samples = 0;
     uint32_t n_units = 0;
     uint32_t max_unit = 0;
     std::vector<uint32_t> unit_cnt;
@@ -90,6 +99,8 @@ struct ctts_gpu_plan {
     std::vector<uint64_t> bounds;
     bool in_arena = false;          // device buffers live in the context arena (batch path)
     std::vector<void*> owned;       // else: cudaMalloc'ed buffers to free
+    const int16_t* d_norm_pool = nullptr;   // context-owned (ctts_gpu_ctx::norm_pools)
+    const int4* d_unit_meta = nullptr;
     ctts_plan_op* d_ops = nullptr;
     ctts::RegionTask* d_tasks = nullptr;
     unsigned long long* d_chain = nullptr;
@@ -359,6 +370,7 @@ int ctts_gpu_init(ctts_gpu_ctx** out, const void* voice_db, size_t db_size, int 
         memcpy(&e, base + h.index_offset + (size_t)u * sizeof(DbEntry), sizeof e);
         memcpy(pool.data() + unit_off[u], pcm + 2ull * e.audio_offset, 2ull * e.sample_count);
     }
+    ctx->pool_samples = pool.size();
     CUI(cudaMalloc(reinterpret_cast<void**>(&ctx->d_pool), pool.size() * sizeof(int16_t)));
     CUI(cudaMemcpy(ctx->d_pool, pool.data(), pool.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
     CUI(cudaMalloc(reinterpret_cast<void**>(&ctx->d_unit_off), std::max<size_t>(h.unit_count, 1) * 4));
@@ -392,6 +404,10 @@ void ctts_gpu_free(ctts_gpu_ctx* ctx) {
     cudaFree(ctx->d_unit_off);
     cudaFree(ctx->d_unit_cnt);
     cudaFree(ctx->d_tables);
+    for (const ctts_gpu_ctx::NormPool& np : ctx->norm_pools) {
+        cudaFree(np.d_pool);
+        cudaFree(np.d_meta);
+    }
     cudaFree(ctx->d_batch_out);
     cudaFree(ctx->d_arena);
     if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
@@ -496,6 +512,35 @@ int ensure_arenas(ctts_gpu_ctx* ctx, size_t d_bytes, size_t h_bytes) {
         }                                                                                       \
     } while (0)
 
+// The normalized pool for `target_rms` (bit pattern compared: the kernel's result depends on nothing
+// else), created on the context stream at first use.
+int norm_pool_for(ctts_gpu_ctx* ctx, float target_rms, const int16_t** pool, const int4** meta) {
+    for (const ctts_gpu_ctx::NormPool& np : ctx->norm_pools)
+        if (memcmp(&np.target_rms, &target_rms, sizeof(float)) == 0) {
+            *pool = np.d_pool;
+            *meta = np.d_meta;
+            return CTTS_GPU_OK;
+        }
+    if (ctx->norm_pools.size() >= 64)
+        return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "more than 64 distinct target_rms values in one context");
+    ctts_gpu_ctx::NormPool np{target_rms, nullptr, nullptr};
+    if (cudaMalloc(reinterpret_cast<void**>(&np.d_pool), std::max<uint64_t>(ctx->pool_samples, 8) * sizeof(int16_t)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&np.d_meta), std::max<size_t>(ctx->n_units, 1) * sizeof(int4)) != cudaSuccess) {
+        cudaFree(np.d_pool);
+        return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "normalized pool");
+    }
+    ctx->norm_pools.push_back(np);
+    if (ctx->n_units) {
+        ctts::normalize_pool_kernel<<<ctx->n_units, ctts::ASM_THREADS, 0, ctx->stream>>>(ctx->d_pool, np.d_pool, ctx->d_unit_off,
+                                                                                       ctx->d_unit_cnt, np.d_meta, target_rms);
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaStreamSynchronize(ctx->stream));   // once: later plans may run on another stream
+    }
+    *pool = np.d_pool;
+    *meta = np.d_meta;
+    return CTTS_GPU_OK;
+}
+
 // The plan compiler, part 1.  chunk_samples == 0: one launch for the whole batch (best kernel
 // efficiency, the resident-plan path); > 0: utterances are cut, in slot order, into launches
 // of about that many output samples so that compiling / copying one chunk overlaps the
@@ -521,8 +566,15 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
     if (sc.bad_factor) return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "WORD_END pitch factors must lie in [0, 2.05]");
     const std::vector<uint64_t>&pre = sc.pre, &bound = sc.bound;
 
+    const int16_t* norm_pool = nullptr;
+    const int4* unit_meta = nullptr;
+    rc = norm_pool_for(ctx, params->target_rms, &norm_pool, &unit_meta);
+    if (rc) return rc;
+
     ctts_gpu_plan* p = new ctts_gpu_plan();
     p->ctx = ctx;
+    p->d_norm_pool = norm_pool;
+    p->d_unit_meta = unit_meta;
     p->n_utts = n;
     p->prm = *params;
     p->bounds = bound;
@@ -912,7 +964,8 @@ int launch_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, int16_t* d_pcm
     const PlanChunk& ch = p->chunks[c];
     if (ch.n_tasks == 0) return CTTS_GPU_OK;
     ctts::AsmArgs a{};
-    a.pool = ctx->d_pool;
+    a.pool = p->d_norm_pool;
+    a.unit_meta = p->d_unit_meta;
     a.unit_off = ctx->d_unit_off;
     a.unit_cnt = ctx->d_unit_cnt;
     a.n_units = ctx->n_units;

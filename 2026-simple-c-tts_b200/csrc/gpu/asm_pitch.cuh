@@ -31,6 +31,10 @@ namespace ctts {
 //
 // Both signals are needed voiced by the caller, so step 2 is skipped entirely
 // when either signal fails the filter.
+//
+// pair == false: only signal `a` is estimated (the threads of signal b idle).  The pitch of an
+// untouched unit head over a given analysis length is a function of the voice alone and comes
+// from a table (unit_pitch_kernel below), which leaves the buffer tail as the only signal.
 constexpr int PITCH_LO = CTTS_PLAN_SAMPLE_RATE / 400;  // 55
 constexpr int PITCH_HI = CTTS_PLAN_SAMPLE_RATE / 80;   // 275
 constexpr int PITCH_LEN = CTTS_PLAN_SAMPLE_RATE / 100; // 220
@@ -105,7 +109,7 @@ __device__ __forceinline__ void pitch_prefix_warp(const int16_t* s, uint32_t nee
 }
 
 __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int16_t* b, uint32_t n,
-                                    float* pa, float* pb) {
+                                    float* pa, float* pb, const bool pair = true) {
     *pa = 0.0f;
     *pb = 0.0f;
     if (n < 200) return;
@@ -126,13 +130,14 @@ __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int1
     uint32_t* ncand = cand + 2 * (PITCH_MAX_CAND + 2);            // [2]
     float* amax = reinterpret_cast<float*>(ncand + 2);            // [4] per lag warp
     float* e1s = amax + 4;                                        // [2]
-    float4* cpart = reinterpret_cast<float4*>(e1s + 10);          // [2 * PITCH_TPS] second-half partial sums
+    float4* cpart = reinterpret_cast<float4*>(e1s + 10);          // [2 * PITCH_TPS] partial sums of the second halves
 
     // ---- warps 0-1: exact prefix sums of squares; warps 2-7: float staging
     if (warp == 0) pitch_prefix_warp(a, need, Sa);
-    else if (warp == 1) pitch_prefix_warp(b, need, Sb);
-    else {
-        for (uint32_t i = tid - 64; i < 2 * PITCH_Y; i += ASM_THREADS - 64) {
+    else if (warp == 1) {
+        if (pair) pitch_prefix_warp(b, need, Sb);
+    } else {
+        for (uint32_t i = tid - 64; i < (pair ? 2u : 1u) * PITCH_Y; i += ASM_THREADS - 64) {
             const uint32_t k = i & (PITCH_Y - 1);
             const int16_t* src = i < PITCH_Y ? a : b;
             ya[i] = k < need ? (float)src[k] : 0.0f;   // yb == ya + PITCH_Y
@@ -144,18 +149,21 @@ __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int1
     }
     __syncthreads();
 
-    // ---- step 1: FMA scores; thread (half, signal, lag group) accumulates its half of the i range
+    // ---- step 1: FMA scores; thread (part, signal, lag group) accumulates its part of the i range:
+    //      two signals x two halves, or one signal x four quarters
     float c[PITCH_LPT] = {0.0f, 0.0f, 0.0f, 0.0f};
-    const int half = tid >> 7;
-    const int sig = (tid >> 6) & 1;
+    const int part = pair ? tid >> 7 : tid >> 6;
+    const int sig = pair ? (tid >> 6) & 1 : 0;
     const uint32_t lag0 = PITCH_LAG0 + PITCH_LPT * (uint32_t)(tid & (PITCH_TPS - 1));
     const bool lag_thread = lag0 <= hi;
-    const uint32_t split = ((len >> 1) + 3u) & ~3u;          // multiple of 4: both halves keep the alignment
+    // part boundaries are multiples of 4: every part keeps the float4 alignment
+    const uint32_t step = pair ? ((len >> 1) + 3u) & ~3u : (((len + 3u) >> 2) + 3u) & ~3u;
+    if (!pair) cpart = reinterpret_cast<float4*>(Sb);   // signal b's prefix array is free: 3 x PITCH_TPS partials
     if (lag_thread) {
         const float* x = sig ? yb : ya;
         const float* y = x + lag0;  // y[j] = s[lag0 + j]; (lag0 + 3) % 4 == 0
-        const uint32_t i_begin = half ? split : 0u;
-        const uint32_t i_end = half ? len : (split < len ? split : len);
+        const uint32_t i_begin = min((uint32_t)part * step, len);
+        const uint32_t i_end = min(i_begin + step, len);
         if (i_begin < i_end) {
             float w0 = y[i_begin], w1 = y[i_begin + 1], w2 = y[i_begin + 2];
             const uint32_t i4 = i_begin + ((i_end - i_begin) & ~3u);
@@ -179,16 +187,18 @@ __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int1
                 for (int k = 0; k < PITCH_LPT; k++) c[k] = __fmaf_rn(xs, y[i + k], c[k]);
             }
         }
-        if (half) cpart[tid & (2 * PITCH_TPS - 1)] = make_float4(c[0], c[1], c[2], c[3]);
+        if (part) cpart[pair ? (tid & (2 * PITCH_TPS - 1)) : (part - 1) * PITCH_TPS + (tid & (PITCH_TPS - 1))] = make_float4(c[0], c[1], c[2], c[3]);
     }
     __syncthreads();
 
-    // ---- scores and per-signal maximum (first-half threads)
+    // ---- scores and per-signal maximum (part 0 threads)
     float sc[PITCH_LPT];
     float my_max = -1.0f;
-    if (lag_thread && !half) {
-        const float4 p2 = cpart[tid];
-        c[0] += p2.x; c[1] += p2.y; c[2] += p2.z; c[3] += p2.w;
+    if (lag_thread && !part) {
+        for (int q = 0; q < (pair ? 1 : 3); q++) {
+            const float4 p2 = cpart[q * PITCH_TPS + tid];   // pair: tid < 128, one partial
+            c[0] += p2.x; c[1] += p2.y; c[2] += p2.z; c[3] += p2.w;
+        }
         const unsigned long long* S = sig ? Sb : Sa;
         const float e1 = (float)(S[len] - S[0]);
 #pragma unroll
@@ -209,7 +219,7 @@ __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int1
         if (lane == 0) amax[warp] = my_max;
     }
     __syncthreads();
-    const float max_a = fmaxf(amax[0], amax[1]), max_b = fmaxf(amax[2], amax[3]);
+    const float max_a = fmaxf(amax[0], amax[1]), max_b = pair ? fmaxf(amax[2], amax[3]) : 1.0f;
     // unvoiced by the filter: the reference's best cannot exceed 0.3
     if (!(max_a > 0.3f - PITCH_EPS) || !(max_b > 0.3f - PITCH_EPS)) {   // CTA-uniform
         __syncthreads();   // scratch is reused by the caller
@@ -217,7 +227,7 @@ __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int1
     }
 
     // ---- candidates
-    if (lag_thread && !half) {
+    if (lag_thread && !part) {
         const float thr = (sig ? max_b : max_a) - 2.0f * PITCH_EPS;
 #pragma unroll
         for (int k = 0; k < PITCH_LPT; k++) {
@@ -230,9 +240,9 @@ __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int1
     __syncthreads();
     uint32_t na = ncand[0], nb = ncand[1];
     // a single candidate well above the voicing threshold IS the reference's answer
-    const bool sure_a = na == 1 && max_a > 0.3f + PITCH_EPS, sure_b = nb == 1 && max_b > 0.3f + PITCH_EPS;
+    const bool sure_a = na == 1 && max_a > 0.3f + PITCH_EPS, sure_b = !pair || (nb == 1 && max_b > 0.3f + PITCH_EPS);
     if (sure_a) *pa = (float)CTTS_PLAN_SAMPLE_RATE / (float)cand[0];
-    if (sure_b) *pb = (float)CTTS_PLAN_SAMPLE_RATE / (float)cand[PITCH_MAX_CAND + 2];
+    if (sure_b && pair) *pb = (float)CTTS_PLAN_SAMPLE_RATE / (float)cand[PITCH_MAX_CAND + 2];
     if (sure_a && sure_b) {
         __syncthreads();
         return;
@@ -293,14 +303,39 @@ __device__ void estimate_pitch_pair(const Smem& sm, const int16_t* a, const int1
     __syncthreads();   // scratch is reused by the caller
 }
 
+// estimate_pitch (ctts.c:1899) of the first job.y samples of the normalized unit at pool offset
+// job.x, into table[job.z]: what smooth_pitch_boundary computes for `next_samples` whenever the
+// analysis length is min(2*xf, n/2).  One CTA per (unit, length) pair the plan compiler has not
+// seen in this context before.
+__global__ void __launch_bounds__(ASM_THREADS) unit_pitch_kernel(const int16_t* __restrict__ norm_pool, const uint3* __restrict__ jobs,
+                                                                 float* __restrict__ table) {
+    __shared__ __align__(16) uint32_t scratch[SCR_WORDS];
+    Smem sm{};
+    sm.scratch = scratch;
+    const uint3 job = jobs[blockIdx.x];
+    const int16_t* head = norm_pool + job.x;
+    float pa = 0.0f, pb = 0.0f;
+    estimate_pitch_pair(sm, head, head, job.y, &pa, &pb, false);
+    if (threadIdx.x == 0) table[job.z] = pa;
+}
+
 // smooth_pitch_boundary + apply_pitch_shift, ctts.c:1946-2024.  `reg` is the analysis length
 // min(2*xf, count/2, n/2) resolved by the caller (0 = the reference returns early); `us` is the
-// staged unit head.
-__device__ void smooth_pitch(const State& s, const Smem& sm, int16_t* us, uint32_t n, uint32_t xf, uint32_t reg) {
+// staged unit head; have_np: the head's pitch over `reg` samples is the table value np_tab.
+__device__ void smooth_pitch(const State& s, const Smem& sm, int16_t* us, uint32_t n, uint32_t xf, uint32_t reg,
+                             bool have_np, float np_tab) {
     if (reg == 0) return;
     const int tid = threadIdx.x;
     float pp, np;
-    estimate_pitch_pair(sm, s.w + ((int)s.cnt - (int)reg), us, reg, &pp, &np);
+    const int16_t* prev = s.w + ((int)s.cnt - (int)reg);
+    if (have_np) {
+        np = np_tab;
+        if (!(np > 0)) return;   // ctts.c:1994: both must be voiced
+        float unused;
+        estimate_pitch_pair(sm, prev, prev, reg, &pp, &unused, false);
+    } else {
+        estimate_pitch_pair(sm, prev, us, reg, &pp, &np);
+    }
     if (!(pp > 0 && np > 0)) return;
     float ratio = np / pp;
     if (!(ratio > 1.15f || ratio < 0.85f)) return;

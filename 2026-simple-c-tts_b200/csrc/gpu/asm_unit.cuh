@@ -141,6 +141,9 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
     const uint32_t n = __float_as_uint(op.f0);
     if (n == 0) return;
     const int4 meta = __ldg(A.unit_meta + op.a);   // needed only after the join
+    // pitch of the unit head over min(2*xf, n/2) samples, if the plan compiler found it in the table
+    const uint32_t np_slot = __float_as_uint(op.f2);
+    const float np_tab = np_slot ? __ldg(A.unit_pitch + (np_slot - 1)) : 0.0f;
     const int16_t* src = A.pool + __float_as_uint(op.f1);
     const int4* srcv = reinterpret_cast<const int4*>(src);
     const uint32_t nvec = (n + 7) >> 3;
@@ -159,6 +162,7 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
     // !join <=> count == 0 || after_word_boundary: the unit starts fresh (fade-in, no crossfade)
     uint32_t a = 0;             // crossfade = energy-match length min(xf, count, n), ctts.c:3319, :1736
     uint32_t reg = 0;           // pitch analysis length, ctts.c:1983-1987
+    uint32_t reg_full = 0;      // its value when the buffer is long enough: what the table is for
     if (join && xf > 0) {
         const uint32_t m = xf < n ? xf : n;
         if (s.cnt >= m) a = m;
@@ -169,6 +173,7 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
         }
         if (n >= 200) {
             const uint32_t m2 = 2 * xf < n / 2 ? 2 * xf : n / 2;
+            reg_full = m2;
             if (s.cnt >= 200 && s.cnt / 2 >= m2) reg = m2;
             else {
                 need_base(s, sm, A);
@@ -210,7 +215,7 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
             hsum = sum8_s16(q, hsum);
         }
         __syncthreads();
-        smooth_pitch(s, sm, us, n, xf, reg);
+        smooth_pitch(s, sm, us, n, xf, reg, np_slot != 0 && reg == reg_full, np_tab);
         match_energy(s, sm, us, a);
         // remove_dc_offset (ctts.c:1568) inside buffer_append_crossfade (ctts.c:3279): the sum over the
         // joined unit = table sum - head as gathered + head as joined

@@ -55,11 +55,16 @@ struct ctts_gpu_ctx {
     // normalize_rms applied to every unit, once per target_rms this context has seen
     // (normalize_pool_kernel); plans keep pointers into these, they live as long as the context
     struct NormPool {
-        float target_rms;
-        int16_t* d_pool;
-        int4* d_meta;
+        float target_rms = 0;
+        int16_t* d_pool = nullptr;
+        int4* d_meta = nullptr;
+        // estimate_pitch of a unit's (normalized, untouched) head over R samples: table slots,
+        // filled by unit_pitch_kernel when the plan compiler first meets a (unit, R) pair
+        float* d_pitch = nullptr;
+        uint32_t pitch_cap = 0, pitch_used = 0;
+        std::vector<std::vector<std::pair<uint32_t, uint32_t>>> pitch_slots;   // per unit: (R, slot)
     };
-    std::vector<NormPool> norm_pools;
+    std::vector<NormPool*> norm_pools;
     uint64_t pool_samples = 0;
     uint32_t n_units = 0;
     uint32_t max_unit = 0;
@@ -99,8 +104,7 @@ struct ctts_gpu_plan {
     std::vector<uint64_t> bounds;
     bool in_arena = false;          // device buffers live in the context arena (batch path)
     std::vector<void*> owned;       // else: cudaMalloc'ed buffers to free
-    const int16_t* d_norm_pool = nullptr;   // context-owned (ctts_gpu_ctx::norm_pools)
-    const int4* d_unit_meta = nullptr;
+    ctts_gpu_ctx::NormPool* np = nullptr;   // context-owned: normalized pool and its tables
     ctts_plan_op* d_ops = nullptr;
     ctts::RegionTask* d_tasks = nullptr;
     unsigned long long* d_chain = nullptr;
@@ -404,9 +408,11 @@ void ctts_gpu_free(ctts_gpu_ctx* ctx) {
     cudaFree(ctx->d_unit_off);
     cudaFree(ctx->d_unit_cnt);
     cudaFree(ctx->d_tables);
-    for (const ctts_gpu_ctx::NormPool& np : ctx->norm_pools) {
-        cudaFree(np.d_pool);
-        cudaFree(np.d_meta);
+    for (ctts_gpu_ctx::NormPool* np : ctx->norm_pools) {
+        cudaFree(np->d_pool);
+        cudaFree(np->d_meta);
+        cudaFree(np->d_pitch);
+        delete np;
     }
     cudaFree(ctx->d_batch_out);
     cudaFree(ctx->d_arena);
@@ -514,30 +520,65 @@ int ensure_arenas(ctts_gpu_ctx* ctx, size_t d_bytes, size_t h_bytes) {
 
 // The normalized pool for `target_rms` (bit pattern compared: the kernel's result depends on nothing
 // else), created on the context stream at first use.
-int norm_pool_for(ctts_gpu_ctx* ctx, float target_rms, const int16_t** pool, const int4** meta) {
-    for (const ctts_gpu_ctx::NormPool& np : ctx->norm_pools)
-        if (memcmp(&np.target_rms, &target_rms, sizeof(float)) == 0) {
-            *pool = np.d_pool;
-            *meta = np.d_meta;
+int norm_pool_for(ctts_gpu_ctx* ctx, float target_rms, ctts_gpu_ctx::NormPool** out) {
+    for (ctts_gpu_ctx::NormPool* np : ctx->norm_pools)
+        if (memcmp(&np->target_rms, &target_rms, sizeof(float)) == 0) {
+            *out = np;
             return CTTS_GPU_OK;
         }
     if (ctx->norm_pools.size() >= 64)
         return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "more than 64 distinct target_rms values in one context");
-    ctts_gpu_ctx::NormPool np{target_rms, nullptr, nullptr};
-    if (cudaMalloc(reinterpret_cast<void**>(&np.d_pool), std::max<uint64_t>(ctx->pool_samples, 8) * sizeof(int16_t)) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void**>(&np.d_meta), std::max<size_t>(ctx->n_units, 1) * sizeof(int4)) != cudaSuccess) {
-        cudaFree(np.d_pool);
+    ctts_gpu_ctx::NormPool* np = new ctts_gpu_ctx::NormPool();
+    np->target_rms = target_rms;
+    np->pitch_cap = std::max<uint32_t>(1u << 16, 64u * ctx->n_units);
+    np->pitch_slots.resize(ctx->n_units);
+    if (cudaMalloc(reinterpret_cast<void**>(&np->d_pool), std::max<uint64_t>(ctx->pool_samples, 8) * sizeof(int16_t)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&np->d_meta), std::max<size_t>(ctx->n_units, 1) * sizeof(int4)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&np->d_pitch), (size_t)np->pitch_cap * sizeof(float)) != cudaSuccess) {
+        cudaFree(np->d_pool);
+        cudaFree(np->d_meta);
+        cudaFree(np->d_pitch);
+        delete np;
         return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "normalized pool");
     }
     ctx->norm_pools.push_back(np);
     if (ctx->n_units) {
-        ctts::normalize_pool_kernel<<<ctx->n_units, ctts::ASM_THREADS, 0, ctx->stream>>>(ctx->d_pool, np.d_pool, ctx->d_unit_off,
-                                                                                       ctx->d_unit_cnt, np.d_meta, target_rms);
+        ctts::normalize_pool_kernel<<<ctx->n_units, ctts::ASM_THREADS, 0, ctx->stream>>>(ctx->d_pool, np->d_pool, ctx->d_unit_off,
+                                                                                       ctx->d_unit_cnt, np->d_meta, target_rms);
         CU(ctx, cudaGetLastError());
         CU(ctx, cudaStreamSynchronize(ctx->stream));   // once: later plans may run on another stream
     }
-    *pool = np.d_pool;
-    *meta = np.d_meta;
+    *out = np;
+    return CTTS_GPU_OK;
+}
+
+// Table slot (+1) of the pitch of unit u's head over R samples; a new pair is appended to `jobs`
+// for unit_pitch_kernel.  0: the table is full (the kernel then estimates the head itself).
+inline uint32_t pitch_slot_for(ctts_gpu_ctx* ctx, ctts_gpu_ctx::NormPool* np, uint32_t u, uint32_t R, std::vector<uint3>* jobs) {
+    std::vector<std::pair<uint32_t, uint32_t>>& v = np->pitch_slots[u];
+    for (const std::pair<uint32_t, uint32_t>& e : v)
+        if (e.first == R) return e.second + 1;
+    if (np->pitch_used >= np->pitch_cap) return 0;
+    const uint32_t slot = np->pitch_used++;
+    v.emplace_back(R, slot);
+    jobs->push_back(make_uint3(ctx->unit_off[u], R, slot));
+    return slot + 1;
+}
+
+// Fill the table slots of `jobs` (rare: only for pairs no earlier plan of this context used).
+int run_pitch_jobs(ctts_gpu_ctx* ctx, ctts_gpu_ctx::NormPool* np, const std::vector<uint3>& jobs) {
+    if (jobs.empty()) return CTTS_GPU_OK;
+    uint3* d_jobs = nullptr;
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&d_jobs), jobs.size() * sizeof(uint3)));
+    cudaError_t e = cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(uint3), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        ctts::unit_pitch_kernel<<<(unsigned)jobs.size(), ctts::ASM_THREADS, 0, ctx->stream>>>(np->d_pool, d_jobs, np->d_pitch);
+        e = cudaGetLastError();
+    }
+    // the slots are used by every later launch, on whichever stream: finish them now
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_jobs);
+    if (e != cudaSuccess) return fail(ctx, CTTS_GPU_ERR_CUDA, "unit_pitch_kernel: %s", cudaGetErrorString(e));
     return CTTS_GPU_OK;
 }
 
@@ -566,15 +607,13 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
     if (sc.bad_factor) return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "WORD_END pitch factors must lie in [0, 2.05]");
     const std::vector<uint64_t>&pre = sc.pre, &bound = sc.bound;
 
-    const int16_t* norm_pool = nullptr;
-    const int4* unit_meta = nullptr;
-    rc = norm_pool_for(ctx, params->target_rms, &norm_pool, &unit_meta);
+    ctts_gpu_ctx::NormPool* np = nullptr;
+    rc = norm_pool_for(ctx, params->target_rms, &np);
     if (rc) return rc;
 
     ctts_gpu_plan* p = new ctts_gpu_plan();
     p->ctx = ctx;
-    p->d_norm_pool = norm_pool;
-    p->d_unit_meta = unit_meta;
+    p->np = np;
     p->n_utts = n;
     p->prm = *params;
     p->bounds = bound;
@@ -832,6 +871,7 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
     // sum still fits the window.
     struct HostTask { uint32_t op_begin, op_end; uint64_t bound; uint32_t region_max; };
     std::vector<HostTask> ht;
+    std::vector<uint3> pitch_jobs;
     std::vector<uint32_t> ht_begin(u1 - u0 + 1, 0);   // CSR: tasks of utterance u0 + i
     uint32_t max_rows = 0;
     for (uint32_t u = u0; u < u1; u++) {
@@ -863,6 +903,14 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
                     // so the kernel needs no dependent table look-up before the gather
                     memcpy(&op.f0, &cn, 4);
                     memcpy(&op.f1, &ctx->unit_off[op.a], 4);
+                    // ... and so does the table slot of the head's pitch over min(2*xf, n/2) samples
+                    // (the analysis length of ctts.c:1983-1987 whenever the buffer is long enough)
+                    uint32_t slot1 = 0;
+                    if (!(op.flags & CTTS_UNIT_AFTER_BOUNDARY) && op.b > 0 && cn >= 200) {
+                        const uint32_t m2 = 2 * op.b < cn / 2 ? 2 * op.b : cn / 2;   // uint32 like the kernel
+                        if (m2 >= 200) slot1 = pitch_slot_for(ctx, p->np, op.a, m2, &pitch_jobs);
+                    }
+                    memcpy(&op.f2, &slot1, 4);
                     count_ub += cn;
                     p->gather += cn;
                     rb += unit_append_bound(op, cn, L);
@@ -893,6 +941,10 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
         max_rows = std::max<uint32_t>(max_rows, (uint32_t)ht.size() - ht_begin[u - u0]);
     }
     ht_begin[u1 - u0] = (uint32_t)ht.size();
+    {
+        const int rcj = run_pitch_jobs(ctx, p->np, pitch_jobs);
+        if (rcj) return rcj;
+    }
 
     // ticket order: region-major (task k of every utterance before task k+1 of any), inside a
     // row longest first (it is the one a successor may have to wait for, and longest-first
@@ -964,8 +1016,9 @@ int launch_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, int16_t* d_pcm
     const PlanChunk& ch = p->chunks[c];
     if (ch.n_tasks == 0) return CTTS_GPU_OK;
     ctts::AsmArgs a{};
-    a.pool = p->d_norm_pool;
-    a.unit_meta = p->d_unit_meta;
+    a.pool = p->np->d_pool;
+    a.unit_meta = p->np->d_meta;
+    a.unit_pitch = p->np->d_pitch;
     a.unit_off = ctx->d_unit_off;
     a.unit_cnt = ctx->d_unit_cnt;
     a.n_units = ctx->n_units;

@@ -358,3 +358,24 @@ def test_chunked_stretch_batch(H, gpu, small_db, oracle_small, front_small, monk
         for u in range(plan.n_utts):
             _assert_same(outs[u], want[u], f"wave {wave} utt {u} speed {speeds[u]}")
     monkeypatch.delenv("CTTS_GPU_STRETCH_WAVE")
+
+
+def test_target_rms_variants_share_a_context(H, synth_small, oracle_small, front_small):
+    """normalize_rms (ctts.c:1709) lives in a per-context table keyed by target_rms (the normalized
+    pool and the unit-head pitch table): plans with different targets -- off, gain clamped at 3.0
+    and at 0.1 -- alternate on one context and each must match the oracle bit for bit."""
+    import copy
+    texts = H.corpus.batch(10, seed=61, target_chars=110) + ["olá mundo"]
+    speeds = [1.0] * 9 + [1.5, 1.0]
+    plan = front_small.plan(texts, speeds)
+    base = front_small.params()
+    plans = []
+    for target in (3000.0, 0.0, 20000.0, 150.0, 3000.0):
+        prm = copy.copy(base)
+        prm.target_rms = target
+        plans.append((prm, synth_small.create_plan(plan, prm)))
+    for prm, rp in plans + plans[::-1]:
+        rp.run()
+        for u, got in enumerate(rp.utterances()):
+            want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))
+            _assert_same(got, want, f"target_rms {prm.target_rms} utt {u}")

@@ -7,27 +7,6 @@ namespace ctts {
 
 // ---------------------------------------------------------------- unit op
 
-// the two crossfade gains at t share the table position (fast_fade_out / fast_fade_in, ctts.c:76-92);
-// xfade4[k] = {fade_out[k], fade_out[k+1], fade_in[k], fade_in[k+1]}: one 16-byte load
-__device__ __forceinline__ void crossfade_gains(const DevTables& tab, float t, float* pg, float* ng) {
-    float x = t * (float)(LUT_N - 1);
-    int k = (int)x;
-    if (k >= LUT_N - 1) {
-        const float4 e = __ldg(tab.xfade4 + LUT_N - 1);
-        *pg = e.x;
-        *ng = e.z;
-    } else if (k < 0) {
-        const float4 e = __ldg(tab.xfade4);
-        *pg = e.x;
-        *ng = e.z;
-    } else {
-        const float4 e = __ldg(tab.xfade4 + k);
-        float fr = x - (float)k, om = 1.0f - fr;
-        *pg = e.x * om + e.y * fr;
-        *ng = e.z * om + e.w * fr;
-    }
-}
-
 __device__ __forceinline__ int sub_dc(int v, int dc) {
     // clamp(v - dc) to int16 (remove_dc_offset, ctts.c:1577-1581)
     return max(__viaddmin_s32(v, -dc, 32767), -32768);
@@ -232,6 +211,8 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
     }
 
     // ---- body: pool -> minus DC -> window, once
+    // (keeping the loads of two vectors in flight, an L1 prefetch before the join and taking tickets
+    // one task ahead were all measured slower: the SM is issue bound, other CTAs fill the wait)
     {
         const DcPack dp = dc_pack(dc);
         for (uint32_t j = tid; j < gvec; j += ASM_THREADS) {
@@ -265,16 +246,31 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
     if (hs) {
         // staged head: crossfade mix (ctts.c:3328-3344) over [0, a), plain copy over [a, hsn)
         const float inv = a ? 1.0f / (float)a : 0.0f;
-        for (uint32_t i = tid; i < hsn; i += ASM_THREADS) {
+        for (uint32_t i = tid; i < a; i += ASM_THREADS) {
+            // fast_fade_out / fast_fade_in (ctts.c:76-92) share the table position;
+            // xfade4[k] = {fade_out[k], fade_out[k+1], fade_in[k], fade_in[k+1]}: one 16-byte load
+            const float x = ((float)i * inv) * (float)(LUT_N - 1);
+            const int k = (int)x;
+            float pg, ng;
+            if (k >= LUT_N - 1 || k < 0) {   // past the ends: the end entry itself
+                const float4 e = __ldg(A.tab.xfade4 + (k < 0 ? 0 : LUT_N - 1));
+                pg = e.x;
+                ng = e.z;
+            } else {
+                const float4 e = __ldg(A.tab.xfade4 + k);
+                const float fr = x - (float)k, om = 1.0f - fr;
+                pg = e.x * om + e.y * fr;
+                ng = e.z * om + e.w * fr;
+            }
             int v = us[i];
             if (remove_dc) v = sub_dc(v, dc);
-            if (i < a) {
-                float pg, ng;
-                crossfade_gains(A.tab, (float)i * inv, &pg, &ng);
-                int p = tail[i];
-                int mix = (int)((float)p * pg + (float)v * ng);
-                v = max(min(mix, 32767), -32768);
-            }
+            const int p = tail[i];
+            const int mix = (int)((float)p * pg + (float)v * ng);
+            tail[i] = (int16_t)max(min(mix, 32767), -32768);
+        }
+        for (uint32_t i = a + tid; i < hsn; i += ASM_THREADS) {
+            int v = us[i];
+            if (remove_dc) v = sub_dc(v, dc);
             tail[i] = (int16_t)v;
         }
     } else if (!join) {

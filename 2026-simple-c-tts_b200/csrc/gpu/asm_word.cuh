@@ -228,7 +228,8 @@ constexpr uint32_t CONTOUR_STAGE = CONTOUR_TILE + CONTOUR_CARRY;  // 256 behind,
 static_assert(CONTOUR_CARRY % 8 == 0, "carry is whole staging vectors");
 constexpr uint32_t CONTOUR_PF_MAX = 1024;                    // frames with a tabulated pitch factor
 constexpr uint32_t CONTOUR_SCRATCH_WORDS = CONTOUR_STAGE + CONTOUR_PF_MAX;
-static_assert(CONTOUR_SCRATCH_WORDS + 8 <= SCR_WORDS, "contour scratch fits");
+// the unit-head staging area follows the scratch and is dead during WORD_END: at least 252 more words (hcap >= 504 samples)
+static_assert(CONTOUR_SCRATCH_WORDS + 8 <= SCR_WORDS + 252, "contour scratch fits");
 static_assert(ASM_THREADS % 128 == 0, "a thread's outputs must keep their position inside a frame");
 
 // one frame's contribution to an output sample (ctts.c:2236-2251): linear-interpolated read at
@@ -269,14 +270,14 @@ __device__ bool pitch_contour(const Smem& sm, int16_t* x, uint32_t n, float f0, 
     // stage[phase + 256 + u] = x[t0 + u]: aligned 8-sample vectors of x land on float4 pairs
     const uint32_t phase = (uint32_t)((reinterpret_cast<uintptr_t>(x) >> 1) & 7u);
     float* sbase = stage + phase + PITCH_FRAME;   // index u relative to the tile start
+    static_assert(CONTOUR_CARRY / 4 <= ASM_THREADS, "one float4 of carry per thread");
+    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
     for (uint32_t t0 = 0; t0 < n; t0 += CONTOUR_TILE) {
         const uint32_t t1 = min(t0 + CONTOUR_TILE, n);
-        // ---- staging: carry what overlaps the previous tile, load and convert the rest
-        if (t0 != 0) {
-            for (uint32_t v = tid; v < CONTOUR_CARRY / 4; v += ASM_THREADS)
-                *(reinterpret_cast<float4*>(stage) + v) = *(reinterpret_cast<const float4*>(stage + CONTOUR_TILE) + v);
-        }
-        __syncthreads();
+        const bool more = t0 + CONTOUR_TILE < n;
+        // ---- staging: what overlaps the previous tile was picked up in a register before that
+        //      tile's closing barrier (no barrier of its own), the rest is loaded and converted
+        if (t0 != 0 && tid < (int)(CONTOUR_CARRY / 4)) *(reinterpret_cast<float4*>(stage) + tid) = carry;
         for (uint32_t v = (t0 == 0 ? 0u : CONTOUR_CARRY / 8) + tid; v < CONTOUR_STAGE / 8; v += ASM_THREADS) {
             const int u0 = (int)(v << 3) - (int)(phase + PITCH_FRAME);   // u of the vector's first sample
             const long long g0 = (long long)t0 + u0;                     // segment index
@@ -328,6 +329,7 @@ __device__ bool pitch_contour(const Smem& sm, int16_t* x, uint32_t n, float f0, 
             }
 #pragma unroll
             for (int r = 0; r < CONTOUR_KPT; r++) x[t0 + (uint32_t)tid + (uint32_t)(ASM_THREADS * r)] = (int16_t)o[r];
+            if (more && tid < (int)(CONTOUR_CARRY / 4)) carry = *(reinterpret_cast<const float4*>(stage + CONTOUR_TILE) + tid);
             __syncthreads();
             continue;
         }
@@ -391,6 +393,7 @@ __device__ bool pitch_contour(const Smem& sm, int16_t* x, uint32_t n, float f0, 
             }
             x[j] = (int16_t)o;
         }
+        if (more && tid < (int)(CONTOUR_CARRY / 4)) carry = *(reinterpret_cast<const float4*>(stage + CONTOUR_TILE) + tid);
         __syncthreads();
     }
     return true;

@@ -35,6 +35,7 @@ def lib(build: bool = True) -> C.CDLL:
     global _lib
     if _lib is None:
         path = _build.build_gpu() if build else _build.GPU_SO
+        path = os.environ.get("CTTS_GPU_LIB", path)   # development: A/B a differently built library
         if not os.path.exists(path):
             raise RuntimeError("libctts_gpu.so is missing: the CUDA back end has no CPU fallback")
         L = C.CDLL(path)

@@ -542,12 +542,16 @@ int norm_pool_for(ctts_gpu_ctx* ctx, float target_rms, ctts_gpu_ctx::NormPool** 
         return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "normalized pool");
     }
     ctx->norm_pools.push_back(np);
+    const auto t0 = std::chrono::steady_clock::now();
     if (ctx->n_units) {
         ctts::normalize_pool_kernel<<<ctx->n_units, ctts::ASM_THREADS, 0, ctx->stream>>>(ctx->d_pool, np->d_pool, ctx->d_unit_off,
                                                                                        ctx->d_unit_cnt, np->d_meta, target_rms);
         CU(ctx, cudaGetLastError());
         CU(ctx, cudaStreamSynchronize(ctx->stream));   // once: later plans may run on another stream
     }
+    if (getenv("CTTS_GPU_TRACE"))
+        fprintf(stderr, "ctts_gpu: normalized pool for target_rms %g: %u units, %llu samples in %.2f ms\n", (double)target_rms, ctx->n_units,
+                (unsigned long long)ctx->pool_samples, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     *out = np;
     return CTTS_GPU_OK;
 }
@@ -568,6 +572,7 @@ inline uint32_t pitch_slot_for(ctts_gpu_ctx* ctx, ctts_gpu_ctx::NormPool* np, ui
 // Fill the table slots of `jobs` (rare: only for pairs no earlier plan of this context used).
 int run_pitch_jobs(ctts_gpu_ctx* ctx, ctts_gpu_ctx::NormPool* np, const std::vector<uint3>& jobs) {
     if (jobs.empty()) return CTTS_GPU_OK;
+    const auto t0 = std::chrono::steady_clock::now();
     uint3* d_jobs = nullptr;
     CU(ctx, cudaMalloc(reinterpret_cast<void**>(&d_jobs), jobs.size() * sizeof(uint3)));
     cudaError_t e = cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(uint3), cudaMemcpyHostToDevice, ctx->stream);
@@ -579,6 +584,9 @@ int run_pitch_jobs(ctts_gpu_ctx* ctx, ctts_gpu_ctx::NormPool* np, const std::vec
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_jobs);
     if (e != cudaSuccess) return fail(ctx, CTTS_GPU_ERR_CUDA, "unit_pitch_kernel: %s", cudaGetErrorString(e));
+    if (getenv("CTTS_GPU_TRACE"))
+        fprintf(stderr, "ctts_gpu: unit-head pitch table: %zu new entries (%u in all) in %.2f ms including the stream drain\n", jobs.size(),
+                np->pitch_used, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     return CTTS_GPU_OK;
 }
 

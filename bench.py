@@ -41,8 +41,8 @@ UNIT = "audio-s/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--utts", type=int, default=4096, help="utterances per GPU (weak scaling)")
     ap.add_argument("--workload", default="speed1", choices=["speed1", "mixed", "long"],
@@ -363,6 +363,7 @@ def main() -> int:
                 "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(dominant), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
+                "kernel_ms_min_max": [float(np.min(step_ms)), float(np.max(step_ms))],
                 "note": "step = one assemble_kernel launch (+4 small memsets)" if args.workload != "mixed"
                         else "step = assemble + wsola_search + wsola_ola; the stretch stage is FP32-issue bound, HBM fraction reported as the metric demands",
             },

@@ -43,60 +43,105 @@ __device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t big, 
     uint32_t keep_n = min_sil / 4;
     if (keep_n < 10) keep_n = 10;
 
-    // A run of >= min_sil silent samples covers >= (min_sil - 7) / 8 whole grid vectors, all of them
-    // silent; that many consecutive vectors contain an aligned group of g = 32, 16 or 8 of them
-    // (2g - 1 <= count).  No such group: nothing can be cut (ctts.c:1662-1668 copies every run).
-    if (have_vm && limit >= 0 && min_sil >= 15 + 8 * 14) {
-        const uint32_t needv = (min_sil - 7) / 8;
-        const int g = needv >= 63 ? 32 : needv >= 31 ? 16 : 8;
-        int found = 0;
-        for (uint32_t j0 = 0; j0 < gvec; j0 += ASM_THREADS) {
-            const uint32_t j = j0 + tid;
-            const bool sil = j < gvec && (int)vm[j] <= limit;
-            const uint32_t w = __ballot_sync(0xffffffffu, sil);
-            if (g == 32) found |= w == 0xffffffffu;
-            else if (g == 16) found |= (w & 0xffffu) == 0xffffu || (w >> 16) == 0xffffu;
-            else found |= ((w & (w >> 1) & (w >> 2) & (w >> 3) & (w >> 4) & (w >> 5) & (w >> 6) & (w >> 7)) & 0x01010101u) != 0;
-        }
-        if (!__syncthreads_or(found)) return len;
-    }
-
     uint32_t* words;
     if (2 * wn <= SCR_WORDS) words = sm.scratch;
     else words = A.trim_scratch + (size_t)big * A.trim_scratch_words;   // host sized it for this task
     uint32_t* woff = words + wn;
+    uint8_t* bytes = reinterpret_cast<uint8_t*>(words);
+    const uint32_t nb = wn * 4;
+    // mask byte t = 8 samples 8t .. 8t+7 of the region, 1 = |x| <= threshold: packed |x| (clamped at 0:
+    // abs16(-32768) is negative, hence silent like 0), minus (limit + 1): the sign bit is the answer
+    const uint32_t c2 = (uint32_t)((-(limit + 1)) & 0xffff) * 0x10001u;
+    auto mask_byte = [&](uint32_t t) -> uint32_t {
+        if (8 * t >= len) return 0u;
+        int4 q = grid[t];
+        if (phase) {
+            int4 hi = make_int4(0, 0, 0, 0);
+            if (8 * (t + 1) < len + phase) hi = grid[t + 1];
+            q = shift_pick(q, hi, phase);
+        }
+        uint32_t acc = sign_mask2(__vadd2(absmax0_2((uint32_t)q.x), c2)) & 0x00020001u;
+        acc |= sign_mask2(__vadd2(absmax0_2((uint32_t)q.y), c2)) & 0x00080004u;
+        acc |= sign_mask2(__vadd2(absmax0_2((uint32_t)q.z), c2)) & 0x00200010u;
+        acc |= sign_mask2(__vadd2(absmax0_2((uint32_t)q.w), c2)) & 0x00800040u;
+        uint32_t byte = (acc | (acc >> 16)) & 0xffu;
+        if (8 * t + 8 > len) byte &= (1u << (len - 8 * t)) - 1u;
+        return byte;
+    };
+
+    // A run of >= min_sil silent samples covers >= needv = (min_sil - 7) / 8 whole grid vectors, all of
+    // them silent, plus parts of the vector before and the vector after.  So the runs that can be cut are
+    // found on the per-vector maxima (1 bit per vector), and the per-sample mask is only formed around
+    // them: everywhere else it is left 0 ("not silent"), which can only split runs that are kept whole
+    // anyway (ctts.c:1662-1668 copies every run shorter than min_sil).  No candidate: nothing is cut.
+    constexpr uint32_t TRIM_MAX_CAND = 48;
+    const uint32_t sv_words = (gvec + 31) >> 5;
+    const uint32_t sv_at = 2 * wn + (gvec + 1) / 2 + 1;          // after the mask arrays and vm
+    bool full_mask = true;
+    if (have_vm && limit >= 0 && min_sil >= 15 + 8 * 14 && sv_at + sv_words + 2 + 2 * TRIM_MAX_CAND <= SCR_WORDS) {
+        const uint32_t needv = (min_sil - 7) / 8;
+        uint32_t* sv = sm.scratch + sv_at;
+        uint32_t* cand = sv + sv_words;                           // [0] count, then (first, last) vector pairs
+        for (uint32_t j0 = 0; j0 < gvec; j0 += ASM_THREADS) {
+            const uint32_t j = j0 + tid;
+            const bool sil = j < gvec && (int)vm[j] <= limit;
+            const uint32_t w = __ballot_sync(0xffffffffu, sil);
+            if (lane == 0 && (j0 >> 5) + warp < sv_words) sv[(j0 >> 5) + warp] = w;
+        }
+        if (tid == 0) cand[0] = 0;
+        __syncthreads();
+        for (uint32_t t = tid; t < sv_words; t += ASM_THREADS) {
+            const uint32_t w = sv[t];
+            uint32_t starts = w & ~((w << 1) | (t ? sv[t - 1] >> 31 : 0u));   // set bits whose predecessor is clear
+            while (starts) {
+                const uint32_t b = (uint32_t)__ffs(starts) - 1u;
+                starts &= starts - 1u;
+                uint32_t wi = t, sh = b, end;
+                for (;;) {   // first clear bit at or after (wi, sh); bits past gvec are clear
+                    const uint32_t z = ~sv[wi] & (0xffffffffu << sh);
+                    if (z) { end = (wi << 5) + (uint32_t)__ffs(z) - 1u; break; }
+                    if (++wi == sv_words) { end = sv_words << 5; break; }
+                    sh = 0;
+                }
+                const uint32_t first = (t << 5) + b;
+                if (end - first >= needv) {
+                    const uint32_t k = atomicAdd(cand, 1u);
+                    if (k < TRIM_MAX_CAND) {
+                        cand[1 + 2 * k] = first;
+                        cand[2 + 2 * k] = end - 1u;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t n_cand = cand[0];
+        if (n_cand == 0) return len;
+        if (n_cand <= TRIM_MAX_CAND) {
+            full_mask = false;
+            for (uint32_t i = tid; i < wn; i += ASM_THREADS) words[i] = 0u;
+            __syncthreads();
+            for (uint32_t k = 0; k < n_cand; k++) {
+                // vectors first-1 .. last+1 hold region samples 8(first-1)-phase .. 8(last+2)-phase-1
+                const uint32_t first = cand[1 + 2 * k], last = cand[2 + 2 * k];
+                const uint32_t back = 1u + (phase ? 1u : 0u);
+                const uint32_t t_lo = first > back ? first - back : 0u;
+                const uint32_t t_hi = min(nb - 1u, last + 1u);
+                for (uint32_t t = t_lo + tid; t <= t_hi; t += ASM_THREADS) bytes[t] = (uint8_t)mask_byte(t);
+            }
+        }
+    }
 
     // 1 bit per sample: |x| <= threshold
-    if (limit >= 0) {
-        // one mask byte (8 samples) per thread step: packed |x| (clamped at 0: abs16(-32768) is
-        // negative, hence silent like 0), minus (limit + 1): the sign bit is the answer
-        uint8_t* bytes = reinterpret_cast<uint8_t*>(words);
-        const uint32_t c2 = (uint32_t)((-(limit + 1)) & 0xffff) * 0x10001u;
-        const uint32_t nb = wn * 4;
-        for (uint32_t t = tid; t < nb; t += ASM_THREADS) {
-            uint32_t byte = 0;
-            if (8 * t < len) {
-                int4 q = grid[t];
-                if (phase) {
-                    int4 hi = make_int4(0, 0, 0, 0);
-                    if (8 * (t + 1) < len + phase) hi = grid[t + 1];
-                    q = shift_pick(q, hi, phase);
-                }
-                uint32_t acc = sign_mask2(__vadd2(absmax0_2((uint32_t)q.x), c2)) & 0x00020001u;
-                acc |= sign_mask2(__vadd2(absmax0_2((uint32_t)q.y), c2)) & 0x00080004u;
-                acc |= sign_mask2(__vadd2(absmax0_2((uint32_t)q.z), c2)) & 0x00200010u;
-                acc |= sign_mask2(__vadd2(absmax0_2((uint32_t)q.w), c2)) & 0x00800040u;
-                byte = (acc | (acc >> 16)) & 0xffu;
-                if (8 * t + 8 > len) byte &= (1u << (len - 8 * t)) - 1u;
+    if (full_mask) {
+        if (limit >= 0) {
+            for (uint32_t t = tid; t < nb; t += ASM_THREADS) bytes[t] = (uint8_t)mask_byte(t);
+        } else {
+            for (uint32_t wd = warp; wd < wn; wd += ASM_THREADS / 32) {
+                uint32_t i = (wd << 5) + lane;
+                bool sil = (i < len) && (abs16(reg[i]) <= limit);
+                uint32_t m = __ballot_sync(0xffffffffu, sil);
+                if (lane == 0) words[wd] = m;
             }
-            bytes[t] = (uint8_t)byte;
-        }
-    } else {
-        for (uint32_t wd = warp; wd < wn; wd += ASM_THREADS / 32) {
-            uint32_t i = (wd << 5) + lane;
-            bool sil = (i < len) && (abs16(reg[i]) <= limit);
-            uint32_t m = __ballot_sync(0xffffffffu, sil);
-            if (lane == 0) words[wd] = m;
         }
     }
     __syncthreads();

@@ -226,6 +226,11 @@ __device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t big, 
     // in-place compaction: destinations never pass their sources, so chunks can
     // be processed in order with one barrier between a chunk's reads and writes
     for (uint32_t c0 = 0; c0 < len; c0 += ASM_THREADS * 8) {
+        {
+            // nothing dropped before the end of this chunk: every sample of it already is where it belongs
+            const uint32_t e = c0 + ASM_THREADS * 8;
+            if (e < len && woff[e >> 5] == e) continue;   // (e is a multiple of 32: woff is the kept count before it)
+        }
         uint32_t i0 = c0 + (uint32_t)tid * 8;
         __align__(16) int16_t v[8];
         uint32_t km = 0, d0 = 0;

@@ -90,6 +90,7 @@ __device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t big, 
         }
         if (tid == 0) cand[0] = 0;
         __syncthreads();
+        int pushed = 0;
         for (uint32_t t = tid; t < sv_words; t += ASM_THREADS) {
             const uint32_t w = sv[t];
             uint32_t starts = w & ~((w << 1) | (t ? sv[t - 1] >> 31 : 0u));   // set bits whose predecessor is clear
@@ -105,6 +106,7 @@ __device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t big, 
                 }
                 const uint32_t first = (t << 5) + b;
                 if (end - first >= needv) {
+                    pushed = 1;
                     const uint32_t k = atomicAdd(cand, 1u);
                     if (k < TRIM_MAX_CAND) {
                         cand[1 + 2 * k] = first;
@@ -113,9 +115,10 @@ __device__ uint32_t trim_region(const Smem& sm, const AsmArgs& A, uint32_t big, 
                 }
             }
         }
-        __syncthreads();
+        // the decision to leave comes out of the barrier itself: a thread that returns goes on to reuse
+        // the scratch, so nobody may still have to read the count from it
+        if (!__syncthreads_or(pushed)) return len;
         const uint32_t n_cand = cand[0];
-        if (n_cand == 0) return len;
         if (n_cand <= TRIM_MAX_CAND) {
             full_mask = false;
             for (uint32_t i = tid; i < wn; i += ASM_THREADS) words[i] = 0u;

@@ -379,3 +379,24 @@ def test_target_rms_variants_share_a_context(H, synth_small, oracle_small, front
         for u, got in enumerate(rp.utterances()):
             want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))
             _assert_same(got, want, f"target_rms {prm.target_rms} utt {u}")
+
+
+def test_many_runs_of_one_plan_are_identical(H, gpu):
+    """A race between CTAs or between the phases of one CTA shows up as a run that differs from the
+    others (or as a device fault), rarely: 40 runs of a 512-utterance resident plan must all produce
+    the same counts and the same PCM (compared through a 64-bit sum and a strided sample)."""
+    db = H.synthetic_db()
+    fr = H.front.Front(db, H.shipped_config(), H.NORM_CSV)
+    prm = fr.params()
+    g = gpu.GpuSynth(db, 0)
+    plan = fr.plan(H.corpus.batch(512, seed=777, target_chars=200))
+    rp = g.create_plan(plan, prm)
+    first = None
+    for k in range(40):
+        rp.run()
+        cnt = rp.counts().astype(np.int64)
+        pcm = rp.read_pcm(0, rp.out_samples)
+        sig = (int(cnt.sum()), int(pcm.astype(np.int64).sum()), pcm[::4099].tobytes())
+        if first is None:
+            first = sig
+        assert sig == first, f"run {k} differs from run 0"

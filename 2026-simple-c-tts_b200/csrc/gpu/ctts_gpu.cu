@@ -81,8 +81,10 @@ struct ctts_gpu_ctx {
     char* h_arena = nullptr;         // pinned staging for the plan upload
     size_t h_arena_cap = 0;
     cudaStream_t copy_stream = nullptr;
-    cudaStream_t aux_stream = nullptr;   // second compute stream: chunks with WSOLA alternate between the two
-    cudaEvent_t fence[2] = {nullptr, nullptr};
+    static constexpr int kAux = 4;
+    cudaStream_t aux_stream[kAux] = {};   // the WSOLA kernels of consecutive chunks rotate over these
+    cudaEvent_t fence[kAux] = {};
+    std::vector<cudaEvent_t> asm_events;               // per chunk: its assembly kernel is done
     std::vector<cudaEvent_t> events;
     char err[512] = {0};
 };
@@ -419,7 +421,8 @@ void ctts_gpu_free(ctts_gpu_ctx* ctx) {
     if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    for (cudaStream_t a : ctx->aux_stream) if (a) cudaStreamDestroy(a);
+    for (cudaEvent_t e : ctx->asm_events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->fence) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -675,10 +678,12 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
 
     // ---- chunks: contiguous utterance ranges.  Without WSOLA a chunk is about chunk_samples
     // output samples.  The WSOLA search is one CTA per utterance walking a long dependent chain
-    // (10 resident CTAs per SM); consecutive chunks run on two streams, so a chunk holds about half
-    // a wave of stretched utterances and the tail of one chunk's chains overlaps the next chunk
-    // (measured on the 4096-utterance mixed batch: 6 chunks 171 ms, 3 chunks 173 ms, 11 chunks 219 ms,
-    // one launch and one copy 238 ms).
+    // (10 resident CTAs per SM); the stretch kernels of consecutive chunks run on four streams, so a
+    // chunk holds about a third of a wave of stretched utterances and the tail of one chunk's chains
+    // overlaps the chunks behind it (measured on the 4096-utterance mixed batch, e2e: 8 chunks on 4
+    // streams 163 ms, 6 chunks on 2 streams 166 ms, 3 chunks 173 ms, 11 chunks on 2 streams 206 ms, one
+    // stream 212 ms, one launch and one copy 238 ms; the kernels alone take 110 ms, the copies 91 ms,
+    // and what is left is the last chains running on a nearly idle GPU).
     uint32_t n_stretched = 0;
     if (sc.any_stretch)
         for (uint32_t u = 0; u < n; u++) {
@@ -690,7 +695,7 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
         ch.utt_end = n;
         p->chunks.push_back(ch);
     } else if (n_stretched) {
-        uint32_t wave = (uint32_t)ctx->sm_count * ctts::WS_CTAS_PER_SM / 2;
+        uint32_t wave = (uint32_t)ctx->sm_count * ctts::WS_CTAS_PER_SM / 3;
         if (const char* e = getenv("CTTS_GPU_STRETCH_WAVE")) wave = (uint32_t)std::max(1, atoi(e));
         const uint32_t k = std::max<uint32_t>(1, (n_stretched + wave / 2) / wave);
         const uint32_t share = (n_stretched + k - 1) / k;
@@ -1225,7 +1230,7 @@ int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
     auto cu_fail = [&](cudaError_t e, const char* what) {
         cudaStreamSynchronize(ctx->stream);
         if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-        if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+        for (cudaStream_t a : ctx->aux_stream) if (a) cudaStreamSynchronize(a);
         ctts_gpu_plan_destroy(p);
         return fail(ctx, CTTS_GPU_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     };
@@ -1247,33 +1252,46 @@ int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
         cudaEventRecord(ev, s_);
         tev.push_back(ev);
     };
-    // Chunks with WSOLA alternate between two compute streams: the search kernel is a wave of long
-    // dependent chains whose tail leaves SMs idle, and the other stream's chunk fills them.
+    // Batches with WSOLA: every chunk is assembled on the context stream, back to back (cheap, and the
+    // search kernels then never hold up an assembly launch); the search + overlap-add of consecutive
+    // chunks alternate between two auxiliary streams, each waiting only for its own chunk's assembly.
+    // The search is a wave of long dependent chains whose tail leaves SMs idle: with two chunks of
+    // half a wave in flight the next chunk fills them.
     const bool two = p->n_stretch && nc > 1 && !getenv("CTTS_GPU_ONE_STREAM");
-    if (two && !ctx->aux_stream) {
-        cudaError_t e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
-        for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->fence[i], cudaEventDisableTiming);
-        if (e != cudaSuccess) return cu_fail(e, "aux stream");
+    int n_aux = ctts_gpu_ctx::kAux;
+    if (const char* e = getenv("CTTS_GPU_AUX_STREAMS")) n_aux = std::max(1, std::min((int)ctts_gpu_ctx::kAux, atoi(e)));
+    if (two && !ctx->aux_stream[0]) {
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < ctts_gpu_ctx::kAux && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->aux_stream[i], cudaStreamNonBlocking);
+        for (int i = 0; i < ctts_gpu_ctx::kAux && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->fence[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) return cu_fail(e, "aux streams");
+    }
+    while (two && ctx->asm_events.size() < nc) {
+        cudaEvent_t ev;
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return cu_fail(e, "event");
+        ctx->asm_events.push_back(ev);
     }
     if (p->n_utts) {
         rc = begin_run(ctx, p);
-        if (two) {   // the aux stream starts after the memsets / uploads enqueued so far
-            cudaError_t e = cudaEventRecord(ctx->fence[0], ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux_stream, ctx->fence[0], 0);
-            if (e != cudaSuccess) return cu_fail(e, "fence");
-        }
         mark(ctx->stream);
         for (uint32_t c = 0; !rc && c < nc; c++) {
-            // compile + upload chunk c on the host while the device assembles chunk c-1
-            cudaStream_t cs = (two && (c & 1)) ? ctx->aux_stream : ctx->stream;
-            rc = build_chunk(ctx, p, c, cs);
-            if (!rc) rc = launch_chunk(ctx, p, c, d_out, cs);
-            mark(cs);
+            // compile + upload chunk c on the host while the device works on the chunks before it
+            const PlanChunk& ch = p->chunks[c];
+            rc = build_chunk(ctx, p, c, ctx->stream);
+            if (!rc) rc = launch_chunk(ctx, p, c, d_out, ctx->stream);
+            mark(ctx->stream);
+            cudaStream_t cs = ctx->stream;   // the stream the chunk's last kernel runs on
+            if (!rc && two && ch.st_count) {
+                cs = ctx->aux_stream[c % (uint32_t)n_aux];
+                cudaError_t e = cudaEventRecord(ctx->asm_events[c], ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ctx->asm_events[c], 0);
+                if (e != cudaSuccess) return cu_fail(e, "fence");
+            }
             if (!rc) rc = launch_stretch(ctx, p, c, d_out, cs);
             mark(cs);
             if (rc) break;
-            // the chunk's slots are one contiguous span; copy it while the next chunk is assembled
-            const PlanChunk& ch = p->chunks[c];
+            // the chunk's slots are one contiguous span; copy it while the other chunks are worked on
             const uint64_t lo = p->offsets[ch.utt_begin], hi = p->offsets[ch.utt_end];
             cudaError_t e = cudaEventRecord(ctx->events[c], cs);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->events[c], 0);
@@ -1282,10 +1300,12 @@ int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
             if (e != cudaSuccess) return cu_fail(e, "D2H");
             mark(ctx->copy_stream);
         }
-        if (two) {   // everything the aux stream did is ordered before what follows on the context stream
-            cudaError_t e = cudaEventRecord(ctx->fence[1], ctx->aux_stream);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->fence[1], 0);
-            if (e != cudaSuccess) return cu_fail(e, "fence");
+        if (two) {   // everything the aux streams did is ordered before what follows on the context stream
+            for (int i = 0; i < n_aux; i++) {
+                cudaError_t e = cudaEventRecord(ctx->fence[i], ctx->aux_stream[i]);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->fence[i], 0);
+                if (e != cudaSuccess) return cu_fail(e, "fence");
+            }
         }
     }
     auto t2 = now();

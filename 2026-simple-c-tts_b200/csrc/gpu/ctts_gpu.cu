@@ -760,7 +760,7 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
                 st.pos_off = (uint32_t)pos_total;
                 st.max_frames = (uint32_t)(pre[u] > 512 ? (pre[u] - 512) / 128 + 1 : 1);
                 const uint64_t used_max = (uint64_t)st.max_frames * hop + 512;
-                const uint32_t per_block = ctts::OLA_THREADS * ctts::OLA_SPT;
+                const uint32_t per_block = ctts::ola_block_span(hop);
                 for (uint64_t f = 0; f < used_max; f += per_block) {
                     ola_task.push_back((uint32_t)stasks.size());
                     ola_first.push_back((uint32_t)f);

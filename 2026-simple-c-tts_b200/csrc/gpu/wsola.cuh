@@ -471,46 +471,106 @@ __global__ void __launch_bounds__(WS_THREADS, WS_CTAS_PER_SM) wsola_search_kerne
     }
 }
 
+// Output samples one OLA block covers for synthesis hop `hop` (host and device must agree).
+// 64 <= hop <= OLA_THREADS (every hop the C-ABI can produce: hop = (size_t)(128 / speed), speed in
+// [0.5, 2]): OLA_THREADS / hop row groups of OLA_SPT rows of hop samples; otherwise plain tiles.
+__host__ __device__ inline uint32_t ola_block_span(uint32_t hop) {
+    return hop >= 64 && hop <= (uint32_t)OLA_THREADS ? ((uint32_t)OLA_THREADS / hop) * (uint32_t)OLA_SPT * hop
+                                                     : (uint32_t)OLA_THREADS * (uint32_t)OLA_SPT;
+}
+
+// Overlap-add in gather form (ctts.c:3563-3606).  Output sample j = row * hop + c (row = j / hop)
+// receives frame k = row - q at window index i = q * hop + c, for every q with i < 512 and
+// 0 <= k < frames.  A thread owns one residue c and OLA_SPT consecutive rows: the window value
+// w[q * hop + c] is the same for all of its outputs, and walking q downwards adds the frames of
+// every output in ascending frame order, which is the order the reference accumulates the float
+// norm in (the int16 accumulator wraps, ctts.c:3577: it is the 32-bit sum mod 2^16).
 __global__ void __launch_bounds__(OLA_THREADS) wsola_ola_kernel(const WsolaArgs A) {
     __shared__ int s_last[OLA_THREADS / 32];
     __shared__ float win[WS_FRAME];
+    __shared__ uint32_t sfp[(OLA_THREADS / 64) * OLA_SPT + 8];
     const int tid = threadIdx.x;
     for (int i = tid; i < WS_FRAME; i += OLA_THREADS) win[i] = __ldg(A.hann512 + i);
     const uint32_t ti = A.ola_block_task[blockIdx.x];
     const StretchTask task = A.tasks[ti];
     const uint32_t frames = A.n_frames[ti];
-    __syncthreads();
-    if (frames == 0) return;
+    if (frames == 0) return;   // CTA-uniform
     const uint32_t hop = task.hop;
     const uint32_t used = (frames - 1) * hop + WS_FRAME;
+    const uint32_t lim = used < task.out_cap ? used : task.out_cap;
     const int16_t* in = A.pre + task.pre_off;
     const uint32_t* fpos = A.frame_pos + task.pos_off;
     int16_t* out = A.out + task.out_off;
     const uint32_t first = A.ola_block_first[blockIdx.x];
     int last_nz = -1;
-    // j / hop by multiplication: exact for j < 2^24 and hop <= 256 (hop = (size_t)(128 / speed), speed >= 0.5)
-    const bool mulhi_ok = used < (1u << 24) && hop <= 256;
-    const uint32_t magic = (uint32_t)((0x100000000ull + hop - 1) / hop);
-#pragma unroll
-    for (int r = 0; r < OLA_SPT; r++) {
-        uint32_t j = first + (uint32_t)r * OLA_THREADS + (uint32_t)tid;
-        if (j >= used || j >= task.out_cap) continue;
-        uint32_t k_hi = mulhi_ok ? __umulhi(j, magic) : j / hop;
-        if (k_hi > frames - 1) k_hi = frames - 1;
-        uint32_t k_lo = j < WS_FRAME ? 0u : (mulhi_ok ? __umulhi(j - WS_FRAME, magic) : (j - WS_FRAME) / hop) + 1u;
-        int16_t acc = 0;
-        float norm = 0.0f;
-        for (uint32_t k = k_lo; k <= k_hi; k++) {
-            uint32_t i = j - k * hop;
-            float wv = win[i];
-            float v = (float)in[__ldg(fpos + k) + i] * wv;
-            acc = (int16_t)(acc + f2s(v));
-            norm += wv;
+    if (hop >= 64 && hop <= (uint32_t)OLA_THREADS) {
+        const uint32_t groups = (uint32_t)OLA_THREADS / hop;
+        const uint32_t row0 = first / hop;   // exact: first is a multiple of the block span
+        // positions of frames row0 - 7 .. row0 + groups * OLA_SPT - 1 (0 where there is no such frame)
+        for (uint32_t i = tid; i < groups * OLA_SPT + 7; i += OLA_THREADS) {
+            const long long k = (long long)row0 - 7 + i;
+            sfp[i] = (k >= 0 && k < (long long)frames) ? __ldg(fpos + k) : 0u;
         }
-        int16_t y = acc;
-        if (norm > 0.01f) y = f2s(clamp16f((float)acc / norm));
-        out[j] = y;
-        if (y != 0) last_nz = (int)j;
+        __syncthreads();
+        const uint32_t g = (uint32_t)tid / hop, c = (uint32_t)tid - g * hop;
+        if (g < groups && first < lim) {
+            const uint32_t rowbase = row0 + g * OLA_SPT;
+            const uint32_t kmax = frames - 1;
+            int acc[OLA_SPT];
+            float nrm[OLA_SPT];
+#pragma unroll
+            for (int r = 0; r < OLA_SPT; r++) {
+                acc[r] = 0;
+                nrm[r] = 0.0f;
+            }
+            for (int q = (int)((WS_FRAME - 1) / hop); q >= 0; q--) {   // CTA-uniform trip count, <= 8
+                const uint32_t i = (uint32_t)q * hop + c;
+                if (i < (uint32_t)WS_FRAME) {
+                    const float wv = win[i];
+                    const uint32_t* fp = sfp + (g * OLA_SPT + 7u - (uint32_t)q);   // frame rowbase - q
+#pragma unroll
+                    for (int r = 0; r < OLA_SPT; r++) {
+                        const uint32_t k = rowbase + (uint32_t)r - (uint32_t)q;    // wraps below frame 0
+                        if (k <= kmax) {
+                            acc[r] += (int)f2s((float)in[fp[r] + i] * wv);
+                            nrm[r] += wv;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < OLA_SPT; r++) {
+                const uint32_t j = (rowbase + (uint32_t)r) * hop + c;
+                if (j < lim) {
+                    const int16_t a = (int16_t)acc[r];
+                    int16_t y = a;
+                    if (nrm[r] > 0.01f) y = f2s(clamp16f((float)a / nrm[r]));
+                    out[j] = y;
+                    if (y != 0) last_nz = (int)j;
+                }
+            }
+        }
+    } else {
+        __syncthreads();
+        for (int r = 0; r < OLA_SPT; r++) {
+            const uint32_t j = first + (uint32_t)r * OLA_THREADS + (uint32_t)tid;
+            if (j >= lim) continue;
+            uint32_t k_hi = j / hop;
+            if (k_hi > frames - 1) k_hi = frames - 1;
+            const uint32_t k_lo = j < WS_FRAME ? 0u : (j - WS_FRAME) / hop + 1u;
+            int16_t acc = 0;
+            float norm = 0.0f;
+            for (uint32_t k = k_lo; k <= k_hi; k++) {
+                const uint32_t i = j - k * hop;
+                const float wv = win[i];
+                acc = (int16_t)(acc + f2s((float)in[__ldg(fpos + k) + i] * wv));
+                norm += wv;
+            }
+            int16_t y = acc;
+            if (norm > 0.01f) y = f2s(clamp16f((float)acc / norm));
+            out[j] = y;
+            if (y != 0) last_nz = (int)j;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

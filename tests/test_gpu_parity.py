@@ -400,3 +400,24 @@ def test_many_runs_of_one_plan_are_identical(H, gpu):
         if first is None:
             first = sig
         assert sig == first, f"run {k} differs from run 0"
+
+
+def test_many_calls_of_the_drop_in_path_are_identical(H, gpu, monkeypatch):
+    """The same for ctts_gpu_synth_batch on a batch that mixes speeds: chunks on several streams,
+    per-chunk copies, arenas reused from call to call.  12 calls must return identical PCM."""
+    monkeypatch.setenv("CTTS_GPU_STRETCH_WAVE", "24")   # several chunks in flight
+    db = H.synthetic_db()
+    fr = H.front.Front(db, H.shipped_config(), H.NORM_CSV)
+    prm = fr.params()
+    g = gpu.GpuSynth(db, 0)
+    texts = H.corpus.batch(160, seed=909, target_chars=160)
+    speeds = H.corpus.mixed_speeds(160, seed=11)
+    speeds[::5] = 1.0
+    plan = fr.plan(texts, speeds)
+    first = None
+    for k in range(12):
+        outs = g.synth_list(plan, prm)
+        sig = [(len(o), int(o.astype(np.int64).sum()), o[::997].tobytes()) for o in outs]
+        if first is None:
+            first = sig
+        assert sig == first, f"call {k} differs from call 0"

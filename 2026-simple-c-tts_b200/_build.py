@@ -4,6 +4,7 @@ libctts_front.so  plain C host front end (gcc)
 libctts_gpu.so    C-ABI + hand-written sm_100a kernels (nvcc, -fmad=false: the
                   reference is built without FMA contraction and discrete
                   decisions flip on 1-ulp differences)
+ctts_b200         the `ctts synth` command line in plain C over the two libraries (gcc)
 """
 from __future__ import annotations
 
@@ -18,6 +19,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 
 FRONT_SO = os.path.join(PKG_DIR, "libctts_front.so")
 GPU_SO = os.path.join(PKG_DIR, "libctts_gpu.so")
+CLI_BIN = os.path.join(PKG_DIR, "ctts_b200")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -76,3 +78,17 @@ def build_gpu(force: bool = False, verbose: bool = False) -> str:
         ["-I", INCLUDE, "-I", d, "-o", GPU_SO] + cus + objs + ["-lcudart"]
     subprocess.run(cmd, check=True)
     return GPU_SO
+
+
+def build_cli(force: bool = False) -> str:
+    """The plain-C drop-in command line (csrc/cli/ctts_b200.c) linked against the two libraries."""
+    src = os.path.join(CSRC, "cli", "ctts_b200.c")
+    deps = [src, FRONT_SO, GPU_SO] + _headers()
+    if not force and _newer(CLI_BIN, deps):
+        return CLI_BIN
+    cc = shutil.which("gcc") or "cc"
+    cmd = [cc, "-O2", "-std=gnu99", "-Wall", "-Wextra", "-I", INCLUDE, "-o", CLI_BIN, src,
+           "-L", PKG_DIR, "-lctts_front", "-lctts_gpu", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link," + PKG_DIR,
+           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lm"]
+    subprocess.run(cmd, check=True)
+    return CLI_BIN

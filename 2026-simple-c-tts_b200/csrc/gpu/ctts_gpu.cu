@@ -436,6 +436,16 @@ int ctts_gpu_set_stream(ctts_gpu_ctx* ctx, void* cuda_stream) {
 
 const char* ctts_gpu_last_error(const ctts_gpu_ctx* ctx) { return ctx ? ctx->err : "no context"; }
 
+void* ctts_gpu_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void ctts_gpu_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int ctts_gpu_plan_bounds(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, uint64_t* out_bound) {
     if (!ctx || !plan || !out_bound) return CTTS_GPU_ERR_INVALID_ARG;
     if (plan->n_utts && (!plan->utt_op_begin || !plan->speed)) return CTTS_GPU_ERR_INVALID_ARG;

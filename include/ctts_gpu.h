@@ -111,6 +111,13 @@ typedef struct ctts_gpu_run_info {
 } ctts_gpu_run_info;
 int ctts_gpu_plan_info(const ctts_gpu_plan* plan, ctts_gpu_run_info* info);
 
+/* Page-locked host memory for the caller's PCM buffer (the device->host copies of
+ * ctts_gpu_synth_batch run at PCIe speed into it; pageable memory works too, slower).  The
+ * reference hands out malloc'ed sample buffers (ctts_synthesize / ctts_free_samples, ctts.h:212-224);
+ * these are the batch equivalents for a plain-C host that does not link the CUDA runtime itself. */
+void* ctts_gpu_host_alloc(size_t bytes);
+void ctts_gpu_host_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

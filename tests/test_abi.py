@@ -53,3 +53,20 @@ def test_product_does_not_import_the_oracle(H):
                 src = open(os.path.join(root, f), errors="replace").read()
                 for needle in ("libctts_oracle", "libctts_ref", "ctts_oracle", "oracle/", "ctts_ref_bench"):
                     assert needle not in src, (f, needle)
+
+
+def test_c_command_line_has_no_cpu_fallback(H, small_db, tmp_path):
+    """The plain-C `ctts synth` driver (csrc/cli/ctts_b200.c) is built by build(); without a CUDA device
+    it must fail like the library does instead of synthesising anything on the CPU."""
+    import subprocess
+    import torch
+    b = H.importlib.import_module("2026-simple-c-tts_b200._build")
+    exe = b.build_cli()
+    assert os.path.exists(exe)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "synth-batch" in r.stderr
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    (tmp_path / "voice.db").write_bytes(small_db)
+    r = subprocess.run([exe, "synth", "voice.db", "olá mundo", "o.wav", "1.0"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr and not (tmp_path / "o.wav").exists()

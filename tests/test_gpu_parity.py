@@ -421,3 +421,29 @@ def test_many_calls_of_the_drop_in_path_are_identical(H, gpu, monkeypatch):
         if first is None:
             first = sig
         assert sig == first, f"call {k} differs from call 0"
+
+
+def test_c_command_line_writes_the_reference_wav(H, small_db, golden, tmp_path):
+    """ctts_b200 (plain C over the two C-ABI libraries, the binding a CTTS maintainer would link):
+    `synth` at 1.0 and 1.5 must write byte for byte the WAV the compiled reference writes (44-byte header
+    of ctts_write_wav, ctts.c:809, + its PCM: BASELINE configs[0] and [1]); `synth-batch` the same files."""
+    import shutil
+    import subprocess
+    b = H.importlib.import_module("2026-simple-c-tts_b200._build")
+    exe = b.build_cli()
+    shutil.copy(H.SHIPPED_YAML, tmp_path / "config.yaml")
+    shutil.copy(H.NORM_CSV, tmp_path / "normalization.csv")
+    (tmp_path / "voice.db").write_bytes(small_db)
+    for k, speed in enumerate(("1.0", "1.5")):
+        r = subprocess.run([exe, "synth", "voice.db", "olá mundo", f"o{k}.wav", speed], cwd=tmp_path, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        raw = (tmp_path / f"o{k}.wav").read_bytes()
+        want = golden[f"e2e_pcm_{k}"]
+        assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt " and raw[36:40] == b"data" and len(raw) == 44 + 2 * len(want)
+        assert np.array_equal(np.frombuffer(raw[44:], dtype="<i2"), want)
+        assert f"Synthesized {len(want)} samples" in r.stdout and "missing: 0" in r.stdout
+    (tmp_path / "t.tsv").write_text("1.0\tolá mundo\n1.5\tolá mundo\n", encoding="utf-8")
+    r = subprocess.run([exe, "synth-batch", "voice.db", "t.tsv", "out"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "out" / "000000.wav").read_bytes() == (tmp_path / "o0.wav").read_bytes()
+    assert (tmp_path / "out" / "000001.wav").read_bytes() == (tmp_path / "o1.wav").read_bytes()

@@ -82,9 +82,12 @@ static int write_wav(const char* path, const int16_t* samples, size_t count) {
 }
 
 /* N texts -> N PCM spans of one pinned buffer: *pcm (release with ctts_gpu_host_free), off[u]
- * (n + 1 entries, malloc'ed) and cnt[u] (malloc'ed); stats may be NULL (2n: found, missing). */
+ * (n + 1 entries, malloc'ed) and cnt[u] (malloc'ed); stats may be NULL (2n: found, missing).
+ * on_chunk (may be NULL) is called as soon as a range of utterances is in host memory; it finds
+ * the three arrays through *pcm, *off, *cnt, which are set before the device starts. */
 static int ctts_b200_synthesize_batch(engine* e, const char* const* texts, const float* speeds, uint32_t n,
-                                      int16_t** pcm, uint64_t** off, uint32_t** cnt, uint32_t* stats) {
+                                      int16_t** pcm, uint64_t** off, uint32_t** cnt, uint32_t* stats,
+                                      ctts_gpu_chunk_fn on_chunk, void* user) {
     ctts_batch_plan plan;
     ctts_assembly_params prm;
     int rc = ctts_front_plan_batch(e->front, texts, speeds, n, &plan, stats);
@@ -102,7 +105,7 @@ static int ctts_b200_synthesize_batch(engine* e, const char* const* texts, const
         *pcm = ctts_gpu_host_alloc(sizeof(int16_t) * ((*off)[n] ? (*off)[n] : 8));
         if (!*pcm) rc = CTTS_GPU_ERR_OUT_OF_MEMORY;
     }
-    if (!rc) rc = ctts_gpu_synth_batch(e->gpu, &plan, &prm, *pcm, *off, *cnt);
+    if (!rc) rc = ctts_gpu_synth_batch_stream(e->gpu, &plan, &prm, *pcm, *off, *cnt, on_chunk, user);
     if (rc) {
         fprintf(stderr, "synthesis failed: %d %s\n", rc, ctts_gpu_last_error(e->gpu));
         ctts_gpu_host_free(*pcm);
@@ -135,7 +138,7 @@ static int cmd_synth(int argc, char** argv) {
     int16_t* pcm;
     uint64_t* off;
     uint32_t *cnt, stats[2] = {0, 0};
-    if (ctts_b200_synthesize_batch(&e, texts, &speed, 1, &pcm, &off, &cnt, stats)) { engine_close(&e); return 1; }
+    if (ctts_b200_synthesize_batch(&e, texts, &speed, 1, &pcm, &off, &cnt, stats, NULL, NULL)) { engine_close(&e); return 1; }
     printf("Synthesized %u samples (%.2f seconds)\n", cnt[0], (float)cnt[0] / SAMPLE_RATE);
     printf("Units found: %u, missing: %u\n", stats[0], stats[1]);
     int rc = write_wav(argv[4], pcm + off[0], cnt[0]);
@@ -146,6 +149,27 @@ static int cmd_synth(int argc, char** argv) {
     free(cnt);
     engine_close(&e);
     return rc ? 1 : 0;
+}
+
+/* synth-batch writes every WAV file as soon as its utterance has arrived (the device is still
+ * working on later ones): state shared with the chunk callback */
+typedef struct {
+    const char* dir;
+    int16_t** pcm;
+    uint64_t** off;
+    uint32_t** cnt;
+    double seconds;
+    int rc;
+} wav_sink;
+
+static void write_chunk(void* user, uint32_t u0, uint32_t u1) {
+    wav_sink* w = user;
+    for (uint32_t u = u0; u < u1 && !w->rc; u++) {
+        char path[4096];
+        snprintf(path, sizeof path, "%s/%06u.wav", w->dir, u);
+        w->rc = write_wav(path, *w->pcm + (*w->off)[u], (*w->cnt)[u]);
+        w->seconds += (double)(*w->cnt)[u] / SAMPLE_RATE;
+    }
 }
 
 static int cmd_synth_batch(int argc, char** argv) {
@@ -188,16 +212,16 @@ static int cmd_synth_batch(int argc, char** argv) {
     int16_t* pcm;
     uint64_t* off;
     uint32_t* cnt;
-    int rc = ctts_b200_synthesize_batch(&e, (const char* const*)texts, speeds, n, &pcm, &off, &cnt, NULL);
-    double seconds = 0;
-    for (uint32_t u = 0; u < n && !rc; u++) {
-        char path[4096];
-        snprintf(path, sizeof path, "%s/%06u.wav", argv[4], u);
-        rc = write_wav(path, pcm + off[u], cnt[u]);
-        seconds += (double)cnt[u] / SAMPLE_RATE;
+    wav_sink sink = {argv[4], &pcm, &off, &cnt, 0.0, 0};
+    int rc = ctts_b200_synthesize_batch(&e, (const char* const*)texts, speeds, n, &pcm, &off, &cnt, NULL, write_chunk, &sink);
+    if (!rc) {
+        rc = sink.rc;
+        if (rc) fprintf(stderr, "Failed to write WAV files into %s\n", argv[4]);
+        else printf("Synthesized %u utterances (%.1f seconds of audio) into %s\n", n, sink.seconds, argv[4]);
+        ctts_gpu_host_free(pcm);
+        free(off);
+        free(cnt);
     }
-    if (!rc) printf("Synthesized %u utterances (%.1f seconds of audio) into %s\n", n, seconds, argv[4]);
-    if (!rc) { ctts_gpu_host_free(pcm); free(off); free(cnt); }
     for (uint32_t u = 0; u < n; u++) free(texts[u]);
     free(texts);
     free(speeds);

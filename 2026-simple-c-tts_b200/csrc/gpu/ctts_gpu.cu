@@ -85,6 +85,9 @@ struct ctts_gpu_ctx {
     cudaStream_t aux_stream[kAux] = {};   // the WSOLA kernels of consecutive chunks rotate over these
     cudaEvent_t fence[kAux] = {};
     std::vector<cudaEvent_t> asm_events;               // per chunk: its assembly kernel is done
+    std::vector<cudaEvent_t> copied_events;            // per chunk (streaming): PCM, counts and flags are on the host
+    uint32_t* h_stream = nullptr;                      // pinned (streaming): counts [n], then device error flags [n]
+    size_t h_stream_cap = 0;
     std::vector<cudaEvent_t> events;
     char err[512] = {0};
 };
@@ -423,6 +426,8 @@ void ctts_gpu_free(ctts_gpu_ctx* ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (cudaStream_t a : ctx->aux_stream) if (a) cudaStreamDestroy(a);
     for (cudaEvent_t e : ctx->asm_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->copied_events) cudaEventDestroy(e);
+    if (ctx->h_stream) cudaFreeHost(ctx->h_stream);
     for (cudaEvent_t e : ctx->fence) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -1210,6 +1215,12 @@ int ctts_gpu_plan_read_pre(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t u, int1
 
 int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_assembly_params* params,
                          int16_t* pcm_out, const uint64_t* out_offsets, uint32_t* out_counts) {
+    return ctts_gpu_synth_batch_stream(ctx, plan, params, pcm_out, out_offsets, out_counts, nullptr, nullptr);
+}
+
+int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_assembly_params* params,
+                                int16_t* pcm_out, const uint64_t* out_offsets, uint32_t* out_counts,
+                                ctts_gpu_chunk_fn on_chunk, void* user) {
     if (!ctx || !plan || !params || !pcm_out || !out_offsets || !out_counts) return CTTS_GPU_ERR_INVALID_ARG;
     const bool trace = getenv("CTTS_GPU_TRACE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
@@ -1254,6 +1265,30 @@ int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
         if (e != cudaSuccess) return cu_fail(e, "event");
         ctx->events.push_back(ev);
     }
+    while (on_chunk && ctx->copied_events.size() < nc) {
+        cudaEvent_t ev;
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return cu_fail(e, "event");
+        ctx->copied_events.push_back(ev);
+    }
+    if (on_chunk && 2 * (size_t)p->n_utts > ctx->h_stream_cap) {      // pinned: a pageable target would make the copies synchronous
+        if (ctx->h_stream) cudaFreeHost(ctx->h_stream);
+        ctx->h_stream = nullptr;
+        ctx->h_stream_cap = 0;
+        const size_t cap = 2 * (size_t)p->n_utts + 1024;
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_stream), cap * 4, cudaHostAllocDefault);
+        if (e != cudaSuccess) return cu_fail(e, "pinned counts");
+        ctx->h_stream_cap = cap;
+    }
+    uint32_t* const h_cnt = ctx->h_stream;                            // streaming: counts, then error flags
+    uint32_t* const h_err = ctx->h_stream ? ctx->h_stream + p->n_utts : nullptr;
+    uint32_t delivered = 0;                                           // chunks already handed to on_chunk
+    auto deliver = [&](uint32_t c) {
+        const PlanChunk& dc = p->chunks[c];
+        if (dc.utt_end <= dc.utt_begin) return;
+        memcpy(out_counts + dc.utt_begin, h_cnt + dc.utt_begin, (size_t)(dc.utt_end - dc.utt_begin) * 4);
+        on_chunk(user, dc.utt_begin, dc.utt_end);
+    };
     std::vector<cudaEvent_t> tev;   // trace only: timing events around each chunk's kernels
     auto mark = [&](cudaStream_t s_) {
         if (!trace) return;
@@ -1307,8 +1342,20 @@ int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->events[c], 0);
             if (e == cudaSuccess && hi > lo)
                 e = cudaMemcpyAsync(pcm_out + lo, d_out + lo, (hi - lo) * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+            if (e == cudaSuccess && on_chunk && ch.utt_end > ch.utt_begin) {
+                // streaming: the chunk's counts and error flags follow its PCM; the event marks all three
+                const size_t nb = (size_t)(ch.utt_end - ch.utt_begin) * 4;
+                e = cudaMemcpyAsync(h_cnt + ch.utt_begin, p->d_counts + ch.utt_begin, nb, cudaMemcpyDeviceToHost, ctx->copy_stream);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(h_err + ch.utt_begin, p->d_err + ch.utt_begin, nb, cudaMemcpyDeviceToHost, ctx->copy_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(ctx->copied_events[c], ctx->copy_stream);
+            }
             if (e != cudaSuccess) return cu_fail(e, "D2H");
             mark(ctx->copy_stream);
+            // hand over what has already arrived (never blocks; the rest is handed over below)
+            while (on_chunk && delivered < c + 1 &&
+                   (p->chunks[delivered].utt_end <= p->chunks[delivered].utt_begin || cudaEventQuery(ctx->copied_events[delivered]) == cudaSuccess))
+                deliver(delivered++);
         }
         if (two) {   // everything the aux streams did is ordered before what follows on the context stream
             for (int i = 0; i < n_aux; i++) {
@@ -1319,7 +1366,22 @@ int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const c
         }
     }
     auto t2 = now();
-    if (!rc) rc = ctts_gpu_plan_read_counts(ctx, p, out_counts);   // waits for the kernels
+    if (on_chunk && !rc) {
+        for (; delivered < nc; delivered++) {
+            const PlanChunk& dc = p->chunks[delivered];
+            if (dc.utt_end > dc.utt_begin) {
+                cudaError_t e = cudaEventSynchronize(ctx->copied_events[delivered]);
+                if (e != cudaSuccess) return cu_fail(e, "D2H");
+            }
+            deliver(delivered);
+        }
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return cu_fail(e, "kernels");
+        for (uint32_t u = 0; u < p->n_utts && !rc; u++)
+            if (h_err[u]) rc = fail(ctx, CTTS_GPU_ERR_DEVICE, "utterance %u: device error %u", u, h_err[u]);
+    } else if (!rc) {
+        rc = ctts_gpu_plan_read_counts(ctx, p, out_counts);   // waits for the kernels
+    }
     auto t3 = now();
     cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
     if (e != cudaSuccess && !rc) rc = fail(ctx, CTTS_GPU_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));

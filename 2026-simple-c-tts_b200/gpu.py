@@ -195,6 +195,27 @@ class GpuSynth:
                                                out_offsets.ctypes.data, counts.ctypes.data))
         return pcm_out, out_offsets, counts[:plan.n_utts]
 
+    def synth_batch_stream(self, plan: BatchPlan, params: AssemblyParams, on_chunk, pcm_out: np.ndarray | None = None,
+                           out_offsets: np.ndarray | None = None):
+        """ctts_gpu_synth_batch_stream: on_chunk(pcm, offsets, counts, utt_begin, utt_end) is called, in utterance
+        order, as soon as that range of utterances is in host memory.  Returns (pcm, offsets, counts)."""
+        if out_offsets is None:
+            out_offsets = self.layout(plan)
+        out_offsets = np.ascontiguousarray(out_offsets, dtype=np.uint64)
+        total = int(out_offsets[-1])
+        if pcm_out is None:
+            pcm_out = np.empty(max(total, 1), dtype=np.int16)
+        assert pcm_out.dtype == np.int16 and pcm_out.size >= total and pcm_out.flags["C_CONTIGUOUS"]
+        counts = np.zeros(max(plan.n_utts, 1), dtype=np.uint32)
+        cp = plan.as_c()
+        fn_t = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint32)
+        cb = fn_t(lambda _user, b, e: on_chunk(pcm_out, out_offsets, counts, int(b), int(e)))
+        L = lib()
+        L.ctts_gpu_synth_batch_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, fn_t, C.c_void_p]
+        self._check(L.ctts_gpu_synth_batch_stream(self._h, C.byref(cp), C.byref(params), pcm_out.ctypes.data,
+                                                  out_offsets.ctypes.data, counts.ctypes.data, cb, None))
+        return pcm_out, out_offsets, counts[:plan.n_utts]
+
     def synth_list(self, plan: BatchPlan, params: AssemblyParams) -> list[np.ndarray]:
         pcm, off, cnt = self.synth_batch(plan, params)
         return [pcm[int(off[u]):int(off[u]) + int(cnt[u])].copy() for u in range(plan.n_utts)]

@@ -65,6 +65,18 @@ int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan,
                          const ctts_assembly_params* params, int16_t* pcm_out,
                          const uint64_t* out_offsets, uint32_t* out_counts);
 
+/* The same call, streaming: `on_chunk(user, utt_begin, utt_end)` is invoked on the calling thread, in
+ * utterance order, as soon as the PCM and the counts of utterances [utt_begin, utt_end) are in host
+ * memory -- while the device is still working on later utterances -- so the caller can write WAV files
+ * (ctts_write_wav, ctts.c:809) or hand audio on without waiting for the batch (the output path of a
+ * 65 536-paragraph batch is 87 GB of PCM).  A device-side error for an utterance is
+ * reported by the return value after the last callback.  on_chunk == NULL: ctts_gpu_synth_batch. */
+typedef void (*ctts_gpu_chunk_fn)(void* user, uint32_t utt_begin, uint32_t utt_end);
+int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan,
+                                const ctts_assembly_params* params, int16_t* pcm_out,
+                                const uint64_t* out_offsets, uint32_t* out_counts,
+                                ctts_gpu_chunk_fn on_chunk, void* user);
+
 /* ---- resident-plan path: upload once, run many times, PCM stays in HBM ---- */
 
 /* Uploads the plan, derives the region tasks and output layout

@@ -447,3 +447,30 @@ def test_c_command_line_writes_the_reference_wav(H, small_db, golden, tmp_path):
     assert r.returncode == 0, r.stderr
     assert (tmp_path / "out" / "000000.wav").read_bytes() == (tmp_path / "o0.wav").read_bytes()
     assert (tmp_path / "out" / "000001.wav").read_bytes() == (tmp_path / "o1.wav").read_bytes()
+
+
+def test_streaming_call_hands_over_finished_ranges(H, gpu, small_db, oracle_small, front_small, monkeypatch):
+    """ctts_gpu_synth_batch_stream: the callback sees every utterance exactly once, in order, and what it
+    finds in the host buffer at that moment already is the final PCM (checked against the oracle);
+    plain and stretched utterances, several chunks."""
+    monkeypatch.setenv("CTTS_GPU_CHUNK_SAMPLES", "150000")
+    prm = front_small.params()
+    texts = H.corpus.batch(20, seed=71, target_chars=110) + ["", "olá mundo"]
+    for speeds in ([1.0] * 22, [1.5, 1.0, 0.5, 2.0, 1.0, 0.7] * 3 + [1.3, 1.0, 0.9, 1.0]):
+        monkeypatch.setenv("CTTS_GPU_STRETCH_WAVE", "3")
+        plan = front_small.plan(texts, speeds)
+        g = gpu.GpuSynth(small_db, 0)
+        seen, snap = [], {}
+
+        def on_chunk(pcm, off, cnt, b, e):
+            seen.append((b, e))
+            for u in range(b, e):
+                snap[u] = pcm[int(off[u]):int(off[u]) + int(cnt[u])].copy()
+
+        pcm, off, cnt = g.synth_batch_stream(plan, prm, on_chunk)
+        assert len(seen) > 1 and seen[0][0] == 0 and seen[-1][1] == plan.n_utts
+        assert all(seen[i][1] == seen[i + 1][0] for i in range(len(seen) - 1))
+        for u in range(plan.n_utts):
+            want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))
+            _assert_same(snap[u], want, f"utt {u} at callback time")
+            _assert_same(pcm[int(off[u]):int(off[u]) + int(cnt[u])], want, f"utt {u} at return")

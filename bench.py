@@ -362,6 +362,7 @@ def main() -> int:
             "roofline": {
                 "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(dominant), "peak_source": peak_src,
+                "frac_of_nominal_8000_GBs": achieved / 8000.0,   # the north star quotes ~8 TB/s; SURVEY 8d asks for both
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
                 "kernel_ms_min_max": [float(np.min(step_ms)), float(np.max(step_ms))],
                 "note": "step = one assemble_kernel launch (+4 small memsets)" if args.workload != "mixed"

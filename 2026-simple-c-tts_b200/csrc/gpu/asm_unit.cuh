@@ -265,8 +265,8 @@ __device__ void op_unit(State& s, const Smem& sm, const AsmArgs& A, const ctts_p
             int v = us[i];
             if (remove_dc) v = sub_dc(v, dc);
             const int p = tail[i];
-            const int mix = (int)((float)p * pg + (float)v * ng);
-            tail[i] = (int16_t)max(min(mix, 32767), -32768);
+            // clamp((int32)(prev * fo + next * fi)) (ctts.c:3336-3340): truncation then clamp == saturating convert
+            tail[i] = (int16_t)cvt_sat_s16((float)p * pg + (float)v * ng);
         }
         for (uint32_t i = a + tid; i < hsn; i += ASM_THREADS) {
             int v = us[i];

@@ -1307,7 +1307,12 @@ int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, 
     if (const char* e = getenv("CTTS_GPU_AUX_STREAMS")) n_aux = std::max(1, std::min((int)ctts_gpu_ctx::kAux, atoi(e)));
     if (two && !ctx->aux_stream[0]) {
         cudaError_t e = cudaSuccess;
-        for (int i = 0; i < ctts_gpu_ctx::kAux && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->aux_stream[i], cudaStreamNonBlocking);
+        // highest priority: a search CTA is one link of a long dependent chain, an assembly CTA is not
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (getenv("CTTS_GPU_AUX_DEFAULT_PRIORITY")) prio_hi = 0;
+        for (int i = 0; i < ctts_gpu_ctx::kAux && e == cudaSuccess; i++)
+            e = cudaStreamCreateWithPriority(&ctx->aux_stream[i], cudaStreamNonBlocking, prio_hi);
         for (int i = 0; i < ctts_gpu_ctx::kAux && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->fence[i], cudaEventDisableTiming);
         if (e != cudaSuccess) return cu_fail(e, "aux streams");
     }

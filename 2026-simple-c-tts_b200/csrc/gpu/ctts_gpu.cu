@@ -549,6 +549,7 @@ int norm_pool_for(ctts_gpu_ctx* ctx, float target_rms, ctts_gpu_ctx::NormPool** 
     ctts_gpu_ctx::NormPool* np = new ctts_gpu_ctx::NormPool();
     np->target_rms = target_rms;
     np->pitch_cap = std::max<uint32_t>(1u << 16, 64u * ctx->n_units);
+    if (const char* e = getenv("CTTS_GPU_PITCH_SLOTS")) np->pitch_cap = (uint32_t)std::max(1, atoi(e));   // tests: a table that fills up
     np->pitch_slots.resize(ctx->n_units);
     if (cudaMalloc(reinterpret_cast<void**>(&np->d_pool), std::max<uint64_t>(ctx->pool_samples, 8) * sizeof(int16_t)) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&np->d_meta), std::max<size_t>(ctx->n_units, 1) * sizeof(int4)) != cudaSuccess ||

@@ -237,8 +237,10 @@ def test_forced_hbm_window_and_chunked_batch(H, gpu, small_db, oracle_small, fro
     texts = H.corpus.batch(24, seed=47, target_chars=120) + ["", "a", ". . .", "olá mundo"]
     plan = front_small.plan(texts)
     want = [oracle_small.synth(prm, plan.utt_ops(u), 1.0)[0] for u in range(plan.n_utts)]
+    # (c) a unit-head pitch table with room for 3 entries: every other join estimates both signals itself
     for env in ({"CTTS_GPU_WINDOW": "2048"}, {"CTTS_GPU_CHUNK_SAMPLES": "300000"},
-                {"CTTS_GPU_WINDOW": "4096", "CTTS_GPU_CHUNK_SAMPLES": "100000", "CTTS_GPU_CTAS_PER_SM": "2"}):
+                {"CTTS_GPU_WINDOW": "4096", "CTTS_GPU_CHUNK_SAMPLES": "100000", "CTTS_GPU_CTAS_PER_SM": "2"},
+                {"CTTS_GPU_PITCH_SLOTS": "3"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         g = gpu.GpuSynth(small_db, 0)

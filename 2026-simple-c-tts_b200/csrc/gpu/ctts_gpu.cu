@@ -44,8 +44,36 @@ inline uint64_t up8(uint64_t v) { return (v + 7) & ~7ull; }
 
 }  // namespace
 
+// Development / test knobs, read from the environment ONCE, by ctts_gpu_init (never on the call path).
+struct Knobs {
+    bool trace = false;               // CTTS_GPU_TRACE: timing lines on stderr
+    int host_threads = 0;             // CTTS_GPU_HOST_THREADS: threads of the plan scan (0: default 4)
+    int pitch_slots = 0;              // CTTS_GPU_PITCH_SLOTS: capacity of the unit-head pitch table (tests: a table that fills up)
+    int ctas_per_sm = 3;              // CTTS_GPU_CTAS_PER_SM: occupancy the assembly window is sized for
+    int window = 0;                   // CTTS_GPU_WINDOW: shared window in samples (tests: force the HBM-window path)
+    uint64_t chunk_samples = 128ull << 20;   // CTTS_GPU_CHUNK_SAMPLES: output samples per launch of ctts_gpu_synth_batch
+    bool wsola_speculate = true;      // CTTS_GPU_WSOLA_SPECULATE=0: walk every WSOLA chain frame by frame
+    uint32_t wsola_force_bad = 0;     // CTTS_GPU_WSOLA_FORCE_BAD=N: report every N-th frame as unverified (tests of the repair path)
+
+    void read_env() {
+        auto num = [](const char* name, long long dflt) {
+            const char* e = getenv(name);
+            return e && *e ? strtoll(e, nullptr, 10) : dflt;
+        };
+        trace = getenv("CTTS_GPU_TRACE") != nullptr;
+        host_threads = (int)std::max(0ll, std::min(16ll, num("CTTS_GPU_HOST_THREADS", 0)));
+        pitch_slots = (int)std::max(0ll, num("CTTS_GPU_PITCH_SLOTS", 0));
+        ctas_per_sm = (int)std::max(1ll, std::min(8ll, num("CTTS_GPU_CTAS_PER_SM", 3)));
+        window = (int)std::max(0ll, num("CTTS_GPU_WINDOW", 0));
+        chunk_samples = (uint64_t)std::max(1ll, num("CTTS_GPU_CHUNK_SAMPLES", 128ll << 20));
+        wsola_speculate = num("CTTS_GPU_WSOLA_SPECULATE", 1) != 0;
+        wsola_force_bad = (uint32_t)std::max(0ll, num("CTTS_GPU_WSOLA_FORCE_BAD", 0));
+    }
+};
+
 struct ctts_gpu_ctx {
     int device = 0;
+    Knobs knobs;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int16_t* d_pool = nullptr;
@@ -81,10 +109,6 @@ struct ctts_gpu_ctx {
     char* h_arena = nullptr;         // pinned staging for the plan upload
     size_t h_arena_cap = 0;
     cudaStream_t copy_stream = nullptr;
-    static constexpr int kAux = 4;
-    cudaStream_t aux_stream[kAux] = {};   // the WSOLA kernels of consecutive chunks rotate over these
-    cudaEvent_t fence[kAux] = {};
-    std::vector<cudaEvent_t> asm_events;               // per chunk: its assembly kernel is done
     std::vector<cudaEvent_t> copied_events;            // per chunk (streaming): PCM, counts and flags are on the host
     uint32_t* h_stream = nullptr;                      // pinned (streaming): counts [n], then device error flags [n]
     size_t h_stream_cap = 0;
@@ -99,6 +123,7 @@ struct PlanChunk {
     uint32_t grid = 0;
     uint32_t st_begin = 0, st_count = 0;     // stretched utterances of the chunk (WSOLA tasks)
     uint32_t ola_begin = 0, ola_count = 0;   // their overlap-add blocks
+    uint32_t verify_tiles = 0;               // tiles of the longest of them (grid.x of wsola_verify_kernel)
 };
 
 struct ctts_gpu_plan {
@@ -283,7 +308,7 @@ int scan_plan(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, uint64_t big
     uint32_t T = 1;
     if (plan->n_ops > (1u << 17)) {
         T = std::min<uint32_t>(4, std::max(1u, std::thread::hardware_concurrency()));
-        if (const char* e = getenv("CTTS_GPU_HOST_THREADS")) T = (uint32_t)std::max(1, std::min(16, atoi(e)));
+        if (ctx->knobs.host_threads) T = (uint32_t)ctx->knobs.host_threads;
     }
     if (T <= 1) return scan_range(ctx, plan, big_threshold, sc, bad_utt, 0, n, sc->pre.data(), sc->bound.data());
     std::vector<PlanScan> part(T);
@@ -334,6 +359,7 @@ int ctts_gpu_init(ctts_gpu_ctx** out, const void* voice_db, size_t db_size, int 
 
     ctts_gpu_ctx* ctx = new ctts_gpu_ctx();
     ctx->device = device_ordinal;
+    ctx->knobs.read_env();
     auto bail = [&](int code) {
         ctts_gpu_free(ctx);
         return code;
@@ -354,6 +380,7 @@ int ctts_gpu_init(ctts_gpu_ctx** out, const void* voice_db, size_t db_size, int 
     CUI(cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_ordinal));
     // once per device: plans of different window sizes may be alive at the same time
     CUI(cudaFuncSetAttribute(ctts::assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+    CUI(cudaFuncSetAttribute(ctts::wsola_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ctts::WvSmem)));
 
     // re-pack: every unit starts on a 16-byte boundary, zero padded (int16x8 loads)
     const uint8_t* base = static_cast<const uint8_t*>(voice_db);
@@ -424,11 +451,8 @@ void ctts_gpu_free(ctts_gpu_ctx* ctx) {
     if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    for (cudaStream_t a : ctx->aux_stream) if (a) cudaStreamDestroy(a);
-    for (cudaEvent_t e : ctx->asm_events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->copied_events) cudaEventDestroy(e);
     if (ctx->h_stream) cudaFreeHost(ctx->h_stream);
-    for (cudaEvent_t e : ctx->fence) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -549,7 +573,7 @@ int norm_pool_for(ctts_gpu_ctx* ctx, float target_rms, ctts_gpu_ctx::NormPool** 
     ctts_gpu_ctx::NormPool* np = new ctts_gpu_ctx::NormPool();
     np->target_rms = target_rms;
     np->pitch_cap = std::max<uint32_t>(1u << 16, 64u * ctx->n_units);
-    if (const char* e = getenv("CTTS_GPU_PITCH_SLOTS")) np->pitch_cap = (uint32_t)std::max(1, atoi(e));   // tests: a table that fills up
+    if (ctx->knobs.pitch_slots) np->pitch_cap = (uint32_t)ctx->knobs.pitch_slots;
     np->pitch_slots.resize(ctx->n_units);
     if (cudaMalloc(reinterpret_cast<void**>(&np->d_pool), std::max<uint64_t>(ctx->pool_samples, 8) * sizeof(int16_t)) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&np->d_meta), std::max<size_t>(ctx->n_units, 1) * sizeof(int4)) != cudaSuccess ||
@@ -568,7 +592,7 @@ int norm_pool_for(ctts_gpu_ctx* ctx, float target_rms, ctts_gpu_ctx::NormPool** 
         CU(ctx, cudaGetLastError());
         CU(ctx, cudaStreamSynchronize(ctx->stream));   // once: later plans may run on another stream
     }
-    if (getenv("CTTS_GPU_TRACE"))
+    if (ctx->knobs.trace)
         fprintf(stderr, "ctts_gpu: normalized pool for target_rms %g: %u units, %llu samples in %.2f ms\n", (double)target_rms, ctx->n_units,
                 (unsigned long long)ctx->pool_samples, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     *out = np;
@@ -603,7 +627,7 @@ int run_pitch_jobs(ctts_gpu_ctx* ctx, ctts_gpu_ctx::NormPool* np, const std::vec
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_jobs);
     if (e != cudaSuccess) return fail(ctx, CTTS_GPU_ERR_CUDA, "unit_pitch_kernel: %s", cudaGetErrorString(e));
-    if (getenv("CTTS_GPU_TRACE"))
+    if (ctx->knobs.trace)
         fprintf(stderr, "ctts_gpu: unit-head pitch table: %zu new entries (%u in all) in %.2f ms including the stream drain\n", jobs.size(),
                 np->pitch_used, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     return CTTS_GPU_OK;
@@ -677,11 +701,10 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
     }
     auto smem_for = [&](uint32_t wcap) { return ctts::SMEM_HSTAGE + hcap * 2 + (wcap + 16) * 2; };
     // window: as large as the target occupancy allows, no larger than the largest region needs
-    int want_ctas = 3;
-    if (const char* e = getenv("CTTS_GPU_CTAS_PER_SM")) want_ctas = std::max(1, std::min(8, atoi(e)));
+    const int want_ctas = ctx->knobs.ctas_per_sm;
     const uint32_t budget = std::min<uint32_t>((uint32_t)ctx->smem_optin, (uint32_t)(ctx->smem_per_sm / want_ctas - 1024));
     uint32_t wcap = (uint32_t)up8(std::min<uint64_t>(sc.region_max + 16, 1u << 20));
-    if (const char* e = getenv("CTTS_GPU_WINDOW")) wcap = (uint32_t)up8(std::max(256, atoi(e)));   // tests: force the HBM path
+    if (ctx->knobs.window) wcap = (uint32_t)up8(std::max(256, ctx->knobs.window));   // tests: force the HBM path
     while (wcap > 1024 && smem_for(wcap) > budget) wcap -= 256;
     wcap &= ~7u;
     if (smem_for(wcap) > (uint32_t)ctx->smem_optin) {
@@ -692,14 +715,10 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
     p->hcap = hcap;
     p->smem_bytes = smem_for(wcap);
 
-    // ---- chunks: contiguous utterance ranges.  Without WSOLA a chunk is about chunk_samples
-    // output samples.  The WSOLA search is one CTA per utterance walking a long dependent chain
-    // (10 resident CTAs per SM); the stretch kernels of consecutive chunks run on four streams, so a
-    // chunk holds about a third of a wave of stretched utterances and the tail of one chunk's chains
-    // overlaps the chunks behind it (measured on the 4096-utterance mixed batch, e2e: 8 chunks on 4
-    // streams 163 ms, 6 chunks on 2 streams 166 ms, 3 chunks 173 ms, 11 chunks on 2 streams 206 ms, one
-    // stream 212 ms, one launch and one copy 238 ms; the kernels alone take 110 ms, the copies 91 ms,
-    // and what is left is the last chains running on a nearly idle GPU).
+    // ---- chunks: contiguous utterance ranges of about chunk_samples output samples (one launch of every
+    // kernel per chunk; the device->host copy of a chunk overlaps the kernels of the next).  Every frame of
+    // a stretched utterance is verified independently (wsola_verify_kernel), so batches with WSOLA need no
+    // geometry of their own.
     uint32_t n_stretched = 0;
     if (sc.any_stretch)
         for (uint32_t u = 0; u < n; u++) {
@@ -710,29 +729,11 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
         PlanChunk ch;
         ch.utt_end = n;
         p->chunks.push_back(ch);
-    } else if (n_stretched) {
-        uint32_t wave = (uint32_t)ctx->sm_count * ctts::WS_CTAS_PER_SM / 3;
-        if (const char* e = getenv("CTTS_GPU_STRETCH_WAVE")) wave = (uint32_t)std::max(1, atoi(e));
-        const uint32_t k = std::max<uint32_t>(1, (n_stretched + wave / 2) / wave);
-        const uint32_t share = (n_stretched + k - 1) / k;
-        uint32_t u0 = 0, cnt = 0;
-        for (uint32_t u = 0; u < n; u++) {
-            uint32_t hop = 0;
-            cnt += needs_stretch(plan->speed[u], &hop);
-            if ((cnt >= share && p->chunks.size() + 1 < k) || u + 1 == n) {
-                PlanChunk ch;
-                ch.utt_begin = u0;
-                ch.utt_end = u + 1;
-                p->chunks.push_back(ch);
-                u0 = u + 1;
-                cnt = 0;
-            }
-        }
     } else {
         uint64_t acc = 0;
         uint32_t u0 = 0;
         for (uint32_t u = 0; u < n; u++) {
-            acc += bound[u];
+            acc += std::max(bound[u], pre[u]);
             if (acc >= chunk_samples || u + 1 == n) {
                 PlanChunk ch;
                 ch.utt_begin = u0;
@@ -775,6 +776,8 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
                 st.out_cap = (uint32_t)(p->offsets[u + 1] - p->offsets[u]);
                 st.pos_off = (uint32_t)pos_total;
                 st.max_frames = (uint32_t)(pre[u] > 512 ? (pre[u] - 512) / 128 + 1 : 1);
+                if (st.max_frames > 1)
+                    ch.verify_tiles = std::max(ch.verify_tiles, (st.max_frames - 1 + ctts::WV_FRAMES - 1) / ctts::WV_FRAMES);
                 const uint64_t used_max = (uint64_t)st.max_frames * hop + 512;
                 const uint32_t per_block = ctts::ola_block_span(hop);
                 for (uint64_t f = 0; f < used_max; f += per_block) {
@@ -811,7 +814,7 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
                         PlanAlloc::up256((size_t)n_chunks * 4) + 3 * PlanAlloc::up256(std::max<size_t>(n, 1) * 4) + 65536;
         if (!stasks.empty())
             d_need += PlanAlloc::up256(stasks.size() * sizeof(ctts::StretchTask)) + 2 * PlanAlloc::up256(ola_task.size() * 4 + 4) +
-                      PlanAlloc::up256(pre_total * 2 + 16) + PlanAlloc::up256(pos_total * 4 + 4) + PlanAlloc::up256(stasks.size() * 8) + 4096;
+                      PlanAlloc::up256(pre_total * 2 + 16) + PlanAlloc::up256(pos_total * 4 + 4) + PlanAlloc::up256(stasks.size() * 20) + 4096;
         const size_t h_need = PlanAlloc::up256(ops_bytes) + PlanAlloc::up256(tasks_bytes) + 4096;
         rc = ensure_arenas(ctx, d_need, h_need);
         if (rc) { delete p; return rc; }
@@ -845,7 +848,7 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
         p->d_ola_first = al.dev<uint32_t>(ola_first.size());
         p->d_pre = al.dev<int16_t>(pre_total);
         p->d_frame_pos = al.dev<uint32_t>(pos_total);
-        p->d_n_frames = al.dev<uint32_t>(2 * (size_t)p->n_stretch);   // frames, then exact-evaluation counts
+        p->d_n_frames = al.dev<uint32_t>(5 * (size_t)p->n_stretch);   // frames, exact evaluations, first bad frame, first silent frame, tier-2 candidates
     }
     if (al.err != cudaSuccess) {
         ctts_gpu_plan_destroy(p);
@@ -865,7 +868,8 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
     p->occ = (uint32_t)occ;
 
     p->info.kernel_launches = n_chunks;
-    for (const PlanChunk& ch : p->chunks) p->info.kernel_launches += ch.st_count ? 2 : 0;
+    for (const PlanChunk& ch : p->chunks)   // scan, verify, repair (chain walk), overlap-add
+        p->info.kernel_launches += ch.st_count ? 2 + (ch.verify_tiles && ctx->knobs.wsola_speculate ? 1 : 0) + (ch.ola_count ? 1 : 0) : 0;
     p->info.n_stretch = p->n_stretch;
     p->info.bound_samples = std::accumulate(bound.begin(), bound.end(), (uint64_t)0);
     p->info.smem_bytes = p->smem_bytes;
@@ -1103,9 +1107,27 @@ int launch_stretch(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, int16_t* d_p
     w.out_counts = p->d_counts;
     w.frame_pos = p->d_frame_pos;
     w.n_frames = p->d_n_frames;
+    w.first_bad = p->d_n_frames + 2 * (size_t)p->n_stretch;
+    w.first_silent = p->d_n_frames + 3 * (size_t)p->n_stretch;
+    w.tier2 = p->d_n_frames + 4 * (size_t)p->n_stretch;
+    w.task_count = ch.st_count;
+    w.speculate = ctx->knobs.wsola_speculate ? 1u : 0u;
+    w.force_bad = ctx->knobs.wsola_force_bad;
     w.hann512 = ctx->d_tables + 3328;
     w.ola_block_task = p->d_ola_task + ch.ola_begin;
     w.ola_block_first = p->d_ola_first + ch.ola_begin;
+    // speculate (scan) -> verify every frame in parallel -> walk the chain only where that failed -> overlap-add
+    ctts::wsola_scan_kernel<<<(ch.st_count + 7) / 8, 256, 0, st>>>(w);
+    CU(ctx, cudaGetLastError());
+    if (w.speculate && ch.verify_tiles) {
+        for (uint32_t t0 = 0; t0 < ch.st_count; t0 += 65535u) {   // grid.y limit
+            ctts::WsolaArgs wv = w;
+            wv.task_first = ch.st_begin + t0;
+            const dim3 grid(ch.verify_tiles, std::min<uint32_t>(ch.st_count - t0, 65535u));
+            ctts::wsola_verify_kernel<<<grid, ctts::WV_THREADS, sizeof(ctts::WvSmem), st>>>(wv);
+            CU(ctx, cudaGetLastError());
+        }
+    }
     ctts::wsola_search_kernel<<<ch.st_count, ctts::WS_THREADS, 0, st>>>(w);
     CU(ctx, cudaGetLastError());
     if (ch.ola_count) {
@@ -1186,18 +1208,24 @@ int ctts_gpu_plan_read_pcm(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, int16_t* dst, ui
     return CTTS_GPU_OK;
 }
 
-int ctts_gpu_plan_wsola_stats(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint64_t* frames, uint64_t* exact_decisions) {
-    if (!ctx || !p || !frames || !exact_decisions) return CTTS_GPU_ERR_INVALID_ARG;
-    *frames = 0;
-    *exact_decisions = 0;
+int ctts_gpu_plan_wsola_stats(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, ctts_gpu_wsola_stats* out) {
+    if (!ctx || !p || !out) return CTTS_GPU_ERR_INVALID_ARG;
+    memset(out, 0, sizeof *out);
     if (!p->n_stretch) return CTTS_GPU_OK;
     CU(ctx, cudaSetDevice(ctx->device));
-    std::vector<uint32_t> h(2 * (size_t)p->n_stretch);
+    const size_t ns = p->n_stretch;
+    std::vector<uint32_t> h(5 * ns);
     CU(ctx, cudaMemcpyAsync(h.data(), p->d_n_frames, h.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    for (uint32_t i = 0; i < p->n_stretch; i++) {
-        *frames += h[i];
-        *exact_decisions += h[p->n_stretch + i];
+    for (size_t i = 0; i < ns; i++) {
+        const uint32_t frames = h[i], bad = h[2 * ns + i];
+        out->frames += frames;
+        out->exact_evaluations += h[ns + i];
+        out->tier2_candidates += h[4 * ns + i];
+        if (bad < frames) {
+            out->walked_utterances++;
+            out->walked_frames += frames - bad;
+        }
     }
     return CTTS_GPU_OK;
 }
@@ -1223,13 +1251,12 @@ int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, 
                                 int16_t* pcm_out, const uint64_t* out_offsets, uint32_t* out_counts,
                                 ctts_gpu_chunk_fn on_chunk, void* user) {
     if (!ctx || !plan || !params || !pcm_out || !out_offsets || !out_counts) return CTTS_GPU_ERR_INVALID_ARG;
-    const bool trace = getenv("CTTS_GPU_TRACE") != nullptr;
+    const bool trace = ctx->knobs.trace;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     auto t0 = now();
     // launches of ~256 MB of PCM: the device->host copy of one chunk overlaps the assembly of the next
-    uint64_t chunk_samples = 128ull << 20;
-    if (const char* e = getenv("CTTS_GPU_CHUNK_SAMPLES")) chunk_samples = strtoull(e, nullptr, 10);
+    const uint64_t chunk_samples = ctx->knobs.chunk_samples;
     ctts_gpu_plan* p = nullptr;
     int rc = prepare_plan(ctx, plan, params, out_offsets, chunk_samples, true, &p);
     if (rc) return rc;
@@ -1252,7 +1279,6 @@ int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, 
     auto cu_fail = [&](cudaError_t e, const char* what) {
         cudaStreamSynchronize(ctx->stream);
         if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-        for (cudaStream_t a : ctx->aux_stream) if (a) cudaStreamSynchronize(a);
         ctts_gpu_plan_destroy(p);
         return fail(ctx, CTTS_GPU_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     };
@@ -1298,31 +1324,6 @@ int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, 
         cudaEventRecord(ev, s_);
         tev.push_back(ev);
     };
-    // Batches with WSOLA: every chunk is assembled on the context stream, back to back (cheap, and the
-    // search kernels then never hold up an assembly launch); the search + overlap-add of consecutive
-    // chunks alternate between two auxiliary streams, each waiting only for its own chunk's assembly.
-    // The search is a wave of long dependent chains whose tail leaves SMs idle: with two chunks of
-    // half a wave in flight the next chunk fills them.
-    const bool two = p->n_stretch && nc > 1 && !getenv("CTTS_GPU_ONE_STREAM");
-    int n_aux = ctts_gpu_ctx::kAux;
-    if (const char* e = getenv("CTTS_GPU_AUX_STREAMS")) n_aux = std::max(1, std::min((int)ctts_gpu_ctx::kAux, atoi(e)));
-    if (two && !ctx->aux_stream[0]) {
-        cudaError_t e = cudaSuccess;
-        // highest priority: a search CTA is one link of a long dependent chain, an assembly CTA is not
-        int prio_lo = 0, prio_hi = 0;
-        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        if (getenv("CTTS_GPU_AUX_DEFAULT_PRIORITY")) prio_hi = 0;
-        for (int i = 0; i < ctts_gpu_ctx::kAux && e == cudaSuccess; i++)
-            e = cudaStreamCreateWithPriority(&ctx->aux_stream[i], cudaStreamNonBlocking, prio_hi);
-        for (int i = 0; i < ctts_gpu_ctx::kAux && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->fence[i], cudaEventDisableTiming);
-        if (e != cudaSuccess) return cu_fail(e, "aux streams");
-    }
-    while (two && ctx->asm_events.size() < nc) {
-        cudaEvent_t ev;
-        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-        if (e != cudaSuccess) return cu_fail(e, "event");
-        ctx->asm_events.push_back(ev);
-    }
     if (p->n_utts) {
         rc = begin_run(ctx, p);
         mark(ctx->stream);
@@ -1332,13 +1333,7 @@ int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, 
             rc = build_chunk(ctx, p, c, ctx->stream);
             if (!rc) rc = launch_chunk(ctx, p, c, d_out, ctx->stream);
             mark(ctx->stream);
-            cudaStream_t cs = ctx->stream;   // the stream the chunk's last kernel runs on
-            if (!rc && two && ch.st_count) {
-                cs = ctx->aux_stream[c % (uint32_t)n_aux];
-                cudaError_t e = cudaEventRecord(ctx->asm_events[c], ctx->stream);
-                if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ctx->asm_events[c], 0);
-                if (e != cudaSuccess) return cu_fail(e, "fence");
-            }
+            cudaStream_t cs = ctx->stream;
             if (!rc) rc = launch_stretch(ctx, p, c, d_out, cs);
             mark(cs);
             if (rc) break;
@@ -1362,13 +1357,6 @@ int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, 
             while (on_chunk && delivered < c + 1 &&
                    (p->chunks[delivered].utt_end <= p->chunks[delivered].utt_begin || cudaEventQuery(ctx->copied_events[delivered]) == cudaSuccess))
                 deliver(delivered++);
-        }
-        if (two) {   // everything the aux streams did is ordered before what follows on the context stream
-            for (int i = 0; i < n_aux; i++) {
-                cudaError_t e = cudaEventRecord(ctx->fence[i], ctx->aux_stream[i]);
-                if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->fence[i], 0);
-                if (e != cudaSuccess) return cu_fail(e, "fence");
-            }
         }
     }
     auto t2 = now();

@@ -1,8 +1,30 @@
-// wsola.cuh -- time stretching (time_stretch, ctts.c:3490-3617) as two kernels.
+// wsola.cuh -- time stretching (time_stretch, ctts.c:3490-3617).
 //
-// 1. wsola_search_kernel: the frame-to-frame dependent chain (the analysis position of frame k
-//    depends on where frame k-1 was taken).  One CTA per stretched utterance walks the frames
-//    in order.  The reference scores <= 65 coarse candidates (offsets -128..128 step 4) and
+// The analysis position of frame k depends on where frame k-1 was taken (ctts.c:3555-3592), but the
+// transition is a pure function T_k(offset of frame k-1), and on real signals it has a fixed point:
+// the candidate at the previous frame's offset IS the target (same samples), so it scores exactly
+// 1.0f (sum_prod == sum_sq1 == sum_sq2 bit for bit and sqrtf(s*s) == s), nothing can score higher
+// than 1 except by rounding, and the offset repeats.  Digital silence behind the frame makes every
+// score 0, the first candidate in bounds (-128) wins (ctts.c:3426, :3452-3461) and then sticks.  So
+// the chain is SPECULATED and VERIFIED instead of walked:
+//   wsola_scan_kernel    per utterance: the frame count and F = the first frame whose target, with
+//                        every offset before it 0, is all zero.  Speculated offsets: 0 before F,
+//                        -128 from F on.
+//   wsola_verify_kernel  every frame independently (tiles of 26 frames per CTA): under the
+//                        speculated previous offset h the frame's offset is h again iff every other
+//                        candidate of the coarse and the fine stage scores < 1.0f.  Tier 1 proves that
+//                        with a partial sum: 1 - corr = |x^ - t^|^2 / 2 >= sum over a few short blocks
+//                        of (x^_i - t^_i)^2 (x^, t^ the unit-normalised windows; energies exact, from
+//                        a 64-bit prefix sum of squares), which needs 32 of the 384 terms.  What tier 1
+//                        cannot reject (0.3 candidates per frame) gets the full 384-term FMA filter
+//                        score (tier 2, one warp per candidate), and what that leaves within eps of 1
+//                        the reference's exact loop (tier 3).  A candidate that really reaches 1.0f
+//                        marks the frame as the utterance's first bad frame.
+//   wsola_search_kernel  the repair: the frame-by-frame chain walk (below), started at the first bad
+//                        frame with the verified position before it; exits at once when the
+//                        speculation held (every utterance of the benchmark workloads).
+//
+// wsola_search_kernel: one CTA per stretched utterance walks the frames in order.  The reference scores <= 65 coarse candidates (offsets -128..128 step 4) and
 //    then <= 6 fine ones around the best, each score a 384-term sequential float loop
 //    (groups of 4: ((p0+p1)+p2)+p3, then +=, ctts.c:3411-3413) -- 91 % of its run time.
 //    Here every frame is decided in two steps that give the identical result:
@@ -25,6 +47,7 @@
 //    (ctts.c:3577) and a float norm (ctts.c:3578), normalises, and the CTA
 //    reports the last non-zero sample for the trailing-zero trim (ctts.c:3611).
 #pragma once
+#include <climits>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -68,6 +91,12 @@ struct WsolaArgs {
     uint32_t* out_counts;
     uint32_t* frame_pos;
     uint32_t* n_frames;   // per task; [n_tasks + task] = decisions that needed an exact evaluation
+    uint32_t* first_bad;    // per task: first frame the speculation could not confirm (0xffffffff: none)
+    uint32_t* first_silent; // per task: F of wsola_scan_kernel (0xffffffff: none)
+    uint32_t* tier2;        // per task: candidates tier 1 could not reject
+    uint32_t task_count;    // tasks of this launch
+    uint32_t speculate;     // 0: every utterance is walked by the chain kernel from frame 1 (debug / tests)
+    uint32_t force_bad;     // != 0: every frame k with k % force_bad == 0 is reported bad (tests of the repair path)
     const float* hann512;
     const uint32_t* ola_block_task;   // per OLA block of this launch: task index (plan-wide)
     const uint32_t* ola_block_first;  // per OLA block: first output sample
@@ -248,15 +277,16 @@ __global__ void __launch_bounds__(WS_THREADS, WS_CTAS_PER_SM) wsola_search_kerne
 
     uint32_t frames = n >= WS_FRAME ? (n - WS_FRAME) / WS_HOP + 1 : 0;
     if (frames > task.max_frames) frames = task.max_frames;
+    // the chain is walked from the first frame the speculation could not confirm (wsola_verify_kernel);
+    // every position before it is verified
+    const uint32_t k0 = A.first_bad[ti];
+    if (k0 >= frames) return;   // (k0 >= 1; CTA-uniform)
+    const uint32_t vstart0 = (k0 - 1u) * WS_HOP;   // the view of frame k0 starts here
     if (tid == 0) {
-        A.n_frames[ti] = frames;
-        *exact_count = 0;
         s_ptotal = 0ull;
-        Pr[0] = 0ull;
+        Pr[vstart0 & (WS_RING - 1)] = 0ull;
     }
-    if (frames == 0) return;
-    if (tid == 0) fpos[0] = 0;
-    uint32_t prev_pos = 0;
+    uint32_t prev_pos = fpos[k0 - 1u];   // written by an earlier kernel
 
     WsDecide D{ca, ce, xoff, list, s_cnt, &s_sb, &s_sb_valid, exact_count};
 
@@ -288,19 +318,20 @@ __global__ void __launch_bounds__(WS_THREADS, WS_CTAS_PER_SM) wsola_search_kerne
         const uint32_t p = base + (uint32_t)tid;
         return p < n ? (float)in[p] : 0.0f;
     };
-    // frame 1 sees input[0 .. 640)
+    // frame k0 sees input[vstart0 .. vstart0 + 640) (the prefix sums start at its first sample: only
+    // differences are used)
     for (uint32_t b = 0; b < WS_RANGE; b += WS_THREADS) {
-        append(b, load(b));
+        append(vstart0 + b, load(vstart0 + b));
         __syncthreads();
     }
-    // frame k >= 2 adds input[128 k + 384 .. 128 k + 512); loaded two frames ahead (the buffer is in HBM)
-    float next_v = frames > 2 ? load(WS_RANGE) : 0.0f;
-    float next_v2 = frames > 3 ? load(WS_RANGE + WS_THREADS) : 0.0f;
+    // frame k > k0 adds input[128 k + 384 .. 128 k + 512); loaded two frames ahead (the buffer is in HBM)
+    float next_v = frames > k0 + 1 ? load(vstart0 + WS_RANGE) : 0.0f;
+    float next_v2 = frames > k0 + 2 ? load(vstart0 + WS_RANGE + WS_THREADS) : 0.0f;
 
-    for (uint32_t k = 1; k < frames; k++) {
+    for (uint32_t k = k0; k < frames; k++) {
         const int nominal = (int)(k * WS_HOP);
         const uint32_t vstart = (uint32_t)(nominal - WS_SHIFT);           // absolute position of the view
-        if (k >= 2) {
+        if (k > k0) {
             append(vstart + WS_RANGE - WS_THREADS, next_v);              // the 128 samples this view adds
             next_v = next_v2;
             if (k + 2 < frames) next_v2 = load(vstart + WS_RANGE + WS_THREADS);   // two frames ahead
@@ -468,6 +499,324 @@ __global__ void __launch_bounds__(WS_THREADS, WS_CTAS_PER_SM) wsola_search_kerne
         if (tid == 0) fpos[k] = pos;
         prev_pos = pos;
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- speculation: scan + verify
+
+constexpr int WV_THREADS = 256;
+constexpr int WV_FRAMES = 26;                                  // frames per tile: 26 * 19 items = 494 = 2 per thread
+constexpr int WV_SPAN = WS_HOP * WV_FRAMES + (WS_RANGE - WS_HOP);   // samples a tile sees: 3840
+constexpr int WV_QUADS = WV_SPAN / 4;
+constexpr int WV_NB = 4;                                       // tier-1 blocks ...
+constexpr int WV_BL = 8;                                       // ... of this many terms (multiple of 4)
+constexpr int WV_B0 = 44;                                      // first term of block 0
+constexpr int WV_BSTEP = 96;                                   // block spacing
+constexpr int WV_ITEMS = 19;   // per frame: 16 coarse groups of 4, the 65th candidate, fine below, fine above
+constexpr int WV_LIST = 768;                                   // tier-2 list entries per tile
+constexpr float WV_THR = 2.5e-4f;   // tier 1 rejects when the partial sum of (x^ - t^)^2 exceeds this (5 x the bound, see below)
+static_assert(WV_SPAN % 4 == 0 && WV_BL % 4 == 0 && WV_B0 % 4 == 0 && WV_BSTEP % 4 == 0, "float4 alignment");
+static_assert(WV_B0 + (WV_NB - 1) * WV_BSTEP + WV_BL <= WS_OVERLAP, "blocks inside the window");
+
+struct WvSmem {
+    float xs[WV_SPAN + 16];                    // samples of the tile as floats (zero past the end of the input)
+    unsigned long long Pbuf[WV_SPAN + 8];      // P[i] = Pbuf[i + 3] = sum_{j<i} xs[j]^2, exact (P[4q + 1] is 16-byte aligned)
+    float W4[WV_QUADS];                        // window energy at 4j (float of the exact integer)
+    float G4[WV_QUADS];                        // energy of the tier-1 blocks of the window at 4j
+    float Et[WV_FRAMES], Bt[WV_FRAMES];        // target: energy, block energy / energy
+    int hyp[WV_FRAMES];                        // speculated previous offset; INT_MIN: frame needs no check
+    int room[WV_FRAMES];                       // largest offset in bounds
+    unsigned long long wtot[WV_THREADS / 32];
+    uint32_t list[WV_LIST];                    // (frame << 16) | (offset + 128)
+    uint32_t n_list;
+    uint32_t bad;                              // smallest bad frame of the tile
+};
+
+// per stretched utterance (one warp each): frame count, the first frame whose target under offset 0
+// is digital silence, and the reset of the per-run state
+__global__ void __launch_bounds__(256) wsola_scan_kernel(const WsolaArgs A) {
+    const uint32_t w = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= A.task_count) return;
+    const uint32_t ti = A.task_first + w;
+    const StretchTask task = A.tasks[ti];
+    const uint32_t n = A.pre_counts[task.utt];
+    const int16_t* in = A.pre + task.pre_off;
+    uint32_t frames = n >= WS_FRAME ? (n - WS_FRAME) / WS_HOP + 1 : 0;
+    if (frames > task.max_frames) frames = task.max_frames;
+    uint32_t F = 0xffffffffu;
+    if (A.speculate) {
+        // target of frame k when frame k-1 sits at its nominal position: in[128 k .. 128 k + 384)
+        for (uint32_t k0 = 1; k0 < frames && F == 0xffffffffu; k0 += 32) {
+            const uint32_t k = k0 + (uint32_t)lane;
+            bool zero = k < frames;
+            if (zero) {
+                const int4* v = reinterpret_cast<const int4*>(in + (size_t)k * WS_HOP);   // pre_off and 128 k are multiples of 8
+                for (int i = 0; i < WS_OVERLAP / 8 && zero; i++) {
+                    const int4 q = v[i];
+                    zero = (q.x | q.y | q.z | q.w) == 0;
+                }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, zero);
+            if (m) F = k0 + (uint32_t)__ffs(m) - 1u;
+        }
+    }
+    if (lane == 0) {
+        A.n_frames[ti] = frames;
+        A.n_frames[A.n_tasks + ti] = 0;
+        A.tier2[ti] = 0;
+        A.first_silent[ti] = F;
+        A.first_bad[ti] = A.speculate ? 0xffffffffu : 1u;
+        if (frames) A.frame_pos[task.pos_off] = 0;
+    }
+}
+
+// tier 1 for one item = 4 candidates (window starts yb + STRIDE * j in the tile) against the target at
+// tb0: the cross terms of the WV_NB blocks, one FMA each, operand loads shared by the 4 candidates
+template <int STRIDE>
+__device__ __forceinline__ void wv_dots(const float* __restrict__ xs, int tb0, int yb, float (&d)[4]) {
+    d[0] = d[1] = d[2] = d[3] = 0.0f;
+    constexpr int TC = WV_BL / 4;                                 // target chunks per block
+    constexpr int YC = STRIDE == 4 ? TC + 3 : TC + 1;             // candidate chunks per block
+#pragma unroll
+    for (int b = 0; b < WV_NB; b++) {
+        const float4* t4 = reinterpret_cast<const float4*>(xs + tb0 + WV_B0 + b * WV_BSTEP);
+        const float4* y4 = reinterpret_cast<const float4*>(xs + yb + WV_B0 + b * WV_BSTEP);
+        float y[4 * YC];
+#pragma unroll
+        for (int m = 0; m < YC; m++) {
+            const float4 v = y4[m];
+            y[4 * m] = v.x; y[4 * m + 1] = v.y; y[4 * m + 2] = v.z; y[4 * m + 3] = v.w;
+        }
+#pragma unroll
+        for (int m = 0; m < TC; m++) {
+            const float4 t = t4[m];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                d[j] = __fmaf_rn(t.x, y[STRIDE * j + 4 * m], d[j]);
+                d[j] = __fmaf_rn(t.y, y[STRIDE * j + 4 * m + 1], d[j]);
+                d[j] = __fmaf_rn(t.z, y[STRIDE * j + 4 * m + 2], d[j]);
+                d[j] = __fmaf_rn(t.w, y[STRIDE * j + 4 * m + 3], d[j]);
+            }
+        }
+    }
+}
+
+// Verification of the speculated offsets, one tile of WV_FRAMES frames of one utterance per CTA
+// (blockIdx.y = task of the launch, blockIdx.x = tile).
+//
+// Frame k, speculated previous offset h (0 up to and including frame F, -128 after it): the target is
+// in[128 k + h .. + 384).  If it is all zero the frame's offset is -128 (see the header).  Otherwise the
+// candidate at offset h is the target itself and scores exactly 1.0f, and the frame's offset is h
+// provided every other candidate the reference would score -- coarse offsets -128, -124 .. 128 and
+// fine offsets h-3 .. h+3, in bounds -- scores < 1.0f.
+//
+// Error budget of tier 1.  With x^ = x/|x|, t^ = t/|t| (exact real arithmetic) the true correlation is
+// rho = 1 - |x^ - t^|^2 / 2 <= 1 - S/2, S = sum over the blocks of (x^_i - t^_i)^2 = A + B - 2C,
+// A = E_blocks(x)/E(x), B = E_blocks(t)/E(t) (ratios of exact integers, evaluated in float: relative
+// error < 4e-7 each incl. the approximate reciprocal), C = dot/sqrt(E(x)E(t)) (32 FMA terms, rsqrt.approx:
+// |error| <= (gamma_32 + 2^-22 + 3u) sqrt(AB) < 2.5e-6).  So |S~ - S| < 4e-6 (A, B <= 1), and the
+// reference's score r satisfies |r - rho| <= 2e-5, hence r <= 1 - S~/2 + 2e-6 + 2e-5 < 1
+// whenever S~ > 4.4e-5.  WV_THR is 2.5e-4.
+__global__ void __launch_bounds__(WV_THREADS, 3) wsola_verify_kernel(const WsolaArgs A) {
+    extern __shared__ __align__(16) unsigned char wv_raw[];
+    WvSmem& sm = *reinterpret_cast<WvSmem*>(wv_raw);
+    const uint32_t ti = A.task_first + blockIdx.y;
+    const uint32_t frames = A.n_frames[ti];
+    const uint32_t k0 = 1u + blockIdx.x * WV_FRAMES;        // first frame of the tile
+    if (k0 >= frames) return;
+    const StretchTask task = A.tasks[ti];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = A.pre_counts[task.utt];
+    const int16_t* in = A.pre + task.pre_off;
+    const uint32_t F = A.first_silent[ti];
+    const uint32_t base = (k0 - 1u) * WS_HOP;               // tile sample 0 = input sample base
+
+    // ---- stage the tile as floats and build the exact prefix sum of squares.  Thread t owns the
+    //      quads t, t + 256, ..: consecutive lanes touch consecutive 16 / 32 byte pieces.
+    if (tid == 0) {
+        sm.n_list = 0;
+        sm.bad = 0xffffffffu;
+        sm.Pbuf[3] = 0ull;
+    }
+    unsigned long long* const P = sm.Pbuf + 3;
+    if (tid < 4) *reinterpret_cast<float4*>(sm.xs + WV_SPAN + 4 * tid) = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned long long carry = 0ull;
+    for (int q0 = 0; q0 < WV_QUADS; q0 += WV_THREADS) {
+        const int q = q0 + tid;
+        int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+        if (q < WV_QUADS) {
+            const uint32_t p = base + 4u * (uint32_t)q;
+            if (p + 4u <= n) {
+                const uint2 w = *reinterpret_cast<const uint2*>(in + p);
+                v0 = (int)(short)(w.x & 0xffffu); v1 = (int)(short)(w.x >> 16);
+                v2 = (int)(short)(w.y & 0xffffu); v3 = (int)(short)(w.y >> 16);
+            } else {
+                if (p < n) v0 = in[p];
+                if (p + 1u < n) v1 = in[p + 1];
+                if (p + 2u < n) v2 = in[p + 2];
+            }
+            *reinterpret_cast<float4*>(sm.xs + 4 * q) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
+        }
+        const unsigned long long s0 = (unsigned long long)(uint32_t)(v0 * v0), s1 = s0 + (uint32_t)(v1 * v1),
+                                 s2 = s1 + (uint32_t)(v2 * v2), s3 = s2 + (uint32_t)(v3 * v3);
+        unsigned long long inc = s3;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) sm.wtot[warp] = inc;
+        __syncthreads();
+        unsigned long long pre = carry, all = carry;
+#pragma unroll
+        for (int w = 0; w < WV_THREADS / 32; w++) {
+            const unsigned long long t = sm.wtot[w];
+            if (w < warp) pre += t;
+            all += t;
+        }
+        carry = all;
+        if (q < WV_QUADS) {
+            const unsigned long long e = pre + inc - s3;   // exclusive prefix at the quad's first sample
+            ulonglong2 a, b;
+            a.x = e + s0; a.y = e + s1;
+            b.x = e + s2; b.y = e + s3;
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(P + 4 * q + 1);
+            dst[0] = a;
+            dst[1] = b;
+        }
+        __syncthreads();
+    }
+
+    auto energy = [&](int p, int len) { return ws_u64_to_float(P[p + len] - P[p]); };
+    auto blocks = [&](int p) {
+        unsigned long long e = 0ull;
+#pragma unroll
+        for (int b = 0; b < WV_NB; b++) e += P[p + WV_B0 + b * WV_BSTEP + WV_BL] - P[p + WV_B0 + b * WV_BSTEP];
+        return ws_u64_to_float(e);
+    };
+    // ---- window / block energies at every 4th sample (the coarse candidates), per-frame quantities
+    for (int j = tid; j < WV_QUADS; j += WV_THREADS) {
+        float w = 0.0f, g = 0.0f;
+        if (4 * j + WS_OVERLAP <= WV_SPAN) {
+            w = energy(4 * j, WS_OVERLAP);
+            g = blocks(4 * j);
+        }
+        sm.W4[j] = w;
+        sm.G4[j] = g;
+    }
+    if (tid < WV_FRAMES) {
+        const uint32_t k = k0 + (uint32_t)tid;
+        int h = INT_MIN;
+        if (k < frames) {
+            h = k <= F ? 0 : -WS_SHIFT;
+            const int ts = WS_HOP * tid + WS_SHIFT + h;
+            const unsigned long long e = P[ts + WS_OVERLAP] - P[ts];
+            uint32_t pos = k * WS_HOP + (uint32_t)(h + 0);
+            if (e == 0ull) {   // digital silence behind the frame: offset -128, nothing to verify
+                pos = k * WS_HOP - WS_SHIFT;
+                h = INT_MIN;
+            } else {
+                const float et = ws_u64_to_float(e);
+                sm.Et[tid] = et;
+                sm.Bt[tid] = __fdividef(blocks(ts), et);
+            }
+            if (A.force_bad && k % A.force_bad == 0) atomicMin(&sm.bad, k);
+            A.frame_pos[task.pos_off + k] = pos;
+            const long long room = (long long)n - WS_FRAME - (long long)k * WS_HOP;   // >= 0
+            sm.room[tid] = room > WS_SHIFT ? WS_SHIFT : (int)room;
+        }
+        sm.hyp[tid] = h;
+    }
+    __syncthreads();
+
+    // ---- tier 1
+    for (int it = tid; it < WV_FRAMES * WV_ITEMS; it += WV_THREADS) {
+        const int f = it / WV_ITEMS, g = it - f * WV_ITEMS;
+        const int h = sm.hyp[f];
+        if (h == INT_MIN) continue;
+        const int v = WS_HOP * f;                 // view of the frame in the tile
+        const int ts = v + WS_SHIFT + h;
+        const int room = sm.room[f];
+        const float et = sm.Et[f], bt = sm.Bt[f];
+        int o0, stride;
+        uint32_t live;                            // which of the 4 candidates count
+        if (g < 16) { o0 = -WS_SHIFT + 16 * g; stride = 4; live = 0xfu; }
+        else if (g == 16) { o0 = WS_SHIFT; stride = 4; live = 0x1u; }             // +128 alone (the other three would lie outside the search range)
+        else if (g == 17) { o0 = h - 4; stride = 1; live = h - 3 >= -WS_SHIFT ? 0xeu : 0u; }   // h-3 .. h-1
+        else { o0 = h; stride = 1; live = 0xeu; }                                   // h+1 .. h+3
+        if (!live) continue;
+        const int yb = v + WS_SHIFT + o0;
+        float d[4], w[4], gb[4];
+        if (stride == 4) {
+            wv_dots<4>(sm.xs, ts, yb, d);
+            const float4 w4 = *reinterpret_cast<const float4*>(sm.W4 + (yb >> 2));
+            const float4 g4 = *reinterpret_cast<const float4*>(sm.G4 + (yb >> 2));
+            w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+            gb[0] = g4.x; gb[1] = g4.y; gb[2] = g4.z; gb[3] = g4.w;
+        } else {
+            wv_dots<1>(sm.xs, ts, yb, d);
+#pragma unroll
+            for (int j = 1; j < 4; j++) {
+                w[j] = energy(yb + j, WS_OVERLAP);
+                gb[j] = blocks(yb + j);
+            }
+            w[0] = gb[0] = 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int o = o0 + stride * j;
+            if (!((live >> j) & 1u) || o == h || o > room) continue;   // not a candidate / the target itself / out of bounds
+            if (w[j] == 0.0f) continue;                                // zero energy: the score is exactly 0 (ctts.c:3426)
+            const float s = __fdividef(gb[j], w[j]) + bt - 2.0f * d[j] * rsqrt_approx(w[j] * et);
+            if (!(s > WV_THR)) {
+                const uint32_t slot = atomicAdd(&sm.n_list, 1u);
+                if (slot < (uint32_t)WV_LIST) sm.list[slot] = ((uint32_t)f << 16) | (uint32_t)(o + WS_SHIFT);
+                else atomicMin(&sm.bad, k0 + (uint32_t)f);             // no room to look closer: let the chain walk decide
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- tiers 2 and 3: one warp per candidate tier 1 could not reject
+    const uint32_t n_list = min(sm.n_list, (uint32_t)WV_LIST);
+    uint32_t n_exact = 0;
+    for (uint32_t e = warp; e < n_list; e += WV_THREADS / 32) {
+        const uint32_t ent = sm.list[e];
+        const int f = (int)(ent >> 16), xo = (int)(ent & 0xffffu);   // xo = offset + 128: window start inside the view
+        const float* tg = sm.xs + WS_HOP * f + WS_SHIFT + sm.hyp[f];
+        const float* xc = sm.xs + WS_HOP * f + xo;
+        float dot = 0.0f;
+#pragma unroll
+        for (int q = 0; q < WS_OVERLAP / 32; q++) dot = __fmaf_rn(tg[lane + 32 * q], xc[lane + 32 * q], dot);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        const float sa = energy(WS_HOP * f + xo, WS_OVERLAP);
+        // the full FMA filter score: within 2e-5 of the reference's (eps = 1e-4 as in the chain kernel)
+        const float a = dot * rsqrt_approx(sa * sm.Et[f]);
+        if (a + WS_EPS < 1.0f) continue;
+        // tier 3: the reference's loop; lanes 0..2 form sum_prod, sum_sq1, sum_sq2 (ctts.c:3411-3413)
+        float acc = 0.0f;
+        if (lane < 3) {
+            const float* p = lane == 2 ? tg : xc;
+            const float* q = lane == 1 ? xc : tg;
+#pragma unroll 2
+            for (int m = 0; m < WS_OVERLAP / 4; m++)
+                acc += p[4 * m] * q[4 * m] + p[4 * m + 1] * q[4 * m + 1] + p[4 * m + 2] * q[4 * m + 2] + p[4 * m + 3] * q[4 * m + 3];
+        }
+        const float sp = __shfl_sync(0xffffffffu, acc, 0), s1 = __shfl_sync(0xffffffffu, acc, 1), s2 = __shfl_sync(0xffffffffu, acc, 2);
+        const float den = sqrtf(s1 * s2);
+        const float r = den < 1.0f ? 0.0f : sp / den;
+        n_exact++;
+        // a candidate that reaches 1.0f ties with (or beats) the speculated one: scan order decides,
+        // which is the chain walk's business
+        if (!(r < 1.0f) && lane == 0) atomicMin(&sm.bad, k0 + (uint32_t)f);
+    }
+    if (lane == 0 && n_exact) atomicAdd(A.n_frames + A.n_tasks + ti, n_exact);
+    __syncthreads();
+    if (tid == 0) {
+        if (n_list) atomicAdd(A.tier2 + ti, n_list);
+        if (sm.bad != 0xffffffffu) atomicMin(A.first_bad + ti, sm.bad);
     }
 }
 

@@ -16,6 +16,11 @@ from .front import AssemblyParams, BatchPlan, CBatchPlan
 ERR_CUDA, ERR_BOUNDS, ERR_DEVICE = -100, -101, -102
 
 
+class WsolaStats(C.Structure):
+    _fields_ = [("frames", C.c_uint64), ("tier2_candidates", C.c_uint64), ("exact_evaluations", C.c_uint64),
+                ("walked_utterances", C.c_uint64), ("walked_frames", C.c_uint64)]
+
+
 class RunInfo(C.Structure):
     _fields_ = [
         ("kernel_launches", C.c_uint32), ("n_stretch", C.c_uint32),
@@ -59,7 +64,7 @@ def lib(build: bool = True) -> C.CDLL:
         L.ctts_gpu_plan_read_pcm.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64]
         L.ctts_gpu_plan_read_pre.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint64, u64p]
         L.ctts_gpu_plan_info.argtypes = [vp, C.POINTER(RunInfo)]
-        L.ctts_gpu_plan_wsola_stats.argtypes = [vp, vp, u64p, u64p]
+        L.ctts_gpu_plan_wsola_stats.argtypes = [vp, vp, C.POINTER(WsolaStats)]
         _lib = L
     return _lib
 
@@ -121,11 +126,11 @@ class ResidentPlan:
         self._ctx._check(lib().ctts_gpu_plan_read_pre(self._ctx._h, self._h, u, out.ctypes.data, cap, C.byref(n)))
         return out[:min(int(n.value), cap)]
 
-    def wsola_stats(self) -> tuple[int, int]:
-        """(frames searched, decisions that needed the exact correlation loop) of the last run."""
-        f, e = C.c_uint64(), C.c_uint64()
-        self._ctx._check(lib().ctts_gpu_plan_wsola_stats(self._ctx._h, self._h, C.byref(f), C.byref(e)))
-        return int(f.value), int(e.value)
+    def wsola_stats(self) -> WsolaStats:
+        """How the WSOLA frame chain of the last run was resolved (ctts_gpu_wsola_stats)."""
+        st = WsolaStats()
+        self._ctx._check(lib().ctts_gpu_plan_wsola_stats(self._ctx._h, self._h, C.byref(st)))
+        return st
 
     def utterances(self) -> list[np.ndarray]:
         """Convenience for tests: per-utterance PCM read back from the plan-owned buffer."""

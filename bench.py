@@ -370,9 +370,11 @@ def main() -> int:
             },
         }
         if args.workload == "mixed":
-            fr_n, ex_n = rp.wsola_stats()
-            line["config"]["wsola_frames"] = fr_n
-            line["config"]["wsola_exact_decisions"] = ex_n
+            ws = rp.wsola_stats()
+            line["config"]["wsola"] = {"frames": int(ws.frames), "tier2_candidates": int(ws.tier2_candidates),
+                                       "exact_evaluations": int(ws.exact_evaluations),
+                                       "chain_walked_utterances": int(ws.walked_utterances),
+                                       "chain_walked_frames": int(ws.walked_frames)}
         if e2e:
             line["e2e"] = {"value": e2e_audio_all / e2e_s_all, "unit": UNIT,
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],

@@ -102,10 +102,17 @@ int ctts_gpu_plan_read_pcm(ctts_gpu_ctx* ctx, ctts_gpu_plan* plan, int16_t* dst,
 int ctts_gpu_plan_read_pre(ctts_gpu_ctx* ctx, ctts_gpu_plan* plan, uint32_t u, int16_t* dst,
                            uint64_t cap, uint64_t* n);
 
-/* After a run: WSOLA frames searched over the batch, and how many of the (two per frame)
- * candidate decisions needed the reference's exact correlation loop after the FMA filter. */
-int ctts_gpu_plan_wsola_stats(ctts_gpu_ctx* ctx, ctts_gpu_plan* plan, uint64_t* frames,
-                              uint64_t* exact_decisions);
+/* After a run: how time_stretch's frame chain (ctts.c:3555-3592) was resolved.  The back end speculates
+ * every frame's analysis offset (the previous frame's, or -128 behind digital silence), verifies all frames
+ * independently, and walks the chain frame by frame only from an utterance's first unverified frame on. */
+typedef struct ctts_gpu_wsola_stats {
+    uint64_t frames;             /* WSOLA frames of the batch */
+    uint64_t tier2_candidates;   /* candidates the partial-sum bound could not reject (full 384-term filter score) */
+    uint64_t exact_evaluations;  /* ... of those, and of the chain walk's decisions: the reference's exact loop */
+    uint64_t walked_utterances;  /* utterances with an unverified frame */
+    uint64_t walked_frames;      /* frames decided by the chain walk */
+} ctts_gpu_wsola_stats;
+int ctts_gpu_plan_wsola_stats(ctts_gpu_ctx* ctx, ctts_gpu_plan* plan, ctts_gpu_wsola_stats* out);
 
 typedef struct ctts_gpu_run_info {
     uint32_t kernel_launches;    /* kernels enqueued by one ctts_gpu_plan_run */

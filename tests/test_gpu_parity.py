@@ -176,7 +176,7 @@ def test_resident_plan_is_idempotent(H, synth_small, oracle_small, front_small):
         want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(plan.speed[u]))
         _assert_same(b[u], want, f"resident utt {u}")
     info = rp.info()
-    assert info.kernel_launches == 3 and info.n_stretch == 4 and info.threads == 256
+    assert info.kernel_launches == 5 and info.n_stretch == 4 and info.threads == 256
     # pre-stretch buffer of a stretched utterance equals the oracle's
     _, _, pre = oracle_small.synth(prm, plan.utt_ops(9), 1.2, want_pre=True)
     _assert_same(rp.read_pre(9, len(pre) + 16), pre, "pre-stretch")
@@ -331,8 +331,11 @@ def test_mixed_speed_batch_properties(H, gpu):
     rp.run()
     assert np.array_equal(cnt, rp.counts().astype(np.int64))
     assert np.array_equal(pcm1, rp.read_pcm(0, rp.out_samples))
-    frames, exact = rp.wsola_stats()
-    assert frames > 0 and exact < 0.05 * 2 * frames      # the filter decides almost every frame
+    st = rp.wsola_stats()
+    # the speculated offsets hold on this workload: no chain is walked, tier 1 rejects almost every
+    # candidate (65 + 6 per frame) and the exact loop is rare
+    assert st.frames > 0 and st.walked_utterances == 0 and st.walked_frames == 0
+    assert st.tier2_candidates < 2 * st.frames and st.exact_evaluations < 0.05 * st.frames
     orc = H.Oracle(db)
     for u in range(0, 512, 37):
         want, st, pre = orc.synth(prm, plan.utt_ops(u), float(speeds[u]), want_pre=True)
@@ -345,21 +348,81 @@ def test_mixed_speed_batch_properties(H, gpu):
 
 def test_chunked_stretch_batch(H, gpu, small_db, oracle_small, front_small, monkeypatch):
     """ctts_gpu_synth_batch on a batch that mixes stretched and plain utterances, cut into several
-    launches of assemble -> WSOLA search -> overlap-add whose device->host copies overlap the next
-    chunk (CTTS_GPU_STRETCH_WAVE forces small waves); the result must not depend on the cut."""
+    launches of assemble -> WSOLA (scan, verify, chain walk, overlap-add) whose device->host copies overlap
+    the next chunk (CTTS_GPU_CHUNK_SAMPLES forces small chunks); the result must not depend on the cut."""
     prm = front_small.params()
     texts = H.corpus.batch(22, seed=53, target_chars=100) + ["", "olá mundo", "a"]
     speeds = [1.5, 1.0, 0.5, 2.0, 1.0, 0.7, 1.3, 1.0, 0.9, 1.1, 1.0, 1.7, 0.6, 1.0, 1.9, 0.8,
               1.0, 1.2, 1.4, 1.0, 1.6, 0.5, 1.5, 1.5, 1.0]
     plan = front_small.plan(texts, speeds)
     want = [oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))[0] for u in range(plan.n_utts)]
-    for wave in ("1", "3", "5", "1000"):
-        monkeypatch.setenv("CTTS_GPU_STRETCH_WAVE", wave)
+    for chunk in ("1", "300000", "1000000", "100000000"):
+        monkeypatch.setenv("CTTS_GPU_CHUNK_SAMPLES", chunk)
         g = gpu.GpuSynth(small_db, 0)
         outs = g.synth_list(plan, prm)
         for u in range(plan.n_utts):
-            _assert_same(outs[u], want[u], f"wave {wave} utt {u} speed {speeds[u]}")
-    monkeypatch.delenv("CTTS_GPU_STRETCH_WAVE")
+            _assert_same(outs[u], want[u], f"chunk {chunk} utt {u} speed {speeds[u]}")
+    monkeypatch.delenv("CTTS_GPU_CHUNK_SAMPLES")
+
+
+def test_wsola_chain_walk_from_unverified_frames(H, gpu, small_db, oracle_small, front_small, monkeypatch):
+    """The WSOLA frame chain (ctts.c:3555-3592) is speculated and verified frame by frame; where the
+    verification fails the chain is walked from that frame on (wsola_search_kernel).  Forced here:
+    every N-th frame reported as unverified (the walk starts in the middle of an utterance, with the
+    verified position before it), and speculation switched off (every chain walked from frame 1).
+    The PCM must not change."""
+    prm = front_small.params()
+    texts = H.corpus.batch(10, seed=97, target_chars=90) + ["olá mundo", "a", ""]
+    speeds = [1.5, 0.5, 2.0, 0.7, 1.3, 0.9, 1.1, 1.7, 0.6, 1.9, 1.5, 1.5, 1.5]
+    plan = front_small.plan(texts, speeds)
+    want = [oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))[0] for u in range(plan.n_utts)]
+    for env, val in (("CTTS_GPU_WSOLA_FORCE_BAD", "1"), ("CTTS_GPU_WSOLA_FORCE_BAD", "2"), ("CTTS_GPU_WSOLA_FORCE_BAD", "37"),
+                     ("CTTS_GPU_WSOLA_FORCE_BAD", "300"), ("CTTS_GPU_WSOLA_SPECULATE", "0")):
+        monkeypatch.setenv(env, val)
+        g = gpu.GpuSynth(small_db, 0)
+        rp = g.create_plan(plan, prm)
+        rp.run()
+        outs = rp.utterances()
+        for u in range(plan.n_utts):
+            _assert_same(outs[u], want[u], f"{env}={val} utt {u} speed {speeds[u]}")
+        st = rp.wsola_stats()
+        assert st.walked_utterances >= 10 and st.walked_frames > 0, (env, val, st.walked_utterances)
+        if env == "CTTS_GPU_WSOLA_SPECULATE":
+            assert st.walked_frames >= st.frames - plan.n_utts and st.tier2_candidates == 0
+        monkeypatch.delenv(env)
+    g = gpu.GpuSynth(small_db, 0)
+    rp = g.create_plan(plan, prm)
+    rp.run()
+    assert rp.wsola_stats().walked_utterances == 0
+
+
+def test_wsola_ties_on_an_exactly_periodic_voice(H, gpu):
+    """A voice whose units are exactly periodic (period 64 samples, no noise): inside a unit the candidate
+    windows one and two periods before the speculated one are the same samples, they score exactly 1.0f
+    too and win by scan order (ctts.c:3459 keeps the first maximum), so the speculated offsets are wrong
+    and the verification must notice: those utterances are resolved by the chain walk.  Bit-exact vs the oracle."""
+    rng = np.random.default_rng(5)
+    units = []
+    for ch in "abcdelmnoprstuv":
+        pattern = rng.integers(-9000, 9000, size=64)
+        n = int(rng.integers(3000, 6000))
+        units.append((ch, np.tile(pattern, n // 64 + 1)[:n].astype(np.int16)))
+    db = H.voicedb.build_voice_db(units)
+    fr = H.front.Front(db, H.shipped_config(), H.NORM_CSV)
+    prm = fr.params()
+    texts = ["a", "aba", "casa de pedra", "um pote de mel", "la no alto da serra, a lua nova"]
+    speeds = [1.5, 0.8, 1.7, 0.6, 1.3]
+    plan = fr.plan(texts, speeds)
+    orc = H.Oracle(db)
+    g = gpu.GpuSynth(db, 0)
+    rp = g.create_plan(plan, prm)
+    rp.run()
+    outs = rp.utterances()
+    for u in range(plan.n_utts):
+        want, _ = orc.synth(prm, plan.utt_ops(u), float(speeds[u]))
+        _assert_same(outs[u], want, f"periodic voice utt {u} speed {speeds[u]}")
+    st = rp.wsola_stats()
+    assert st.walked_utterances >= 2 and st.exact_evaluations > 0
 
 
 def test_target_rms_variants_share_a_context(H, synth_small, oracle_small, front_small):
@@ -407,7 +470,7 @@ def test_many_runs_of_one_plan_are_identical(H, gpu):
 def test_many_calls_of_the_drop_in_path_are_identical(H, gpu, monkeypatch):
     """The same for ctts_gpu_synth_batch on a batch that mixes speeds: chunks on several streams,
     per-chunk copies, arenas reused from call to call.  12 calls must return identical PCM."""
-    monkeypatch.setenv("CTTS_GPU_STRETCH_WAVE", "24")   # several chunks in flight
+    monkeypatch.setenv("CTTS_GPU_CHUNK_SAMPLES", "4000000")   # several chunks in flight
     db = H.synthetic_db()
     fr = H.front.Front(db, H.shipped_config(), H.NORM_CSV)
     prm = fr.params()
@@ -459,7 +522,6 @@ def test_streaming_call_hands_over_finished_ranges(H, gpu, small_db, oracle_smal
     prm = front_small.params()
     texts = H.corpus.batch(20, seed=71, target_chars=110) + ["", "olá mundo"]
     for speeds in ([1.0] * 22, [1.5, 1.0, 0.5, 2.0, 1.0, 0.7] * 3 + [1.3, 1.0, 0.9, 1.0]):
-        monkeypatch.setenv("CTTS_GPU_STRETCH_WAVE", "3")
         plan = front_small.plan(texts, speeds)
         g = gpu.GpuSynth(small_db, 0)
         seen, snap = [], {}

@@ -518,9 +518,15 @@ constexpr float WV_THR = 2.5e-4f;   // tier 1 rejects when the partial sum of (x
 static_assert(WV_SPAN % 4 == 0 && WV_BL % 4 == 0 && WV_B0 % 4 == 0 && WV_BSTEP % 4 == 0, "float4 alignment");
 static_assert(WV_B0 + (WV_NB - 1) * WV_BSTEP + WV_BL <= WS_OVERLAP, "blocks inside the window");
 
+// Shared-memory layout of the staged samples: 4 floats of padding after every 16, so that the 16-float
+// segments consecutive lanes start their float4 loads at (one group of 4 coarse candidates per lane) fall
+// on different banks (lane stride 80 bytes: 8 lanes of a quarter warp cover all 32 banks once).
+__host__ __device__ constexpr int wv_phys(int i) { return i + ((i >> 4) << 2); }
+
 struct WvSmem {
-    float xs[WV_SPAN + 16];                    // samples of the tile as floats (zero past the end of the input)
-    unsigned long long Pbuf[WV_SPAN + 8];      // P[i] = Pbuf[i + 3] = sum_{j<i} xs[j]^2, exact (P[4q + 1] is 16-byte aligned)
+    float xs[wv_phys(WV_SPAN + 16)];           // samples of the tile as floats (zero past the end of the input), padded layout
+    unsigned long long PQ[WV_QUADS + 1];       // PQ[j] = sum_{i < 4j} x[i]^2, exact
+    float e4[WV_QUADS + 4];                    // energy of quad j (float of the exact integer)
     float W4[WV_QUADS];                        // window energy at 4j (float of the exact integer)
     float G4[WV_QUADS];                        // energy of the tier-1 blocks of the window at 4j
     float Et[WV_FRAMES], Bt[WV_FRAMES];        // target: energy, block energy / energy
@@ -571,32 +577,44 @@ __global__ void __launch_bounds__(256) wsola_scan_kernel(const WsolaArgs A) {
     }
 }
 
-// tier 1 for one item = 4 candidates (window starts yb + STRIDE * j in the tile) against the target at
-// tb0: the cross terms of the WV_NB blocks, one FMA each, operand loads shared by the 4 candidates
-template <int STRIDE>
-__device__ __forceinline__ void wv_dots(const float* __restrict__ xs, int tb0, int yb, float (&d)[4]) {
+// tier 1 for one item = 4 candidates (window starts yb + SHIFT + STRIDE * j, yb a multiple of 16 in the tile)
+// against the target at tb0 (a multiple of 16): the cross terms of the WV_NB blocks, one FMA each, operand loads
+// shared by the 4 candidates.  y_head / y_tail: the first / last 3 squares sums needed to slide a block energy
+// by 1..3 samples (STRIDE == 1 only).
+template <int STRIDE, int SHIFT>
+__device__ __forceinline__ void wv_dots(const float* __restrict__ xs, int tb0, int yb, float (&d)[4], float (&slide)[4]) {
     d[0] = d[1] = d[2] = d[3] = 0.0f;
+    slide[0] = slide[1] = slide[2] = slide[3] = 0.0f;
     constexpr int TC = WV_BL / 4;                                 // target chunks per block
     constexpr int YC = STRIDE == 4 ? TC + 3 : TC + 1;             // candidate chunks per block
+    const float* tp = xs + wv_phys(tb0);
+    const float* yp = xs + wv_phys(yb);
 #pragma unroll
     for (int b = 0; b < WV_NB; b++) {
-        const float4* t4 = reinterpret_cast<const float4*>(xs + tb0 + WV_B0 + b * WV_BSTEP);
-        const float4* y4 = reinterpret_cast<const float4*>(xs + yb + WV_B0 + b * WV_BSTEP);
         float y[4 * YC];
 #pragma unroll
         for (int m = 0; m < YC; m++) {
-            const float4 v = y4[m];
+            const float4 v = *reinterpret_cast<const float4*>(yp + wv_phys(SHIFT + WV_B0 + b * WV_BSTEP + 4 * m));
             y[4 * m] = v.x; y[4 * m + 1] = v.y; y[4 * m + 2] = v.z; y[4 * m + 3] = v.w;
         }
 #pragma unroll
         for (int m = 0; m < TC; m++) {
-            const float4 t = t4[m];
+            const float4 t = *reinterpret_cast<const float4*>(tp + wv_phys(WV_B0 + b * WV_BSTEP + 4 * m));
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 d[j] = __fmaf_rn(t.x, y[STRIDE * j + 4 * m], d[j]);
                 d[j] = __fmaf_rn(t.y, y[STRIDE * j + 4 * m + 1], d[j]);
                 d[j] = __fmaf_rn(t.z, y[STRIDE * j + 4 * m + 2], d[j]);
                 d[j] = __fmaf_rn(t.w, y[STRIDE * j + 4 * m + 3], d[j]);
+            }
+        }
+        if (STRIDE == 1) {
+            // block energy of candidate j = that of candidate 0 + sum_{i<j} (y[BL + i]^2 - y[i]^2)
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 1; j < 4; j++) {
+                acc += y[WV_BL + j - 1] * y[WV_BL + j - 1] - y[j - 1] * y[j - 1];
+                slide[j] += acc;
             }
         }
     }
@@ -613,11 +631,12 @@ __device__ __forceinline__ void wv_dots(const float* __restrict__ xs, int tb0, i
 //
 // Error budget of tier 1.  With x^ = x/|x|, t^ = t/|t| (exact real arithmetic) the true correlation is
 // rho = 1 - |x^ - t^|^2 / 2 <= 1 - S/2, S = sum over the blocks of (x^_i - t^_i)^2 = A + B - 2C,
-// A = E_blocks(x)/E(x), B = E_blocks(t)/E(t) (ratios of exact integers, evaluated in float: relative
-// error < 4e-7 each incl. the approximate reciprocal), C = dot/sqrt(E(x)E(t)) (32 FMA terms, rsqrt.approx:
-// |error| <= (gamma_32 + 2^-22 + 3u) sqrt(AB) < 2.5e-6).  So |S~ - S| < 4e-6 (A, B <= 1), and the
-// reference's score r satisfies |r - rho| <= 2e-5, hence r <= 1 - S~/2 + 2e-6 + 2e-5 < 1
-// whenever S~ > 4.4e-5.  WV_THR is 2.5e-4.
+// A = E_blocks(x)/E(x), B = E_blocks(t)/E(t) (window energies exact integers from the prefix sum, block
+// energies float sums of <= 32 exact squares, approximate reciprocal: relative error < 3e-6 each incl. the
+// slid energies of the fine candidates), C = dot/sqrt(E(x)E(t)) (32 FMA terms, rsqrt.approx:
+// |error| <= (gamma_32 + 2^-22 + 3u) sqrt(AB) < 2.5e-6).  So |S~ - S| < 1e-5 (A, B <= 1), and the
+// reference's score r satisfies |r - rho| <= 2e-5, hence r <= 1 - S~/2 + 5e-6 + 2e-5 < 1
+// whenever S~ > 5e-5.  WV_THR is 2.5e-4.
 __global__ void __launch_bounds__(WV_THREADS, 3) wsola_verify_kernel(const WsolaArgs A) {
     extern __shared__ __align__(16) unsigned char wv_raw[];
     WvSmem& sm = *reinterpret_cast<WvSmem*>(wv_raw);
@@ -632,15 +651,17 @@ __global__ void __launch_bounds__(WV_THREADS, 3) wsola_verify_kernel(const Wsola
     const uint32_t F = A.first_silent[ti];
     const uint32_t base = (k0 - 1u) * WS_HOP;               // tile sample 0 = input sample base
 
-    // ---- stage the tile as floats and build the exact prefix sum of squares.  Thread t owns the
-    //      quads t, t + 256, ..: consecutive lanes touch consecutive 16 / 32 byte pieces.
+    // ---- stage the tile as floats; exact prefix sum of squares at every 4th sample.  Thread t owns the
+    //      quads t, t + 256, ..
     if (tid == 0) {
         sm.n_list = 0;
         sm.bad = 0xffffffffu;
-        sm.Pbuf[3] = 0ull;
+        sm.PQ[0] = 0ull;
     }
-    unsigned long long* const P = sm.Pbuf + 3;
-    if (tid < 4) *reinterpret_cast<float4*>(sm.xs + WV_SPAN + 4 * tid) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < 4) {
+        *reinterpret_cast<float4*>(sm.xs + wv_phys(WV_SPAN + 4 * tid)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        sm.e4[WV_QUADS + tid] = 0.0f;
+    }
     unsigned long long carry = 0ull;
     for (int q0 = 0; q0 < WV_QUADS; q0 += WV_THREADS) {
         const int q = q0 + tid;
@@ -656,10 +677,10 @@ __global__ void __launch_bounds__(WV_THREADS, 3) wsola_verify_kernel(const Wsola
                 if (p + 1u < n) v1 = in[p + 1];
                 if (p + 2u < n) v2 = in[p + 2];
             }
-            *reinterpret_cast<float4*>(sm.xs + 4 * q) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
+            *reinterpret_cast<float4*>(sm.xs + wv_phys(4 * q)) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
         }
-        const unsigned long long s0 = (unsigned long long)(uint32_t)(v0 * v0), s1 = s0 + (uint32_t)(v1 * v1),
-                                 s2 = s1 + (uint32_t)(v2 * v2), s3 = s2 + (uint32_t)(v3 * v3);
+        const unsigned long long s3 = (unsigned long long)(uint32_t)(v0 * v0) + (uint32_t)(v1 * v1) +
+                                      (unsigned long long)(uint32_t)(v2 * v2) + (uint32_t)(v3 * v3);
         unsigned long long inc = s3;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -677,49 +698,40 @@ __global__ void __launch_bounds__(WV_THREADS, 3) wsola_verify_kernel(const Wsola
         }
         carry = all;
         if (q < WV_QUADS) {
-            const unsigned long long e = pre + inc - s3;   // exclusive prefix at the quad's first sample
-            ulonglong2 a, b;
-            a.x = e + s0; a.y = e + s1;
-            b.x = e + s2; b.y = e + s3;
-            ulonglong2* dst = reinterpret_cast<ulonglong2*>(P + 4 * q + 1);
-            dst[0] = a;
-            dst[1] = b;
+            sm.PQ[q + 1] = pre + inc;
+            sm.e4[q] = ws_u64_to_float(s3);   // < 2^32: two roundings of 2^-24
         }
         __syncthreads();
     }
 
-    auto energy = [&](int p, int len) { return ws_u64_to_float(P[p + len] - P[p]); };
-    auto blocks = [&](int p) {
-        unsigned long long e = 0ull;
-#pragma unroll
-        for (int b = 0; b < WV_NB; b++) e += P[p + WV_B0 + b * WV_BSTEP + WV_BL] - P[p + WV_B0 + b * WV_BSTEP];
-        return ws_u64_to_float(e);
-    };
-    // ---- window / block energies at every 4th sample (the coarse candidates), per-frame quantities
+    // ---- window energies (exact) and tier-1 block energies at every 4th sample
     for (int j = tid; j < WV_QUADS; j += WV_THREADS) {
         float w = 0.0f, g = 0.0f;
         if (4 * j + WS_OVERLAP <= WV_SPAN) {
-            w = energy(4 * j, WS_OVERLAP);
-            g = blocks(4 * j);
+            w = ws_u64_to_float(sm.PQ[j + WS_OVERLAP / 4] - sm.PQ[j]);
+#pragma unroll
+            for (int b = 0; b < WV_NB; b++)
+#pragma unroll
+                for (int m = 0; m < WV_BL / 4; m++) g += sm.e4[j + (WV_B0 + b * WV_BSTEP) / 4 + m];
         }
         sm.W4[j] = w;
         sm.G4[j] = g;
     }
+    __syncthreads();
     if (tid < WV_FRAMES) {
         const uint32_t k = k0 + (uint32_t)tid;
         int h = INT_MIN;
         if (k < frames) {
             h = k <= F ? 0 : -WS_SHIFT;
             const int ts = WS_HOP * tid + WS_SHIFT + h;
-            const unsigned long long e = P[ts + WS_OVERLAP] - P[ts];
-            uint32_t pos = k * WS_HOP + (uint32_t)(h + 0);
-            if (e == 0ull) {   // digital silence behind the frame: offset -128, nothing to verify
+            const float et = sm.W4[ts >> 2];            // float of the exact integer: 0 iff all zero
+            uint32_t pos = k * WS_HOP + (uint32_t)h;
+            if (et == 0.0f) {   // digital silence behind the frame: offset -128, nothing to verify
                 pos = k * WS_HOP - WS_SHIFT;
                 h = INT_MIN;
             } else {
-                const float et = ws_u64_to_float(e);
                 sm.Et[tid] = et;
-                sm.Bt[tid] = __fdividef(blocks(ts), et);
+                sm.Bt[tid] = __fdividef(sm.G4[ts >> 2], et);
             }
             if (A.force_bad && k % A.force_bad == 0) atomicMin(&sm.bad, k);
             A.frame_pos[task.pos_off + k] = pos;
@@ -747,28 +759,42 @@ __global__ void __launch_bounds__(WV_THREADS, 3) wsola_verify_kernel(const Wsola
         else { o0 = h; stride = 1; live = 0xeu; }                                   // h+1 .. h+3
         if (!live) continue;
         const int yb = v + WS_SHIFT + o0;
-        float d[4], w[4], gb[4];
+        float d[4], w[4], gb[4], slide[4];
+        float w4base = 0.0f;
         if (stride == 4) {
-            wv_dots<4>(sm.xs, ts, yb, d);
+            wv_dots<4, 0>(sm.xs, ts, yb, d, slide);
             const float4 w4 = *reinterpret_cast<const float4*>(sm.W4 + (yb >> 2));
             const float4 g4 = *reinterpret_cast<const float4*>(sm.G4 + (yb >> 2));
             w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
             gb[0] = g4.x; gb[1] = g4.y; gb[2] = g4.z; gb[3] = g4.w;
         } else {
-            wv_dots<1>(sm.xs, ts, yb, d);
-#pragma unroll
-            for (int j = 1; j < 4; j++) {
-                w[j] = energy(yb + j, WS_OVERLAP);
-                gb[j] = blocks(yb + j);
-            }
+            if (g == 17) wv_dots<1, 12>(sm.xs, ts, yb - 12, d, slide);   // yb = 12 mod 16
+            else wv_dots<1, 0>(sm.xs, ts, yb, d, slide);
+            // energies of the windows at yb + 1 .. yb + 3 from the one at yb (a multiple of 4):
+            // drop the first j samples, take j more at the end
+            const float4 x0 = *reinterpret_cast<const float4*>(sm.xs + wv_phys(yb));
+            const float4 x1 = *reinterpret_cast<const float4*>(sm.xs + wv_phys(yb + WS_OVERLAP));
+            const float wb = sm.W4[yb >> 2], gq = sm.G4[yb >> 2];
+            w4base = wb;
             w[0] = gb[0] = 0.0f;
+            w[1] = wb + (x1.x * x1.x - x0.x * x0.x);
+            w[2] = w[1] + (x1.y * x1.y - x0.y * x0.y);
+            w[3] = w[2] + (x1.z * x1.z - x0.z * x0.z);
+#pragma unroll
+            for (int j = 1; j < 4; j++) gb[j] = gq + slide[j];
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int o = o0 + stride * j;
             if (!((live >> j) & 1u) || o == h || o > room) continue;   // not a candidate / the target itself / out of bounds
-            if (w[j] == 0.0f) continue;                                // zero energy: the score is exactly 0 (ctts.c:3426)
-            const float s = __fdividef(gb[j], w[j]) + bt - 2.0f * d[j] * rsqrt_approx(w[j] * et);
+            // zero energy: the score is exactly 0 (ctts.c:3426).  (A slid energy is a float difference: anything
+            // below one sample's worth is treated as inconclusive rather than trusted.)
+            if (stride == 4 && w[j] == 0.0f) continue;
+            // (a slid window energy is trusted only while it has not lost most of the energy it was slid
+            // from -- cancellation: its relative error is then < 8 * 3 * 2^-24)
+            float s = -1.0f;
+            if (w[j] >= 1.0f && (stride == 4 || w[j] >= 0.125f * w4base))
+                s = __fdividef(gb[j], w[j]) + bt - 2.0f * d[j] * rsqrt_approx(w[j] * et);
             if (!(s > WV_THR)) {
                 const uint32_t slot = atomicAdd(&sm.n_list, 1u);
                 if (slot < (uint32_t)WV_LIST) sm.list[slot] = ((uint32_t)f << 16) | (uint32_t)(o + WS_SHIFT);
@@ -784,25 +810,38 @@ __global__ void __launch_bounds__(WV_THREADS, 3) wsola_verify_kernel(const Wsola
     for (uint32_t e = warp; e < n_list; e += WV_THREADS / 32) {
         const uint32_t ent = sm.list[e];
         const int f = (int)(ent >> 16), xo = (int)(ent & 0xffffu);   // xo = offset + 128: window start inside the view
-        const float* tg = sm.xs + WS_HOP * f + WS_SHIFT + sm.hyp[f];
-        const float* xc = sm.xs + WS_HOP * f + xo;
-        float dot = 0.0f;
+        const int tg = WS_HOP * f + WS_SHIFT + sm.hyp[f], xc = WS_HOP * f + xo;
+        float dot = 0.0f, ea = 0.0f;
 #pragma unroll
-        for (int q = 0; q < WS_OVERLAP / 32; q++) dot = __fmaf_rn(tg[lane + 32 * q], xc[lane + 32 * q], dot);
+        for (int q = 0; q < WS_OVERLAP / 32; q++) {
+            const float a = sm.xs[wv_phys(xc + lane + 32 * q)];
+            dot = __fmaf_rn(sm.xs[wv_phys(tg + lane + 32 * q)], a, dot);
+            ea = __fmaf_rn(a, a, ea);
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        const float sa = energy(WS_HOP * f + xo, WS_OVERLAP);
+        for (int o = 16; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            ea += __shfl_xor_sync(0xffffffffu, ea, o);
+        }
+        // the candidate's energy: exact where the window starts on a quad, else a float sum of exact squares
+        // (relative error < 2e-6, far inside the filter's eps)
+        const float sa = (xc & 3) == 0 ? sm.W4[xc >> 2] : ea;
+        if (sa == 0.0f) continue;                        // all zero: the score is exactly 0
         // the full FMA filter score: within 2e-5 of the reference's (eps = 1e-4 as in the chain kernel)
         const float a = dot * rsqrt_approx(sa * sm.Et[f]);
         if (a + WS_EPS < 1.0f) continue;
         // tier 3: the reference's loop; lanes 0..2 form sum_prod, sum_sq1, sum_sq2 (ctts.c:3411-3413)
         float acc = 0.0f;
         if (lane < 3) {
-            const float* p = lane == 2 ? tg : xc;
-            const float* q = lane == 1 ? xc : tg;
+            const int p = lane == 2 ? tg : xc, q = lane == 1 ? xc : tg;
 #pragma unroll 2
-            for (int m = 0; m < WS_OVERLAP / 4; m++)
-                acc += p[4 * m] * q[4 * m] + p[4 * m + 1] * q[4 * m + 1] + p[4 * m + 2] * q[4 * m + 2] + p[4 * m + 3] * q[4 * m + 3];
+            for (int m = 0; m < WS_OVERLAP / 4; m++) {
+                const float p0 = sm.xs[wv_phys(p + 4 * m)], p1 = sm.xs[wv_phys(p + 4 * m + 1)], p2 = sm.xs[wv_phys(p + 4 * m + 2)],
+                            p3 = sm.xs[wv_phys(p + 4 * m + 3)];
+                const float q0 = sm.xs[wv_phys(q + 4 * m)], q1 = sm.xs[wv_phys(q + 4 * m + 1)], q2 = sm.xs[wv_phys(q + 4 * m + 2)],
+                            q3 = sm.xs[wv_phys(q + 4 * m + 3)];
+                acc += p0 * q0 + p1 * q1 + p2 * q2 + p3 * q3;
+            }
         }
         const float sp = __shfl_sync(0xffffffffu, acc, 0), s1 = __shfl_sync(0xffffffffu, acc, 1), s2 = __shfl_sync(0xffffffffu, acc, 2);
         const float den = sqrtf(s1 * s2);
@@ -834,10 +873,13 @@ __host__ __device__ inline uint32_t ola_block_span(uint32_t hop) {
 // w[q * hop + c] is the same for all of its outputs, and walking q downwards adds the frames of
 // every output in ascending frame order, which is the order the reference accumulates the float
 // norm in (the int16 accumulator wraps, ctts.c:3577: it is the 32-bit sum mod 2^16).
+constexpr int OLA_STAGE = WS_HOP * (OLA_THREADS / 64) * OLA_SPT + 1536;   // input samples an interior block can touch (hop >= 64)
+
 __global__ void __launch_bounds__(OLA_THREADS) wsola_ola_kernel(const WsolaArgs A) {
     __shared__ int s_last[OLA_THREADS / 32];
     __shared__ float win[WS_FRAME];
     __shared__ uint32_t sfp[(OLA_THREADS / 64) * OLA_SPT + 8];
+    __shared__ __align__(16) float xin[OLA_STAGE + 8];
     const int tid = threadIdx.x;
     for (int i = tid; i < WS_FRAME; i += OLA_THREADS) win[i] = __ldg(A.hann512 + i);
     const uint32_t ti = A.ola_block_task[blockIdx.x];
@@ -852,6 +894,81 @@ __global__ void __launch_bounds__(OLA_THREADS) wsola_ola_kernel(const WsolaArgs 
     int16_t* out = A.out + task.out_off;
     const uint32_t first = A.ola_block_first[blockIdx.x];
     int last_nz = -1;
+    const uint32_t groups_ = hop >= 64 && hop <= (uint32_t)OLA_THREADS ? (uint32_t)OLA_THREADS / hop : 0u;
+    const uint32_t row0_ = groups_ ? first / hop : 0u;
+    // INTERIOR block: every output is covered by whole frames that all exist (no start / end effects), so
+    // the norm of an output depends on its residue alone and the frames' input span is bounded: the span is
+    // staged once as floats (an input sample feeds 4 frames x up to 2 outputs), the per-thread norm and its
+    // reciprocal are loop invariants, and a contribution costs a shared load, a multiply, a truncation, an add.
+    if (groups_ && row0_ >= 7 && row0_ + groups_ * OLA_SPT - 1 <= frames - 1 && first + groups_ * OLA_SPT * hop <= lim) {
+        const uint32_t groups = groups_, row0 = row0_;
+        const uint32_t n_in = A.pre_counts[task.utt];
+        for (uint32_t i = tid; i < groups * OLA_SPT + 7; i += OLA_THREADS) sfp[i] = __ldg(fpos + (row0 - 7 + i));
+        // frame k sits at 128 k + offset, |offset| <= 128 (and never past n - 512)
+        const uint32_t s0 = (row0 - 7) * WS_HOP - WS_SHIFT;   // row0 >= 7, multiple of 8
+        const uint32_t span = WS_HOP * (groups * OLA_SPT + 6) + 2 * WS_SHIFT + WS_FRAME;   // <= OLA_STAGE
+        for (uint32_t v = tid; v < span / 8; v += OLA_THREADS) {
+            const uint32_t p = s0 + 8 * v;
+            int4 q = make_int4(0, 0, 0, 0);
+            if (p + 8 <= n_in) q = *reinterpret_cast<const int4*>(in + p);
+            else if (p < n_in) {
+                int16_t* e = reinterpret_cast<int16_t*>(&q);
+                for (uint32_t k = 0; k < 8 && p + k < n_in; k++) e[k] = in[p + k];
+            }
+            float4 a, b;
+            a.x = (float)(short)((uint32_t)q.x & 0xffffu); a.y = (float)(short)((uint32_t)q.x >> 16);
+            a.z = (float)(short)((uint32_t)q.y & 0xffffu); a.w = (float)(short)((uint32_t)q.y >> 16);
+            b.x = (float)(short)((uint32_t)q.z & 0xffffu); b.y = (float)(short)((uint32_t)q.z >> 16);
+            b.z = (float)(short)((uint32_t)q.w & 0xffffu); b.w = (float)(short)((uint32_t)q.w >> 16);
+            *(reinterpret_cast<float4*>(xin) + 2 * v) = a;
+            *(reinterpret_cast<float4*>(xin) + 2 * v + 1) = b;
+        }
+        __syncthreads();
+        const uint32_t g = (uint32_t)tid / hop, c = (uint32_t)tid - g * hop;
+        if (g < groups) {
+            const uint32_t rowbase = row0 + g * OLA_SPT;
+            // positions (relative to the staged span) of frames rowbase - 7 .. rowbase + 7
+            int fpr[2 * OLA_SPT - 1];
+            bool inside = true;
+#pragma unroll
+            for (int k = 0; k < 2 * OLA_SPT - 1; k++) {
+                fpr[k] = (int)(sfp[g * OLA_SPT + k] - s0);
+                inside &= fpr[k] >= 0 && fpr[k] + WS_FRAME <= (int)span;
+            }
+            const int qmax = (int)((WS_FRAME - 1) / hop);   // <= 7
+            float nrm = 0.0f;
+            int acc[OLA_SPT];
+#pragma unroll
+            for (int r = 0; r < OLA_SPT; r++) acc[r] = 0;
+#pragma unroll
+            for (int q = OLA_SPT - 1; q >= 0; q--) {
+                const uint32_t i = (uint32_t)q * hop + c;
+                if (q <= qmax && i < (uint32_t)WS_FRAME) {
+                    const float wv = win[i];
+                    nrm += wv;                       // ascending frame order, as the reference accumulates it (ctts.c:3578)
+                    if (inside) {
+#pragma unroll
+                        for (int r = 0; r < OLA_SPT; r++)   // |x * w| <= 32767: the int32 truncation is the int16 value
+                            acc[r] += (int)(xin[fpr[r - q + OLA_SPT - 1] + (int)i] * wv);
+                    } else {                          // (a frame outside the analytic span: cannot happen, kept for safety)
+#pragma unroll
+                        for (int r = 0; r < OLA_SPT; r++)
+                            acc[r] += (int)((float)in[sfp[g * OLA_SPT + r - q + OLA_SPT - 1] + i] * wv);
+                    }
+                }
+            }
+            const bool norm_ok = nrm > 0.01f;
+            const float rn = recip_for_div(norm_ok ? nrm : 1.0f);
+#pragma unroll
+            for (int r = 0; r < OLA_SPT; r++) {
+                const uint32_t j = (rowbase + (uint32_t)r) * hop + c;
+                const int a16 = (int)(int16_t)acc[r];
+                const int y = norm_ok ? cvt_sat_s16(div_by((float)a16, nrm, rn)) : a16;
+                out[j] = (int16_t)y;
+                if (y != 0) last_nz = (int)j;
+            }
+        }
+    } else
     if (hop >= 64 && hop <= (uint32_t)OLA_THREADS) {
         const uint32_t groups = (uint32_t)OLA_THREADS / hop;
         const uint32_t row0 = first / hop;   // exact: first is a multiple of the block span

@@ -1,6 +1,7 @@
 """In-tree builds of the native libraries (no JIT cache: the .so files travel with the repo).
 
 libctts_front.so  plain C host front end (gcc)
+libctts_b200.so   texts -> PCM: planner threads feeding a device session, plain C over the two libraries (gcc)
 libctts_gpu.so    C-ABI + hand-written sm_100a kernels (nvcc, -fmad=false: the
                   reference is built without FMA contraction and discrete
                   decisions flip on 1-ulp differences)
@@ -19,6 +20,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 
 FRONT_SO = os.path.join(PKG_DIR, "libctts_front.so")
 GPU_SO = os.path.join(PKG_DIR, "libctts_gpu.so")
+PIPE_SO = os.path.join(PKG_DIR, "libctts_b200.so")
 CLI_BIN = os.path.join(PKG_DIR, "ctts_b200")
 
 NVCC_FLAGS = [
@@ -80,15 +82,30 @@ def build_gpu(force: bool = False, verbose: bool = False) -> str:
     return GPU_SO
 
 
-def build_cli(force: bool = False) -> str:
-    """The plain-C drop-in command line (csrc/cli/ctts_b200.c) linked against the two libraries."""
-    src = os.path.join(CSRC, "cli", "ctts_b200.c")
+def build_pipeline(force: bool = False) -> str:
+    """libctts_b200.so: ctts_b200_synth_texts (csrc/cli/ctts_pipeline.c) over the two libraries."""
+    src = os.path.join(CSRC, "cli", "ctts_pipeline.c")
     deps = [src, FRONT_SO, GPU_SO] + _headers()
+    if not force and _newer(PIPE_SO, deps):
+        return PIPE_SO
+    cc = shutil.which("gcc") or "cc"
+    cmd = [cc, "-O2", "-std=gnu99", "-Wall", "-Wextra", "-fPIC", "-shared", "-I", INCLUDE, "-o", PIPE_SO, src,
+           "-L", PKG_DIR, "-lctts_front", "-lctts_gpu", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link," + PKG_DIR,
+           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lpthread", "-lm"]
+    subprocess.run(cmd, check=True)
+    return PIPE_SO
+
+
+def build_cli(force: bool = False) -> str:
+    """The plain-C drop-in command line (csrc/cli/ctts_b200.c) linked against the three libraries."""
+    src = os.path.join(CSRC, "cli", "ctts_b200.c")
+    build_pipeline(force)
+    deps = [src, FRONT_SO, GPU_SO, PIPE_SO] + _headers()
     if not force and _newer(CLI_BIN, deps):
         return CLI_BIN
     cc = shutil.which("gcc") or "cc"
     cmd = [cc, "-O2", "-std=gnu99", "-Wall", "-Wextra", "-I", INCLUDE, "-o", CLI_BIN, src,
-           "-L", PKG_DIR, "-lctts_front", "-lctts_gpu", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link," + PKG_DIR,
+           "-L", PKG_DIR, "-lctts_b200", "-lctts_front", "-lctts_gpu", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link," + PKG_DIR,
            "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lm"]
     subprocess.run(cmd, check=True)
     return CLI_BIN

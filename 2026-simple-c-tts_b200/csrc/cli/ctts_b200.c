@@ -8,8 +8,9 @@
  * Like the reference it reads config.yaml and normalization.csv from the working directory
  * (ctts.c:3990, :3636), clamps the speed to [0.5, 2.0] (ctts.c:3976-3981) and takes default_speed
  * from the config when none is given (ctts.c:3993).  ctts_b200_synthesize_batch() below is the
- * glue INTEGRATION.md describes (text -> plan -> one ctts_gpu_synth_batch call -> per-utterance
- * PCM); everything that touches samples runs on the GPU, and without a CUDA device it fails.
+ * glue INTEGRATION.md describes (texts -> ctts_b200_synth_texts: planner threads feeding a device
+ * session -> per-utterance PCM); everything that touches samples runs on the GPU, and without a CUDA
+ * device it fails.
  */
 #include <errno.h>
 #include <stdio.h>
@@ -17,8 +18,7 @@
 #include <string.h>
 #include <sys/stat.h>
 
-#include "ctts_front.h"
-#include "ctts_gpu.h"
+#include "ctts_b200.h"
 
 #define SAMPLE_RATE CTTS_PLAN_SAMPLE_RATE
 
@@ -81,31 +81,25 @@ static int write_wav(const char* path, const int16_t* samples, size_t count) {
     return fclose(f) == 0 ? 0 : -1;
 }
 
-/* N texts -> N PCM spans of one pinned buffer: *pcm (release with ctts_gpu_host_free), off[u]
- * (n + 1 entries, malloc'ed) and cnt[u] (malloc'ed); stats may be NULL (2n: found, missing).
- * on_chunk (may be NULL) is called as soon as a range of utterances is in host memory; it finds
- * the three arrays through *pcm, *off, *cnt, which are set before the device starts. */
+/* N texts -> N PCM spans of one pinned buffer through ctts_b200_synth_texts (the front end's planner threads
+ * feed the device piece by piece): *pcm (release with ctts_gpu_host_free), off[u] and cnt[u] (malloc'ed, n
+ * entries each); stats may be NULL (2n: found, missing).  on_chunk (may be NULL) is called as soon as a range of
+ * utterances is in host memory; it finds the three arrays through *pcm, *off, *cnt, which are set before the
+ * device starts. */
 static int ctts_b200_synthesize_batch(engine* e, const char* const* texts, const float* speeds, uint32_t n,
                                       int16_t** pcm, uint64_t** off, uint32_t** cnt, uint32_t* stats,
                                       ctts_gpu_chunk_fn on_chunk, void* user) {
-    ctts_batch_plan plan;
-    ctts_assembly_params prm;
-    int rc = ctts_front_plan_batch(e->front, texts, speeds, n, &plan, stats);
-    if (rc) return rc;
-    ctts_front_params(e->front, &prm);
-    uint64_t* bound = malloc(sizeof *bound * (n ? n : 1));
+    int rc = 0;
+    const uint64_t cap = ctts_b200_capacity_hint(e->front, texts, speeds, n);   /* replaces the SampleBuffer growth policy */
     *off = malloc(sizeof **off * ((size_t)n + 1));
     *cnt = calloc(n ? n : 1, sizeof **cnt);
-    *pcm = NULL;
-    if (!bound || !*off || !*cnt) rc = CTTS_GPU_ERR_OUT_OF_MEMORY;
-    if (!rc) rc = ctts_gpu_plan_bounds(e->gpu, &plan, bound);   /* replaces the SampleBuffer growth policy */
-    if (!rc) {
-        (*off)[0] = 0;
-        for (uint32_t u = 0; u < n; u++) (*off)[u + 1] = (*off)[u] + ((bound[u] + 7) & ~7ull) + 8;   /* 16-byte slots */
-        *pcm = ctts_gpu_host_alloc(sizeof(int16_t) * ((*off)[n] ? (*off)[n] : 8));
-        if (!*pcm) rc = CTTS_GPU_ERR_OUT_OF_MEMORY;
-    }
-    if (!rc) rc = ctts_gpu_synth_batch_stream(e->gpu, &plan, &prm, *pcm, *off, *cnt, on_chunk, user);
+    *pcm = ctts_gpu_host_alloc(sizeof(int16_t) * (cap ? cap : 8));
+    if (!*off || !*cnt || !*pcm) rc = CTTS_GPU_ERR_OUT_OF_MEMORY;
+    ctts_b200_options opt;
+    memset(&opt, 0, sizeof opt);
+    opt.on_piece = on_chunk;
+    opt.user = user;
+    if (!rc) rc = ctts_b200_synth_texts(e->front, e->gpu, texts, speeds, n, *pcm, cap, *off, *cnt, stats, NULL, &opt, NULL);
     if (rc) {
         fprintf(stderr, "synthesis failed: %d %s\n", rc, ctts_gpu_last_error(e->gpu));
         ctts_gpu_host_free(*pcm);
@@ -113,8 +107,6 @@ static int ctts_b200_synthesize_batch(engine* e, const char* const* texts, const
         free(*cnt);
         *pcm = NULL; *off = NULL; *cnt = NULL;
     }
-    free(bound);
-    ctts_front_plan_free(&plan);
     return rc;
 }
 
@@ -155,6 +147,7 @@ static int cmd_synth(int argc, char** argv) {
  * working on later ones): state shared with the chunk callback */
 typedef struct {
     const char* dir;
+    uint32_t base;   /* first utterance of the group being synthesised */
     int16_t** pcm;
     uint64_t** off;
     uint32_t** cnt;
@@ -166,7 +159,7 @@ static void write_chunk(void* user, uint32_t u0, uint32_t u1) {
     wav_sink* w = user;
     for (uint32_t u = u0; u < u1 && !w->rc; u++) {
         char path[4096];
-        snprintf(path, sizeof path, "%s/%06u.wav", w->dir, u);
+        snprintf(path, sizeof path, "%s/%06u.wav", w->dir, w->base + u);
         w->rc = write_wav(path, *w->pcm + (*w->off)[u], (*w->cnt)[u]);
         w->seconds += (double)(*w->cnt)[u] / SAMPLE_RATE;
     }
@@ -212,16 +205,22 @@ static int cmd_synth_batch(int argc, char** argv) {
     int16_t* pcm;
     uint64_t* off;
     uint32_t* cnt;
-    wav_sink sink = {argv[4], &pcm, &off, &cnt, 0.0, 0};
-    int rc = ctts_b200_synthesize_batch(&e, (const char* const*)texts, speeds, n, &pcm, &off, &cnt, NULL, write_chunk, &sink);
-    if (!rc) {
-        rc = sink.rc;
-        if (rc) fprintf(stderr, "Failed to write WAV files into %s\n", argv[4]);
-        else printf("Synthesized %u utterances (%.1f seconds of audio) into %s\n", n, sink.seconds, argv[4]);
-        ctts_gpu_host_free(pcm);
-        free(off);
-        free(cnt);
+    wav_sink sink = {argv[4], 0, &pcm, &off, &cnt, 0.0, 0};
+    /* groups of 1024 utterances: the pinned buffer is sized from the texts alone (ctts_b200_capacity_hint) */
+    int rc = 0;
+    for (uint32_t g0 = 0; g0 < n && !rc; g0 += 1024) {
+        const uint32_t gn = n - g0 < 1024 ? n - g0 : 1024;
+        sink.base = g0;
+        rc = ctts_b200_synthesize_batch(&e, (const char* const*)texts + g0, speeds + g0, gn, &pcm, &off, &cnt, NULL, write_chunk, &sink);
+        if (!rc) {
+            rc = sink.rc;
+            ctts_gpu_host_free(pcm);
+            free(off);
+            free(cnt);
+        }
     }
+    if (rc) fprintf(stderr, "Failed to write WAV files into %s\n", argv[4]);
+    else printf("Synthesized %u utterances (%.1f seconds of audio) into %s\n", n, sink.seconds, argv[4]);
     for (uint32_t u = 0; u < n; u++) free(texts[u]);
     free(texts);
     free(speeds);

@@ -1,0 +1,186 @@
+/*
+ * ctts_pipeline.c -- ctts_b200_synth_texts (include/ctts_b200.h): the text front end pipelined into the GPU
+ * back end.  Plain C + pthreads over the two C-ABI libraries.
+ *
+ * The reference's ctts_synthesize (ctts.c:3623) does, per utterance, normalisation (:3638-3655), the walk
+ * with unit selection (:3689-3871, :1406) and every sample loop in one call on one core.  Here:
+ *   planner threads   take pieces (128 utterances) off a shared counter and plan them with the unchanged
+ *                     front end (ctts_front_plan_batch_threads(..., 1, ...): re-entrant, the handle is only
+ *                     read), at most LOOKAHEAD pieces ahead of the device;
+ *   the calling thread submits finished plans in order to a ctts_gpu_session (asynchronous: up to three
+ *                     pieces are compiled / assembled / copied at any time) and frees them.
+ * Nothing here touches a sample.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "ctts_b200.h"
+
+#define LOOKAHEAD 24   /* pieces planned ahead of the one being submitted (bounds the memory held in plans) */
+
+typedef struct {
+    ctts_batch_plan plan;
+    int state;   /* 0: not planned, 1: planned, <0: error code */
+} piece_slot;
+
+typedef struct {
+    ctts_front* front;
+    const char* const* texts;
+    const float* speeds;
+    uint32_t* stats;
+    uint32_t n, piece_utts, n_pieces;
+    piece_slot* slots;
+    pthread_mutex_t mu;
+    pthread_cond_t cv_ready;   /* a piece became ready */
+    pthread_cond_t cv_room;    /* the submitter moved on */
+    uint32_t next;             /* next piece to plan */
+    uint32_t consumed;         /* pieces the submitter is done with */
+    int stop;
+    double t0, first_plan_s, all_plans_s;
+    uint32_t planned;
+} pipeline;
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static void* planner(void* arg) {
+    pipeline* P = arg;
+    for (;;) {
+        pthread_mutex_lock(&P->mu);
+        while (!P->stop && P->next < P->n_pieces && P->next >= P->consumed + LOOKAHEAD) pthread_cond_wait(&P->cv_room, &P->mu);
+        if (P->stop || P->next >= P->n_pieces) {
+            pthread_mutex_unlock(&P->mu);
+            return NULL;
+        }
+        const uint32_t i = P->next++;
+        pthread_mutex_unlock(&P->mu);
+        const uint32_t u0 = i * P->piece_utts, cnt = (u0 + P->piece_utts <= P->n ? P->piece_utts : P->n - u0);
+        ctts_batch_plan pl;
+        int rc = ctts_front_plan_batch_threads(P->front, P->texts + u0, P->speeds ? P->speeds + u0 : NULL, cnt, 1, &pl,
+                                               P->stats ? P->stats + 2 * (size_t)u0 : NULL);
+        pthread_mutex_lock(&P->mu);
+        if (rc == 0) {
+            P->slots[i].plan = pl;
+            P->slots[i].state = 1;
+        } else {
+            P->slots[i].state = rc < 0 ? rc : -1;
+        }
+        const double t = now_s() - P->t0;
+        if (P->planned++ == 0) P->first_plan_s = t;
+        P->all_plans_s = t;
+        pthread_cond_broadcast(&P->cv_ready);
+        pthread_mutex_unlock(&P->mu);
+    }
+}
+
+uint64_t ctts_b200_capacity_hint(ctts_front* front, const char* const* texts, const float* speeds, uint32_t n) {
+    if (!front || (n && !texts)) return 0;
+    /* every character yields at most one unit or one pause; pauses are shorter than the longest unit for
+     * any sane config, but take the larger of the two anyway */
+    uint64_t per_char = ctts_front_max_unit_samples(front);
+    if (per_char < 8192) per_char = 8192;
+    uint64_t total = 0;
+    for (uint32_t u = 0; u < n; u++) {
+        uint64_t chars = 8;
+        for (const unsigned char* c = (const unsigned char*)(texts[u] ? texts[u] : ""); *c; c++)
+            chars += (*c >= '0' && *c <= '9') ? 16 : 1;   /* a digit expands to words ("novecentos e ") */
+        uint64_t s = chars * per_char;
+        if (speeds && speeds[u] < 1.0f) s *= 2;   /* hop = 128 / speed <= 256 */
+        total += s + 1024;
+    }
+    return total;
+}
+
+int ctts_b200_synth_texts(ctts_front* front, ctts_gpu_ctx* gpu, const char* const* texts, const float* speeds,
+                          uint32_t n, int16_t* pcm_out, uint64_t capacity, uint64_t* out_offsets,
+                          uint32_t* out_counts, uint32_t* stats, uint64_t* samples_used,
+                          const ctts_b200_options* opt, ctts_b200_timing* timing) {
+    if (!front || !gpu || (n && (!texts || !out_offsets || !out_counts))) return CTTS_GPU_ERR_INVALID_ARG;
+    pipeline P;
+    memset(&P, 0, sizeof P);
+    P.front = front;
+    P.texts = texts;
+    P.speeds = speeds;
+    P.stats = stats;
+    P.n = n;
+    P.piece_utts = opt && opt->piece_utts ? opt->piece_utts : 128;
+    P.n_pieces = (n + P.piece_utts - 1) / P.piece_utts;
+    P.t0 = now_s();
+    long cores = sysconf(_SC_NPROCESSORS_ONLN);
+    uint32_t T = opt && opt->threads ? opt->threads : (uint32_t)(cores > 1 ? cores - 1 : 1);
+    if (T > 32) T = 32;
+    if (T > P.n_pieces) T = P.n_pieces;
+    if (T < 1) T = 1;
+
+    ctts_assembly_params prm;
+    ctts_front_params(front, &prm);
+    ctts_gpu_session* ses = NULL;
+    int rc = ctts_gpu_session_begin(gpu, &prm, pcm_out, capacity, opt ? opt->on_piece : NULL, opt ? opt->user : NULL, &ses);
+    if (rc) return rc;
+    P.slots = calloc(P.n_pieces ? P.n_pieces : 1, sizeof *P.slots);
+    pthread_t* tids = calloc(T, sizeof *tids);
+    if (!P.slots || !tids) {
+        free(P.slots);
+        free(tids);
+        ctts_gpu_session_end(ses, NULL);
+        return CTTS_GPU_ERR_OUT_OF_MEMORY;
+    }
+    pthread_mutex_init(&P.mu, NULL);
+    pthread_cond_init(&P.cv_ready, NULL);
+    pthread_cond_init(&P.cv_room, NULL);
+    uint32_t started = 0;
+    for (; started < T; started++)
+        if (pthread_create(&tids[started], NULL, planner, &P) != 0) break;
+    double waited = 0.0, all_submitted = 0.0;
+    if (started == 0 && P.n_pieces) rc = CTTS_GPU_ERR_OUT_OF_MEMORY;
+    for (uint32_t i = 0; i < P.n_pieces && !rc; i++) {
+        const double w0 = now_s();
+        pthread_mutex_lock(&P.mu);
+        while (P.slots[i].state == 0) pthread_cond_wait(&P.cv_ready, &P.mu);
+        const int st = P.slots[i].state;
+        pthread_mutex_unlock(&P.mu);
+        waited += now_s() - w0;
+        if (st < 0) {
+            rc = st;
+            break;
+        }
+        const uint32_t u0 = i * P.piece_utts;
+        rc = ctts_gpu_session_submit(ses, &P.slots[i].plan, out_offsets + u0, out_counts + u0);
+        ctts_front_plan_free(&P.slots[i].plan);   /* the session keeps nothing of the plan */
+        P.slots[i].state = 2;
+        pthread_mutex_lock(&P.mu);
+        P.consumed = i + 1;
+        pthread_cond_broadcast(&P.cv_room);
+        pthread_mutex_unlock(&P.mu);
+        all_submitted = now_s() - P.t0;
+    }
+    pthread_mutex_lock(&P.mu);
+    P.stop = 1;
+    pthread_cond_broadcast(&P.cv_room);
+    pthread_mutex_unlock(&P.mu);
+    for (uint32_t t = 0; t < started; t++) pthread_join(tids[t], NULL);
+    for (uint32_t i = 0; i < P.n_pieces; i++)
+        if (P.slots[i].state == 1) ctts_front_plan_free(&P.slots[i].plan);
+    const int rc_end = ctts_gpu_session_end(ses, samples_used);
+    if (!rc) rc = rc_end;
+    if (timing) {
+        timing->first_plan_s = P.first_plan_s;
+        timing->all_plans_s = P.all_plans_s;
+        timing->all_submitted_s = all_submitted;
+        timing->done_s = now_s() - P.t0;
+        timing->wait_for_plans_s = waited;
+    }
+    pthread_mutex_destroy(&P.mu);
+    pthread_cond_destroy(&P.cv_ready);
+    pthread_cond_destroy(&P.cv_room);
+    free(P.slots);
+    free(tids);
+    return rc;
+}

@@ -1069,6 +1069,12 @@ void ctts_front_close(ctts_front* f) {
 
 uint32_t ctts_front_rule_count(const ctts_front* f) { return f ? f->n_rules : 0; }
 uint32_t ctts_front_unit_count(const ctts_front* f) { return f ? f->hdr.unit_count : 0; }
+uint32_t ctts_front_max_unit_samples(const ctts_front* f) {
+    uint32_t m = 0;
+    for (uint32_t u = 0; f && u < f->hdr.unit_count; u++)
+        if (f->index[u].sample_count > m) m = f->index[u].sample_count;
+    return m;
+}
 
 void ctts_front_params(const ctts_front* f, ctts_assembly_params* out) {
     memset(out, 0, sizeof *out);
@@ -1148,6 +1154,11 @@ static uint32_t plan_threads(uint32_t n) {
 
 int ctts_front_plan_batch(ctts_front* f, const char* const* texts, const float* speeds,
                           uint32_t n, ctts_batch_plan* out, uint32_t* stats) {
+    return ctts_front_plan_batch_threads(f, texts, speeds, n, 0, out, stats);
+}
+
+int ctts_front_plan_batch_threads(ctts_front* f, const char* const* texts, const float* speeds,
+                                  uint32_t n, uint32_t threads, ctts_batch_plan* out, uint32_t* stats) {
     if (!f || !out || (n && !texts)) return CTTS_FRONT_ERR_INVALID_ARG;
     memset(out, 0, sizeof *out);
     uint32_t* begin = malloc(((size_t)n + 1) * sizeof *begin);
@@ -1160,7 +1171,7 @@ int ctts_front_plan_batch(ctts_front* f, const char* const* texts, const float* 
     for (uint32_t u = 0; u < n; u++) sp[u] = speeds ? speeds[u] : 1.0f;
 
     /* utterances are independent: contiguous slices planned by worker threads, then concatenated */
-    const uint32_t T = plan_threads(n);
+    const uint32_t T = threads ? (threads > 64 ? 64 : threads) : plan_threads(n);
     plan_job* jobs = calloc(T, sizeof *jobs);
     pthread_t* tids = calloc(T, sizeof *tids);
     if (!jobs || !tids) {

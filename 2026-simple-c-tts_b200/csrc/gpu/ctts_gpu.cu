@@ -71,6 +71,16 @@ struct Knobs {
     }
 };
 
+struct Arena {
+    char* d = nullptr;
+    size_t d_cap = 0;
+    char* h = nullptr;   // pinned
+    size_t h_cap = 0;
+};
+
+struct ctts_gpu_plan;
+struct ctts_gpu_session;
+
 struct ctts_gpu_ctx {
     int device = 0;
     Knobs knobs;
@@ -101,18 +111,25 @@ struct ctts_gpu_ctx {
     int sm_count = 0;
     int smem_per_sm = 0;
     int smem_optin = 0;
-    int16_t* d_batch_out = nullptr;  // reused by ctts_gpu_synth_batch
-    uint64_t batch_out_cap = 0;
-    // grow-only workspaces of ctts_gpu_synth_batch (no cudaMalloc / cudaFree per call)
-    char* d_arena = nullptr;
-    size_t d_arena_cap = 0;
-    char* h_arena = nullptr;         // pinned staging for the plan upload
-    size_t h_arena_cap = 0;
+    // A batch is worked on in PIECES (contiguous utterance ranges); up to kLanes pieces are in flight: the
+    // host compiles piece c+1 while the device assembles piece c and piece c-1 is copied to the caller.
+    // Every lane owns grow-only workspaces (no cudaMalloc / cudaFree per call).
+    static constexpr int kLanes = 3;
+    struct Lane {
+        Arena arena;                       // device workspace + pinned staging of the plan upload
+        int16_t* d_out = nullptr;          // the piece's output slots
+        uint64_t d_out_cap = 0;
+        uint32_t* h_res = nullptr;         // pinned: counts [n], then device error flags [n]
+        size_t h_res_cap = 0;
+        cudaEvent_t kernels_done = nullptr, copied = nullptr;
+        ctts_gpu_plan* plan = nullptr;     // piece in flight
+        uint32_t* user_counts = nullptr;   // where its counts go
+        uint32_t utt_base = 0, n = 0;      // its utterances in the session's numbering
+        bool busy = false;
+    };
+    Lane lane[kLanes];
     cudaStream_t copy_stream = nullptr;
-    std::vector<cudaEvent_t> copied_events;            // per chunk (streaming): PCM, counts and flags are on the host
-    uint32_t* h_stream = nullptr;                      // pinned (streaming): counts [n], then device error flags [n]
-    size_t h_stream_cap = 0;
-    std::vector<cudaEvent_t> events;
+    ctts_gpu_session* session = nullptr;   // at most one at a time
     char err[512] = {0};
 };
 
@@ -132,7 +149,8 @@ struct ctts_gpu_plan {
     ctts_assembly_params prm{};
     std::vector<uint64_t> offsets;  // n_utts + 1
     std::vector<uint64_t> bounds;
-    bool in_arena = false;          // device buffers live in the context arena (batch path)
+    Arena* arena = nullptr;         // device buffers live in a lane's arena (batch path); else cudaMalloc'ed
+    uint32_t op0 = 0;               // first op of the plan's utterances in the caller's op array (ops are kept from there on)
     std::vector<void*> owned;       // else: cudaMalloc'ed buffers to free
     ctts_gpu_ctx::NormPool* np = nullptr;   // context-owned: normalized pool and its tables
     ctts_plan_op* d_ops = nullptr;
@@ -292,6 +310,7 @@ int scan_range(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, uint64_t bi
         }
         close_region();
         pre_out[u] = total;
+        if (!std::isfinite(plan->speed[u])) return CTTS_GPU_ERR_INVALID_ARG;   // (size_t)(128 / NaN) is undefined in the reference too
         uint32_t hop = 0;
         const bool st = needs_stretch(plan->speed[u], &hop);
         sc->any_stretch |= st;
@@ -435,6 +454,7 @@ int ctts_gpu_init(ctts_gpu_ctx** out, const void* voice_db, size_t db_size, int 
 void ctts_gpu_free(ctts_gpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->session) ctts_gpu_session_end(ctx->session, nullptr);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     cudaFree(ctx->d_pool);
     cudaFree(ctx->d_unit_off);
@@ -446,13 +466,17 @@ void ctts_gpu_free(ctts_gpu_ctx* ctx) {
         cudaFree(np->d_pitch);
         delete np;
     }
-    cudaFree(ctx->d_batch_out);
-    cudaFree(ctx->d_arena);
-    if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
-    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    for (ctts_gpu_ctx::Lane& l : ctx->lane) {
+        if (l.plan) ctts_gpu_plan_destroy(l.plan);
+        cudaFree(l.arena.d);
+        if (l.arena.h) cudaFreeHost(l.arena.h);
+        cudaFree(l.d_out);
+        if (l.h_res) cudaFreeHost(l.h_res);
+        if (l.kernels_done) cudaEventDestroy(l.kernels_done);
+        if (l.copied) cudaEventDestroy(l.copied);
+    }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    for (cudaEvent_t e : ctx->copied_events) cudaEventDestroy(e);
-    if (ctx->h_stream) cudaFreeHost(ctx->h_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -488,7 +512,8 @@ int ctts_gpu_plan_bounds(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, u
 
 void ctts_gpu_plan_destroy(ctts_gpu_plan* p) {
     if (!p) return;
-    if (p->ctx) {
+    if (p->ctx && (!p->arena || !p->owned.empty())) {
+        // (a piece of a session is destroyed after its lane's events: nothing of it is still running)
         cudaSetDevice(p->ctx->device);
         cudaStreamSynchronize(p->ctx->stream);
     }
@@ -515,8 +540,8 @@ struct PlanAlloc {
     template <typename T>
     T* dev(size_t count) {
         const size_t bytes = up256(std::max<size_t>(count, 1) * sizeof(T));
-        if (p->in_arena) {
-            T* r = reinterpret_cast<T*>(ctx->d_arena + d_used);
+        if (p->arena) {
+            T* r = reinterpret_cast<T*>(p->arena->d + d_used);
             d_used += bytes;
             return r;
         }
@@ -528,24 +553,24 @@ struct PlanAlloc {
     }
 };
 
-int ensure_arenas(ctts_gpu_ctx* ctx, size_t d_bytes, size_t h_bytes) {
-    if (d_bytes > ctx->d_arena_cap) {
-        cudaFree(ctx->d_arena);
-        ctx->d_arena = nullptr;
-        ctx->d_arena_cap = 0;
+int ensure_arena(ctts_gpu_ctx* ctx, Arena* a, size_t d_bytes, size_t h_bytes) {
+    if (d_bytes > a->d_cap) {
+        cudaFree(a->d);
+        a->d = nullptr;
+        a->d_cap = 0;
         const size_t cap = d_bytes + d_bytes / 4;
-        if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_arena), cap) != cudaSuccess)
+        if (cudaMalloc(reinterpret_cast<void**>(&a->d), cap) != cudaSuccess)
             return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "device workspace of %zu bytes", cap);
-        ctx->d_arena_cap = cap;
+        a->d_cap = cap;
     }
-    if (h_bytes > ctx->h_arena_cap) {
-        if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
-        ctx->h_arena = nullptr;
-        ctx->h_arena_cap = 0;
+    if (h_bytes > a->h_cap) {
+        if (a->h) cudaFreeHost(a->h);
+        a->h = nullptr;
+        a->h_cap = 0;
         const size_t cap = h_bytes + h_bytes / 4;
-        if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_arena), cap, cudaHostAllocDefault) != cudaSuccess)
+        if (cudaHostAlloc(reinterpret_cast<void**>(&a->h), cap, cudaHostAllocDefault) != cudaSuccess)
             return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "pinned staging of %zu bytes", cap);
-        ctx->h_arena_cap = cap;
+        a->h_cap = cap;
     }
     return 0;
 }
@@ -584,14 +609,22 @@ int norm_pool_for(ctts_gpu_ctx* ctx, float target_rms, ctts_gpu_ctx::NormPool** 
         delete np;
         return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "normalized pool");
     }
-    ctx->norm_pools.push_back(np);
     const auto t0 = std::chrono::steady_clock::now();
-    if (ctx->n_units) {
+    cudaError_t ce = cudaMemsetAsync(np->d_pitch, 0, (size_t)np->pitch_cap * sizeof(float), ctx->stream);
+    if (ce == cudaSuccess && ctx->n_units) {
         ctts::normalize_pool_kernel<<<ctx->n_units, ctts::ASM_THREADS, 0, ctx->stream>>>(ctx->d_pool, np->d_pool, ctx->d_unit_off,
                                                                                        ctx->d_unit_cnt, np->d_meta, target_rms);
-        CU(ctx, cudaGetLastError());
-        CU(ctx, cudaStreamSynchronize(ctx->stream));   // once: later plans may run on another stream
+        ce = cudaGetLastError();
     }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);   // once: later plans may run on another stream
+    if (ce != cudaSuccess) {   // the pool is registered only once it is filled
+        cudaFree(np->d_pool);
+        cudaFree(np->d_meta);
+        cudaFree(np->d_pitch);
+        delete np;
+        return fail(ctx, CTTS_GPU_ERR_CUDA, "normalize_pool_kernel: %s", cudaGetErrorString(ce));
+    }
+    ctx->norm_pools.push_back(np);
     if (ctx->knobs.trace)
         fprintf(stderr, "ctts_gpu: normalized pool for target_rms %g: %u units, %llu samples in %.2f ms\n", (double)target_rms, ctx->n_units,
                 (unsigned long long)ctx->pool_samples, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
@@ -633,12 +666,11 @@ int run_pitch_jobs(ctts_gpu_ctx* ctx, ctts_gpu_ctx::NormPool* np, const std::vec
     return CTTS_GPU_OK;
 }
 
-// The plan compiler, part 1.  chunk_samples == 0: one launch for the whole batch (best kernel
-// efficiency, the resident-plan path); > 0: utterances are cut, in slot order, into launches
-// of about that many output samples so that compiling / copying one chunk overlaps the
-// assembly of another (ctts_gpu_synth_batch).  Chunks are then built with build_chunk().
+// The plan compiler, part 1: validation, bounds, output layout, workspace.  One launch of every kernel
+// per plan; a large batch is cut into pieces (plans) by the session code below.  `arena` != nullptr:
+// device / pinned workspace comes from that lane's grow-only arena.  build_chunk() is part 2.
 int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_assembly_params* params,
-                 const uint64_t* out_offsets, uint64_t chunk_samples, bool in_arena, ctts_gpu_plan** out) {
+                 const uint64_t* out_offsets, Arena* arena, ctts_gpu_plan** out) {
     if (!ctx || !plan || !params || !out) return CTTS_GPU_ERR_INVALID_ARG;
     if (plan->n_utts && (!plan->utt_op_begin || !plan->speed)) return CTTS_GPU_ERR_INVALID_ARG;
     if (plan->n_ops && !plan->ops) return CTTS_GPU_ERR_INVALID_ARG;
@@ -668,8 +700,10 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
     p->n_utts = n;
     p->prm = *params;
     p->bounds = bound;
-    p->in_arena = in_arena;
+    p->arena = arena;
     p->src = plan;
+    p->op0 = n ? plan->utt_op_begin[0] : 0;
+    const uint32_t n_ops_local = n ? plan->utt_op_begin[n] - p->op0 : 0;   // (validated by the scan)
 
     // ---- output layout
     p->offsets.resize((size_t)n + 1);
@@ -686,6 +720,10 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
     } else {
         uint64_t o = 0;
         for (uint32_t u = 0; u < n; u++) {
+            if (bound[u] + 16 > 0xffffffffull) {
+                delete p;
+                return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "utterance %u too long (%llu samples)", u, (unsigned long long)bound[u]);
+            }
             p->offsets[u] = o;
             o += up8(bound[u]) + 8;
         }
@@ -715,34 +753,16 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
     p->hcap = hcap;
     p->smem_bytes = smem_for(wcap);
 
-    // ---- chunks: contiguous utterance ranges of about chunk_samples output samples (one launch of every
-    // kernel per chunk; the device->host copy of a chunk overlaps the kernels of the next).  Every frame of
-    // a stretched utterance is verified independently (wsola_verify_kernel), so batches with WSOLA need no
-    // geometry of their own.
     uint32_t n_stretched = 0;
     if (sc.any_stretch)
         for (uint32_t u = 0; u < n; u++) {
             uint32_t hop = 0;
             n_stretched += needs_stretch(plan->speed[u], &hop);
         }
-    if (chunk_samples == 0 || n == 0) {
+    {
         PlanChunk ch;
         ch.utt_end = n;
         p->chunks.push_back(ch);
-    } else {
-        uint64_t acc = 0;
-        uint32_t u0 = 0;
-        for (uint32_t u = 0; u < n; u++) {
-            acc += std::max(bound[u], pre[u]);
-            if (acc >= chunk_samples || u + 1 == n) {
-                PlanChunk ch;
-                ch.utt_begin = u0;
-                ch.utt_end = u + 1;
-                p->chunks.push_back(ch);
-                u0 = u + 1;
-                acc = 0;
-            }
-        }
     }
 
     // ---- slots of stretched utterances and WSOLA tasks, chunk by chunk, longest first inside a chunk
@@ -805,10 +825,10 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
     }
 
     // ---- workspace.  The private op copy and the tasks are built directly in (pinned) staging.
-    const size_t ops_bytes = std::max<size_t>(plan->n_ops, 1) * sizeof(ctts_plan_op);
+    const size_t ops_bytes = std::max<size_t>(n_ops_local, 1) * sizeof(ctts_plan_op);
     const size_t tasks_cap = (size_t)sc.n_regions + 1;   // merging only lowers the count
     const size_t tasks_bytes = tasks_cap * sizeof(ctts::RegionTask);
-    if (in_arena) {
+    if (arena) {
         // device side: ops, tasks, chain, tickets, counts, pre_counts, err (+ the stretch buffers)
         size_t d_need = PlanAlloc::up256(ops_bytes) + PlanAlloc::up256(tasks_bytes) + PlanAlloc::up256(tasks_cap * 8) +
                         PlanAlloc::up256((size_t)n_chunks * 4) + 3 * PlanAlloc::up256(std::max<size_t>(n, 1) * 4) + 65536;
@@ -816,18 +836,18 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
             d_need += PlanAlloc::up256(stasks.size() * sizeof(ctts::StretchTask)) + 2 * PlanAlloc::up256(ola_task.size() * 4 + 4) +
                       PlanAlloc::up256(pre_total * 2 + 16) + PlanAlloc::up256(pos_total * 4 + 4) + PlanAlloc::up256(stasks.size() * 20) + 4096;
         const size_t h_need = PlanAlloc::up256(ops_bytes) + PlanAlloc::up256(tasks_bytes) + 4096;
-        rc = ensure_arenas(ctx, d_need, h_need);
+        rc = ensure_arena(ctx, arena, d_need, h_need);
         if (rc) { delete p; return rc; }
-        p->h_ops = reinterpret_cast<ctts_plan_op*>(ctx->h_arena);
-        p->h_tasks = reinterpret_cast<ctts::RegionTask*>(ctx->h_arena + PlanAlloc::up256(ops_bytes));
+        p->h_ops = reinterpret_cast<ctts_plan_op*>(arena->h);
+        p->h_tasks = reinterpret_cast<ctts::RegionTask*>(arena->h + PlanAlloc::up256(ops_bytes));
     } else {
-        p->ops_vec.resize(std::max<size_t>(plan->n_ops, 1));
+        p->ops_vec.resize(std::max<size_t>(n_ops_local, 1));
         p->tasks_vec.resize(tasks_cap);
         p->h_ops = p->ops_vec.data();
         p->h_tasks = p->tasks_vec.data();
     }
     PlanAlloc al{ctx, p};
-    p->d_ops = al.dev<ctts_plan_op>(plan->n_ops);
+    p->d_ops = al.dev<ctts_plan_op>(n_ops_local);
     p->d_tasks = al.dev<ctts::RegionTask>(tasks_cap);
     p->d_chain = al.dev<unsigned long long>(tasks_cap);
     p->d_ticket = al.dev<uint32_t>(n_chunks);
@@ -893,8 +913,9 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
     const uint32_t wcap = p->wcap;
     const uint64_t scr_samples = (uint64_t)(ctts::SCR_WORDS - 4) / 2 * 32;
     ctts_plan_op* h_ops = p->h_ops;
-    const uint32_t op_lo = u1 > u0 ? ub[u0] : 0, op_hi = u1 > u0 ? ub[u1] : 0;
-    if (op_hi > op_lo) memcpy(h_ops + op_lo, plan->ops + op_lo, (size_t)(op_hi - op_lo) * sizeof(ctts_plan_op));
+    const uint32_t op0 = p->op0;   // h_ops / d_ops hold the caller's ops from op0 on
+    const uint32_t op_lo = u1 > u0 ? ub[u0] : op0, op_hi = u1 > u0 ? ub[u1] : op0;
+    if (op_hi > op_lo) memcpy(h_ops + (op_lo - op0), plan->ops + op_lo, (size_t)(op_hi - op_lo) * sizeof(ctts_plan_op));
 
     // A fade-out that provably acts on zeros (or on an empty buffer) becomes a no-op, so that a
     // pause-only region never has to reach back into its predecessor's samples.  Trailing zeros:
@@ -905,6 +926,7 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
     struct HostTask { uint32_t op_begin, op_end; uint64_t bound; uint32_t region_max; };
     std::vector<HostTask> ht;
     std::vector<uint3> pitch_jobs;
+    std::vector<uint32_t> pitch_job_units;   // unit of every new table entry (to take them back if the fill fails)
     std::vector<uint32_t> ht_begin(u1 - u0 + 1, 0);   // CSR: tasks of utterance u0 + i
     uint32_t max_rows = 0;
     for (uint32_t u = u0; u < u1; u++) {
@@ -928,7 +950,7 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
             L = 0;
         };
         for (uint32_t k = ub[u]; k < ub[u + 1]; k++) {
-            ctts_plan_op& op = h_ops[k];
+            ctts_plan_op& op = h_ops[k - op0];
             switch (op.kind) {
                 case CTTS_OP_UNIT: {
                     const uint32_t cn = ucnt[op.a];
@@ -941,7 +963,11 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
                     uint32_t slot1 = 0;
                     if (!(op.flags & CTTS_UNIT_AFTER_BOUNDARY) && op.b > 0 && cn >= 200) {
                         const uint32_t m2 = 2 * op.b < cn / 2 ? 2 * op.b : cn / 2;   // uint32 like the kernel
-                        if (m2 >= 200) slot1 = pitch_slot_for(ctx, p->np, op.a, m2, &pitch_jobs);
+                        if (m2 >= 200) {
+                            const size_t before = pitch_jobs.size();
+                            slot1 = pitch_slot_for(ctx, p->np, op.a, m2, &pitch_jobs);
+                            if (pitch_jobs.size() != before) pitch_job_units.push_back(op.a);
+                        }
                     }
                     memcpy(&op.f2, &slot1, 4);
                     count_ub += cn;
@@ -976,7 +1002,12 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
     ht_begin[u1 - u0] = (uint32_t)ht.size();
     {
         const int rcj = run_pitch_jobs(ctx, p->np, pitch_jobs);
-        if (rcj) return rcj;
+        if (rcj) {
+            // the new slots were never filled: un-register them, or every later plan would read garbage
+            for (size_t i = pitch_job_units.size(); i-- > 0;) p->np->pitch_slots[pitch_job_units[i]].pop_back();
+            p->np->pitch_used -= (uint32_t)pitch_jobs.size();
+            return rcj;
+        }
     }
 
     // ticket order: region-major (task k of every utterance before task k+1 of any), inside a
@@ -999,8 +1030,8 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
             const HostTask& h = ht[ht_begin[ui] + k];
             ctts::RegionTask t{};
             t.utt = u;
-            t.op_begin = h.op_begin;
-            t.op_end = h.op_end;
+            t.op_begin = h.op_begin - op0;
+            t.op_end = h.op_end - op0;
             t.bound = (uint32_t)std::min<uint64_t>(h.bound, 0xffffffffull);
             t.pred = last_index[ui];
             const bool stretched = p->pre_off[u] != ~0ull;
@@ -1022,7 +1053,8 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
     ch.grid = (uint32_t)std::min<uint64_t>((uint64_t)p->occ * (uint64_t)ctx->sm_count, std::max<uint32_t>(ch.n_tasks, 1));
 
     if (op_hi > op_lo)
-        CU(ctx, cudaMemcpyAsync(p->d_ops + op_lo, h_ops + op_lo, (size_t)(op_hi - op_lo) * sizeof(ctts_plan_op), cudaMemcpyHostToDevice, st));
+        CU(ctx, cudaMemcpyAsync(p->d_ops + (op_lo - op0), h_ops + (op_lo - op0), (size_t)(op_hi - op_lo) * sizeof(ctts_plan_op),
+                                cudaMemcpyHostToDevice, st));
     if (ch.n_tasks)
         CU(ctx, cudaMemcpyAsync(p->d_tasks + ch.task_begin, p->h_tasks + ch.task_begin, (size_t)ch.n_tasks * sizeof(ctts::RegionTask),
                                 cudaMemcpyHostToDevice, st));
@@ -1033,7 +1065,7 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
     p->info.grid = std::max(p->info.grid, ch.grid);
     if (p->built_chunks == p->chunks.size()) {
         p->src = nullptr;
-        if (!p->in_arena) {
+        if (!p->arena) {
             // pageable staging must outlive the async copies
             CU(ctx, cudaStreamSynchronize(st));
             std::vector<ctts_plan_op>().swap(p->ops_vec);
@@ -1144,7 +1176,7 @@ extern "C" {
 int ctts_gpu_plan_create(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_assembly_params* params,
                          const uint64_t* out_offsets, ctts_gpu_plan** out) {
     ctts_gpu_plan* p = nullptr;
-    int rc = prepare_plan(ctx, plan, params, out_offsets, 0, false, &p);
+    int rc = prepare_plan(ctx, plan, params, out_offsets, nullptr, &p);
     for (uint32_t c = 0; !rc && c < p->chunks.size(); c++) rc = build_chunk(ctx, p, c, ctx->stream);
     if (rc) {
         ctts_gpu_plan_destroy(p);
@@ -1242,6 +1274,219 @@ int ctts_gpu_plan_read_pre(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t u, int1
     return CTTS_GPU_OK;
 }
 
+// ---------------------------------------------------------------- sessions: a batch fed in pieces
+
+}  // extern "C"
+
+struct ctts_gpu_session {
+    ctts_gpu_ctx* ctx = nullptr;
+    ctts_assembly_params prm{};
+    int16_t* pcm_out = nullptr;
+    uint64_t capacity = 0;        // samples
+    uint64_t cursor = 0;          // next free sample (library-chosen layout)
+    uint32_t submitted = 0, harvested = 0;   // pieces
+    uint32_t utts = 0;            // utterances submitted so far
+    ctts_gpu_chunk_fn on_piece = nullptr;
+    void* user = nullptr;
+    int error = 0;
+    uint64_t d2h_samples = 0;     // samples copied to the host
+    std::chrono::steady_clock::time_point t0;
+};
+
+namespace {
+
+void drain(ctts_gpu_ctx* ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+}
+
+// Wait for the oldest piece in flight, hand its counts (and the piece itself) to the caller, free its lane.
+int harvest_one(ctts_gpu_session* s) {
+    ctts_gpu_ctx* ctx = s->ctx;
+    ctts_gpu_ctx::Lane& l = ctx->lane[s->harvested % ctts_gpu_ctx::kLanes];
+    s->harvested++;
+    if (!l.busy) return CTTS_GPU_OK;
+    cudaError_t e = cudaEventSynchronize(l.copied);
+    int rc = CTTS_GPU_OK;
+    if (e != cudaSuccess) rc = fail(ctx, CTTS_GPU_ERR_CUDA, "piece of utterances %u..%u: %s", l.utt_base, l.utt_base + l.n, cudaGetErrorString(e));
+    if (!rc) {
+        const uint32_t* h_cnt = l.h_res;
+        const uint32_t* h_err = l.h_res + l.n;
+        if (l.user_counts) memcpy(l.user_counts, h_cnt, (size_t)l.n * 4);
+        for (uint32_t u = 0; u < l.n && !rc; u++)
+            if (h_err[u]) rc = fail(ctx, CTTS_GPU_ERR_DEVICE, "utterance %u: device error %u", l.utt_base + u, h_err[u]);
+    }
+    if (ctx->knobs.trace)
+        fprintf(stderr, "  piece of utterances %u..%u on the host at %.1f ms\n", l.utt_base, l.utt_base + l.n,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s->t0).count());
+    // a piece with a device error is not handed over (its counts are arbitrary)
+    if (!rc && !s->error && s->on_piece && l.n) s->on_piece(s->user, l.utt_base, l.utt_base + l.n);
+    if (rc && !s->error) s->error = rc;
+    if (l.plan) {
+        if (rc) drain(ctx);
+        ctts_gpu_plan_destroy(l.plan);
+        l.plan = nullptr;
+    }
+    l.busy = false;
+    return rc;
+}
+
+// One piece: compile, launch, copy.  Utterance i of the piece is delivered to pcm_out[slot_off[i] ..),
+// slot_cap[i] samples of room (>= its bound); slot_off == nullptr: the library appends packed slots at the
+// session's cursor and reports them through offsets_out.  Asynchronous: returns once everything is enqueued.
+int submit_piece(ctts_gpu_session* s, const ctts_batch_plan* piece, const uint64_t* slot_off, const uint64_t* slot_cap,
+                 uint64_t* offsets_out, uint32_t* out_counts) {
+    ctts_gpu_ctx* ctx = s->ctx;
+    const uint32_t n = piece->n_utts;
+    ctts_gpu_ctx::Lane& l = ctx->lane[s->submitted % ctts_gpu_ctx::kLanes];
+    if (s->submitted - s->harvested >= (uint32_t)ctts_gpu_ctx::kLanes) harvest_one(s);   // the lane's previous piece
+    if (s->error) return s->error;
+    ctts_gpu_plan* p = nullptr;
+    int rc = prepare_plan(ctx, piece, &s->prm, nullptr, &l.arena, &p);
+    if (rc) return rc;
+    auto bail = [&](int code) {
+        drain(ctx);
+        ctts_gpu_plan_destroy(p);
+        return code;
+    };
+    std::vector<uint64_t> lib_off, lib_cap;
+    if (!slot_off) {
+        lib_off.resize(std::max<uint32_t>(n, 1));
+        lib_cap.resize(std::max<uint32_t>(n, 1));
+        for (uint32_t u = 0; u < n; u++) {
+            lib_off[u] = s->cursor + p->offsets[u];
+            lib_cap[u] = p->offsets[u + 1] - p->offsets[u];
+            if (offsets_out) offsets_out[u] = lib_off[u];
+        }
+        slot_off = lib_off.data();
+        slot_cap = lib_cap.data();
+        if (s->cursor + p->offsets[n] > s->capacity)
+            return bail(fail(ctx, CTTS_GPU_ERR_BOUNDS, "output buffer too small: %llu samples needed so far",
+                             (unsigned long long)(s->cursor + p->offsets[n])));
+    }
+    for (uint32_t u = 0; u < n; u++)
+        if ((slot_off[u] & 7) || slot_cap[u] < p->bounds[u] || slot_off[u] + slot_cap[u] > s->capacity)
+            return bail(fail(ctx, CTTS_GPU_ERR_BOUNDS, "output slot of utterance %u is misaligned, outside the buffer or smaller than its bound %llu",
+                             s->utts + u, (unsigned long long)p->bounds[u]));
+    const uint64_t total = p->offsets[n];
+    if (total > l.d_out_cap) {
+        cudaFree(l.d_out);
+        l.d_out = nullptr;
+        l.d_out_cap = 0;
+        const uint64_t cap = std::max<uint64_t>(total + total / 8, 8);
+        if (cudaMalloc(reinterpret_cast<void**>(&l.d_out), cap * sizeof(int16_t)) != cudaSuccess)
+            return bail(fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "output buffer of %llu samples", (unsigned long long)cap));
+        // never-written slot tails must not carry an earlier allocation's bytes to the host
+        if (cudaMemsetAsync(l.d_out, 0, cap * sizeof(int16_t), ctx->stream) != cudaSuccess) return bail(fail(ctx, CTTS_GPU_ERR_CUDA, "memset"));
+        l.d_out_cap = cap;
+    }
+    if (2 * (size_t)n > l.h_res_cap) {
+        if (l.h_res) cudaFreeHost(l.h_res);
+        l.h_res = nullptr;
+        l.h_res_cap = 0;
+        const size_t cap = 2 * (size_t)n + 1024;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&l.h_res), cap * 4, cudaHostAllocDefault) != cudaSuccess)
+            return bail(fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "pinned counts"));
+        l.h_res_cap = cap;
+    }
+    if (!l.kernels_done) {
+        cudaError_t e = cudaEventCreateWithFlags(&l.kernels_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.copied, cudaEventDisableTiming);
+        if (e != cudaSuccess) return bail(fail(ctx, CTTS_GPU_ERR_CUDA, "event: %s", cudaGetErrorString(e)));
+    }
+    p->d_out_last = l.d_out;
+    if (n) {
+        rc = begin_run(ctx, p);
+        if (!rc) rc = build_chunk(ctx, p, 0, ctx->stream);
+        if (!rc) rc = launch_chunk(ctx, p, 0, l.d_out, ctx->stream);
+        if (!rc) rc = launch_stretch(ctx, p, 0, l.d_out, ctx->stream);
+        if (rc) return bail(rc);
+        cudaError_t e = cudaEventRecord(l.kernels_done, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, l.kernels_done, 0);
+        // device slots are packed (up8(bound) + 8 each); runs of utterances whose host slots are packed the
+        // same way go in one copy
+        for (uint32_t u = 0; u < n && e == cudaSuccess;) {
+            uint32_t v = u;
+            while (v + 1 < n && slot_off[v + 1] == slot_off[v] + (p->offsets[v + 1] - p->offsets[v]) &&
+                   slot_cap[v] >= p->offsets[v + 1] - p->offsets[v])
+                v++;
+            const uint64_t len = (p->offsets[v] - p->offsets[u]) + std::min<uint64_t>(p->offsets[v + 1] - p->offsets[v], slot_cap[v]);
+            if (len) e = cudaMemcpyAsync(s->pcm_out + slot_off[u], l.d_out + p->offsets[u], len * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+            s->d2h_samples += len;
+            u = v + 1;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(l.h_res, p->d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(l.h_res + n, p->d_err, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(l.copied, ctx->copy_stream);
+        if (e != cudaSuccess) return bail(fail(ctx, CTTS_GPU_ERR_CUDA, "enqueue: %s", cudaGetErrorString(e)));
+    } else {
+        cudaError_t e = cudaEventRecord(l.copied, ctx->copy_stream);
+        if (e != cudaSuccess) return bail(fail(ctx, CTTS_GPU_ERR_CUDA, "enqueue: %s", cudaGetErrorString(e)));
+    }
+    l.plan = p;
+    l.user_counts = out_counts;
+    l.utt_base = s->utts;
+    l.n = n;
+    l.busy = true;
+    s->submitted++;
+    s->utts += n;
+    if (!lib_off.empty()) s->cursor += p->offsets[n];
+    // hand over whatever has arrived in the meantime (never blocks)
+    while (s->harvested < s->submitted) {
+        ctts_gpu_ctx::Lane& h = ctx->lane[s->harvested % ctts_gpu_ctx::kLanes];
+        if (h.busy && cudaEventQuery(h.copied) != cudaSuccess) break;
+        harvest_one(s);
+    }
+    return s->error;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctts_gpu_session_begin(ctts_gpu_ctx* ctx, const ctts_assembly_params* params, int16_t* pcm_out, uint64_t capacity,
+                           ctts_gpu_chunk_fn on_piece, void* user, ctts_gpu_session** out) {
+    if (!ctx || !params || !out || (capacity && !pcm_out)) return CTTS_GPU_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (ctx->session) return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "a session is already open on this context");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    ctts_gpu_session* s = new ctts_gpu_session();
+    s->ctx = ctx;
+    s->prm = *params;
+    s->pcm_out = pcm_out;
+    s->capacity = capacity;
+    s->on_piece = on_piece;
+    s->user = user;
+    s->t0 = std::chrono::steady_clock::now();
+    ctx->session = s;
+    *out = s;
+    return CTTS_GPU_OK;
+}
+
+int ctts_gpu_session_submit(ctts_gpu_session* s, const ctts_batch_plan* piece, uint64_t* out_offsets, uint32_t* out_counts) {
+    if (!s || !piece || !out_counts || (piece->n_utts && !out_offsets)) return CTTS_GPU_ERR_INVALID_ARG;
+    if (s->error) return s->error;
+    ctts_gpu_ctx* ctx = s->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    return submit_piece(s, piece, nullptr, nullptr, out_offsets, out_counts);
+}
+
+int ctts_gpu_session_end(ctts_gpu_session* s, uint64_t* samples_used) {
+    if (!s) return CTTS_GPU_ERR_INVALID_ARG;
+    ctts_gpu_ctx* ctx = s->ctx;
+    cudaSetDevice(ctx->device);
+    while (s->harvested < s->submitted) harvest_one(s);
+    if (samples_used) *samples_used = s->cursor;
+    if (ctx->knobs.trace)
+        fprintf(stderr, "ctts_gpu session: %u utterances in %u pieces, %.1f MB to the host, %.1f ms\n", s->utts, s->submitted,
+                2e-6 * (double)s->d2h_samples, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s->t0).count());
+    const int rc = s->error;
+    ctx->session = nullptr;
+    delete s;
+    return rc;
+}
+
 int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_assembly_params* params,
                          int16_t* pcm_out, const uint64_t* out_offsets, uint32_t* out_counts) {
     return ctts_gpu_synth_batch_stream(ctx, plan, params, pcm_out, out_offsets, out_counts, nullptr, nullptr);
@@ -1251,151 +1496,34 @@ int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, 
                                 int16_t* pcm_out, const uint64_t* out_offsets, uint32_t* out_counts,
                                 ctts_gpu_chunk_fn on_chunk, void* user) {
     if (!ctx || !plan || !params || !pcm_out || !out_offsets || !out_counts) return CTTS_GPU_ERR_INVALID_ARG;
-    const bool trace = ctx->knobs.trace;
-    auto now = [] { return std::chrono::steady_clock::now(); };
-    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-    auto t0 = now();
-    // launches of ~256 MB of PCM: the device->host copy of one chunk overlaps the assembly of the next
-    const uint64_t chunk_samples = ctx->knobs.chunk_samples;
-    ctts_gpu_plan* p = nullptr;
-    int rc = prepare_plan(ctx, plan, params, out_offsets, chunk_samples, true, &p);
+    if (plan->n_utts && (!plan->utt_op_begin || !plan->speed)) return CTTS_GPU_ERR_INVALID_ARG;
+    const uint32_t n = plan->n_utts;
+    for (uint32_t u = 0; u < n; u++)
+        if (out_offsets[u + 1] < out_offsets[u] || plan->utt_op_begin[u + 1] < plan->utt_op_begin[u] || plan->utt_op_begin[u + 1] > plan->n_ops)
+            return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "offsets of utterance %u are not ascending", u);
+    ctts_gpu_session* s = nullptr;
+    int rc = ctts_gpu_session_begin(ctx, params, pcm_out, n ? out_offsets[n] : 0, on_chunk, user, &s);
     if (rc) return rc;
-    auto t1 = now();
-    const uint64_t total = p->offsets[p->n_utts];
-    if (total > ctx->batch_out_cap) {
-        cudaFree(ctx->d_batch_out);
-        ctx->d_batch_out = nullptr;
-        ctx->batch_out_cap = 0;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_batch_out), std::max<uint64_t>(total, 8) * sizeof(int16_t));
-        if (e != cudaSuccess) {
-            ctts_gpu_plan_destroy(p);
-            return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "output buffer: %s", cudaGetErrorString(e));
-        }
-        ctx->batch_out_cap = total;
-    }
-    int16_t* d_out = ctx->d_batch_out;
-    p->d_out_last = d_out;
-    const uint32_t nc = (uint32_t)p->chunks.size();
-    auto cu_fail = [&](cudaError_t e, const char* what) {
-        cudaStreamSynchronize(ctx->stream);
-        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-        ctts_gpu_plan_destroy(p);
-        return fail(ctx, CTTS_GPU_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
-    };
-    if (!ctx->copy_stream) {
-        cudaError_t e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-        if (e != cudaSuccess) return cu_fail(e, "copy stream");
-    }
-    while (ctx->events.size() < nc) {
-        cudaEvent_t ev;
-        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-        if (e != cudaSuccess) return cu_fail(e, "event");
-        ctx->events.push_back(ev);
-    }
-    while (on_chunk && ctx->copied_events.size() < nc) {
-        cudaEvent_t ev;
-        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-        if (e != cudaSuccess) return cu_fail(e, "event");
-        ctx->copied_events.push_back(ev);
-    }
-    if (on_chunk && 2 * (size_t)p->n_utts > ctx->h_stream_cap) {      // pinned: a pageable target would make the copies synchronous
-        if (ctx->h_stream) cudaFreeHost(ctx->h_stream);
-        ctx->h_stream = nullptr;
-        ctx->h_stream_cap = 0;
-        const size_t cap = 2 * (size_t)p->n_utts + 1024;
-        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_stream), cap * 4, cudaHostAllocDefault);
-        if (e != cudaSuccess) return cu_fail(e, "pinned counts");
-        ctx->h_stream_cap = cap;
-    }
-    uint32_t* const h_cnt = ctx->h_stream;                            // streaming: counts, then error flags
-    uint32_t* const h_err = ctx->h_stream ? ctx->h_stream + p->n_utts : nullptr;
-    uint32_t delivered = 0;                                           // chunks already handed to on_chunk
-    auto deliver = [&](uint32_t c) {
-        const PlanChunk& dc = p->chunks[c];
-        if (dc.utt_end <= dc.utt_begin) return;
-        memcpy(out_counts + dc.utt_begin, h_cnt + dc.utt_begin, (size_t)(dc.utt_end - dc.utt_begin) * 4);
-        on_chunk(user, dc.utt_begin, dc.utt_end);
-    };
-    std::vector<cudaEvent_t> tev;   // trace only: timing events around each chunk's kernels
-    auto mark = [&](cudaStream_t s_) {
-        if (!trace) return;
-        cudaEvent_t ev;
-        cudaEventCreate(&ev);
-        cudaEventRecord(ev, s_);
-        tev.push_back(ev);
-    };
-    if (p->n_utts) {
-        rc = begin_run(ctx, p);
-        mark(ctx->stream);
-        for (uint32_t c = 0; !rc && c < nc; c++) {
-            // compile + upload chunk c on the host while the device works on the chunks before it
-            const PlanChunk& ch = p->chunks[c];
-            rc = build_chunk(ctx, p, c, ctx->stream);
-            if (!rc) rc = launch_chunk(ctx, p, c, d_out, ctx->stream);
-            mark(ctx->stream);
-            cudaStream_t cs = ctx->stream;
-            if (!rc) rc = launch_stretch(ctx, p, c, d_out, cs);
-            mark(cs);
-            if (rc) break;
-            // the chunk's slots are one contiguous span; copy it while the other chunks are worked on
-            const uint64_t lo = p->offsets[ch.utt_begin], hi = p->offsets[ch.utt_end];
-            cudaError_t e = cudaEventRecord(ctx->events[c], cs);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->events[c], 0);
-            if (e == cudaSuccess && hi > lo)
-                e = cudaMemcpyAsync(pcm_out + lo, d_out + lo, (hi - lo) * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
-            if (e == cudaSuccess && on_chunk && ch.utt_end > ch.utt_begin) {
-                // streaming: the chunk's counts and error flags follow its PCM; the event marks all three
-                const size_t nb = (size_t)(ch.utt_end - ch.utt_begin) * 4;
-                e = cudaMemcpyAsync(h_cnt + ch.utt_begin, p->d_counts + ch.utt_begin, nb, cudaMemcpyDeviceToHost, ctx->copy_stream);
-                if (e == cudaSuccess)
-                    e = cudaMemcpyAsync(h_err + ch.utt_begin, p->d_err + ch.utt_begin, nb, cudaMemcpyDeviceToHost, ctx->copy_stream);
-                if (e == cudaSuccess) e = cudaEventRecord(ctx->copied_events[c], ctx->copy_stream);
-            }
-            if (e != cudaSuccess) return cu_fail(e, "D2H");
-            mark(ctx->copy_stream);
-            // hand over what has already arrived (never blocks; the rest is handed over below)
-            while (on_chunk && delivered < c + 1 &&
-                   (p->chunks[delivered].utt_end <= p->chunks[delivered].utt_begin || cudaEventQuery(ctx->copied_events[delivered]) == cudaSuccess))
-                deliver(delivered++);
+    // pieces of about chunk_samples samples of slot space: the device->host copy of one overlaps the kernels of
+    // the next and the host-side compilation of the one after
+    std::vector<uint64_t> cap(std::max<uint32_t>(n, 1));
+    for (uint32_t u = 0; u < n; u++) cap[u] = out_offsets[u + 1] - out_offsets[u];
+    const uint64_t chunk = ctx->knobs.chunk_samples;
+    uint64_t acc = 0;
+    for (uint32_t u0 = 0, u = 0; u < n && !rc; u++) {
+        acc += cap[u];
+        if (acc >= chunk || u + 1 == n) {
+            ctts_batch_plan piece = *plan;
+            piece.n_utts = u + 1 - u0;
+            piece.utt_op_begin = plan->utt_op_begin + u0;
+            piece.speed = plan->speed + u0;
+            rc = submit_piece(s, &piece, out_offsets + u0, cap.data() + u0, nullptr, out_counts + u0);
+            u0 = u + 1;
+            acc = 0;
         }
     }
-    auto t2 = now();
-    if (on_chunk && !rc) {
-        for (; delivered < nc; delivered++) {
-            const PlanChunk& dc = p->chunks[delivered];
-            if (dc.utt_end > dc.utt_begin) {
-                cudaError_t e = cudaEventSynchronize(ctx->copied_events[delivered]);
-                if (e != cudaSuccess) return cu_fail(e, "D2H");
-            }
-            deliver(delivered);
-        }
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) return cu_fail(e, "kernels");
-        for (uint32_t u = 0; u < p->n_utts && !rc; u++)
-            if (h_err[u]) rc = fail(ctx, CTTS_GPU_ERR_DEVICE, "utterance %u: device error %u", u, h_err[u]);
-    } else if (!rc) {
-        rc = ctts_gpu_plan_read_counts(ctx, p, out_counts);   // waits for the kernels
-    }
-    auto t3 = now();
-    cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
-    if (e != cudaSuccess && !rc) rc = fail(ctx, CTTS_GPU_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
-    auto t4 = now();
-    ctts_gpu_plan_destroy(p);
-    if (trace && !tev.empty()) {
-        // per chunk, relative to the start of the run: assembly done, WSOLA done, copy done
-        for (size_t i = 1; i + 2 < tev.size(); i += 3) {
-            float a = 0, b = 0, c = 0;
-            cudaEventElapsedTime(&a, tev[0], tev[i]);
-            cudaEventElapsedTime(&b, tev[0], tev[i + 1]);
-            cudaEventElapsedTime(&c, tev[0], tev[i + 2]);
-            fprintf(stderr, "  chunk %zu: assembled at %.1f ms, stretched at %.1f ms, on the host at %.1f ms\n", (i - 1) / 3, a, b, c);
-        }
-        for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
-    }
-    if (trace)
-        fprintf(stderr, "ctts_gpu_synth_batch: compile+upload %.1f ms, enqueue %u chunks %.1f ms, kernels done +%.1f ms, copies done +%.1f ms\n",
-                ms(t0, t1), nc, ms(t1, t2), ms(t2, t3), ms(t3, t4));
-    return rc;
+    const int rc_end = ctts_gpu_session_end(s, nullptr);
+    return rc ? rc : rc_end;
 }
 
 }  // extern "C"

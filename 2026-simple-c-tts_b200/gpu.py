@@ -65,6 +65,9 @@ def lib(build: bool = True) -> C.CDLL:
         L.ctts_gpu_plan_read_pre.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint64, u64p]
         L.ctts_gpu_plan_info.argtypes = [vp, C.POINTER(RunInfo)]
         L.ctts_gpu_plan_wsola_stats.argtypes = [vp, vp, C.POINTER(WsolaStats)]
+        L.ctts_gpu_session_begin.argtypes = [vp, C.POINTER(AssemblyParams), vp, C.c_uint64, vp, vp, C.POINTER(vp)]
+        L.ctts_gpu_session_submit.argtypes = [vp, C.POINTER(CBatchPlan), vp, vp]
+        L.ctts_gpu_session_end.argtypes = [vp, u64p]
         _lib = L
     return _lib
 
@@ -220,6 +223,27 @@ class GpuSynth:
         self._check(L.ctts_gpu_synth_batch_stream(self._h, C.byref(cp), C.byref(params), pcm_out.ctypes.data,
                                                   out_offsets.ctypes.data, counts.ctypes.data, cb, None))
         return pcm_out, out_offsets, counts[:plan.n_utts]
+
+    def synth_pieces(self, pieces: list[BatchPlan], params: AssemblyParams, pcm_out: np.ndarray):
+        """A session fed with the given plans, one piece each (ctts_gpu_session_*).
+        Returns (offsets, counts) over all utterances of all pieces, in order."""
+        L = lib()
+        h = C.c_void_p()
+        self._check(L.ctts_gpu_session_begin(self._h, C.byref(params), pcm_out.ctypes.data, pcm_out.size, None, None, C.byref(h)))
+        n = sum(p.n_utts for p in pieces)
+        off = np.zeros(max(n, 1), dtype=np.uint64)
+        cnt = np.zeros(max(n, 1), dtype=np.uint32)
+        at, rc = 0, 0
+        for p in pieces:
+            cp = p.as_c()
+            rc = L.ctts_gpu_session_submit(h, C.byref(cp), off[at:].ctypes.data, cnt[at:].ctypes.data)
+            if rc:
+                break
+            at += p.n_utts
+        used = C.c_uint64()
+        rc_end = L.ctts_gpu_session_end(h, C.byref(used))
+        self._check(rc or rc_end)
+        return off[:n], cnt[:n]
 
     def synth_list(self, plan: BatchPlan, params: AssemblyParams) -> list[np.ndarray]:
         pcm, off, cnt = self.synth_batch(plan, params)

@@ -10,8 +10,10 @@ characters at speed 1.0 on the seeded synthetic voice).  Prints ONE JSON line.
 
 value      audio-seconds synthesised per second, plan and voice resident in HBM,
            timed with CUDA events on the launching stream, max over ranks.
-e2e        the same through the drop-in C-ABI call ctts_gpu_synth_batch() with
-           host buffers (plan H2D and PCM D2H inside the timed region).
+e2e        TEXT -> host PCM through ctts_b200_synth_texts (libctts_b200.so): the text front end's planner
+           threads feeding a device session, host buffers, every copy inside the timed region.  This
+           is what the reference arm times (texts as C strings in memory -> PCM in memory), so the two are
+           like for like.  e2e.plan_to_pcm is the back end alone (ctts_gpu_synth_batch on a ready plan).
 roofline   algorithmic bytes of the assembly kernel / its duration / measured HBM peak.
 cpu_baseline  the unmodified reference (oracle/_ref/ctts_ref_bench, N processes) on a
            bounded sample of the same workload, rank 0 only.
@@ -296,38 +298,53 @@ def main() -> int:
     total_ms = evs[0].elapsed_time(evs[args.steps])
     rp.counts()  # surfaces device error flags
 
-    # ---- e2e through the drop-in call, host buffers, copies inside the timed region
+    # ---- e2e, host buffers, copies inside the timed region: (1) plan -> PCM through the drop-in call
+    #      ctts_gpu_synth_batch, (2) TEXT -> PCM through ctts_b200_synth_texts (planner threads + device session)
     e2e = None
     if not args.no_e2e:
+        pipe = importlib.import_module("2026-simple-c-tts_b200.pipeline")
         offsets = rp.out_offsets()
-        host_out = torch.empty(max(out_samples, 8), dtype=torch.int16).pin_memory()
+        host_out = torch.empty(max(out_samples, 8) + 4096, dtype=torch.int16).pin_memory()
         host_np = host_out.numpy()
         e2e_steps = max(1, min(args.e2e_steps, args.steps))
-        g.synth_batch(plan, prm, host_np, offsets)  # warm-up (allocates the device buffer once)
+        g.synth_batch(plan, prm, host_np, offsets)  # warm-up (allocates the lanes' buffers once)
         sync_all()
         te = time.perf_counter()
         for _ in range(e2e_steps):
             _, _, c2 = g.synth_batch(plan, prm, host_np, offsets)
         torch.cuda.synchronize(local_rank)
+        plan_s_e2e = (time.perf_counter() - te) / e2e_steps
+        tb = pipe.TextBatch(texts, speeds)
+        pipe.synth_texts(fr, g, tb, host_np)          # warm-up
+        sync_all()
+        te = time.perf_counter()
+        for _ in range(e2e_steps):
+            _, c3, used, tm = pipe.synth_texts(fr, g, tb, host_np)
+        torch.cuda.synchronize(local_rank)
         e2e_s = (time.perf_counter() - te) / e2e_steps
+        assert np.array_equal(c3, c2), "text pipeline and planned batch disagree"
         h2d = int(plan.ops.nbytes + plan.utt_op_begin.nbytes + plan.speed.nbytes)
-        d2h = int(out_samples * 2 + 8 * plan.n_utts)
+        d2h = int(used * 2 + 8 * plan.n_utts)
         e2e = {"seconds_per_step": e2e_s, "h2d": h2d, "d2h": d2h, "steps": e2e_steps,
-               "audio_s": float(c2.astype(np.int64).sum()) / SAMPLE_RATE}
+               "audio_s": float(c3.astype(np.int64).sum()) / SAMPLE_RATE, "plan_to_pcm_s": plan_s_e2e,
+               "timing": {"first_piece_planned_ms": 1e3 * tm.first_plan_s, "all_planned_ms": 1e3 * tm.all_plans_s,
+                          "all_submitted_ms": 1e3 * tm.all_submitted_s, "done_ms": 1e3 * tm.done_s,
+                          "submitter_waited_for_plans_ms": 1e3 * tm.wait_for_plans_s}}
 
     # ---- reduce over ranks: time = max, work = sum
     t_rank = torch.tensor([total_ms, audio_s, e2e["seconds_per_step"] if e2e else 0.0,
-                           e2e["audio_s"] if e2e else 0.0], dtype=torch.float64, device=f"cuda:{local_rank}")
+                           e2e["audio_s"] if e2e else 0.0, e2e["plan_to_pcm_s"] if e2e else 0.0],
+                          dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         mx = t_rank.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t_rank.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         total_ms_all, audio_all = float(mx[0]), float(sm[1])
-        e2e_s_all, e2e_audio_all = float(mx[2]), float(sm[3])
+        e2e_s_all, e2e_audio_all, e2e_plan_s_all = float(mx[2]), float(sm[3]), float(mx[4])
     else:
         total_ms_all, audio_all = total_ms, audio_s
-        e2e_s_all, e2e_audio_all = (e2e["seconds_per_step"], e2e["audio_s"]) if e2e else (0.0, 0.0)
+        e2e_s_all, e2e_audio_all, e2e_plan_s_all = (e2e["seconds_per_step"], e2e["audio_s"], e2e["plan_to_pcm_s"]) if e2e else (0.0, 0.0, 0.0)
 
     if rank == 0:
         ms_per_step = total_ms_all / args.steps
@@ -379,7 +396,12 @@ def main() -> int:
             line["e2e"] = {"value": e2e_audio_all / e2e_s_all, "unit": UNIT,
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                            "steps": e2e["steps"], "ms_per_step": 1e3 * e2e_s_all,
-                           "call": "ctts_gpu_synth_batch (pinned host PCM buffer)"}
+                           "call": "ctts_b200_synth_texts: texts (C strings) -> pinned host PCM; planner threads feed a device "
+                                   "session piece by piece, like for like with the reference arm (text -> PCM)",
+                           "host_threads": cores, "rank0_timing": e2e["timing"],
+                           "d2h_GBps_all_gpus": 1e-9 * world * e2e["d2h"] / e2e_s_all,
+                           "plan_to_pcm": {"value": e2e_audio_all / e2e_plan_s_all, "ms_per_step": 1e3 * e2e_plan_s_all,
+                                           "call": "ctts_gpu_synth_batch on a ready plan (the back end alone)"}}
         if not args.no_cpu_baseline:
             try:
                 n_sample = cpu_sample_size(args.utts, cores, args.workload == "mixed")

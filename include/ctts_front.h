@@ -70,6 +70,8 @@ void ctts_front_close(ctts_front* f);
  * glibc, which rejects the BSD-only [[:<:]] the reference emits) */
 uint32_t ctts_front_rule_count(const ctts_front* f);
 uint32_t ctts_front_unit_count(const ctts_front* f);
+/* longest unit of the voice in samples (CTTSIndexEntry.sample_count, ctts.h:108) */
+uint32_t ctts_front_max_unit_samples(const ctts_front* f);
 
 /* batch-constant scalar parameters for the executor */
 void ctts_front_params(const ctts_front* f, ctts_assembly_params* out);
@@ -85,6 +87,11 @@ void ctts_front_free(void* p);
  * (engine->units_found/missing, ctts.c:3861, :3866). */
 int ctts_front_plan_batch(ctts_front* f, const char* const* texts, const float* speeds,
                           uint32_t n, ctts_batch_plan* out, uint32_t* stats);
+/* The same with an explicit number of worker threads (0: chosen from the batch size and the host's
+ * cores; 1: the calling thread alone -- what a caller that runs its own pool of planners wants,
+ * ctts_b200_synth_texts).  Re-entrant: the handle is only read. */
+int ctts_front_plan_batch_threads(ctts_front* f, const char* const* texts, const float* speeds,
+                                  uint32_t n, uint32_t threads, ctts_batch_plan* out, uint32_t* stats);
 void ctts_front_plan_free(ctts_batch_plan* plan);
 
 /* The WORD_END op the walk emits for word `word_index` of `total_words` in a

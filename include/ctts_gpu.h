@@ -60,7 +60,8 @@ int ctts_gpu_plan_bounds(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, u
  * synchronous on return.  Utterance u's PCM is written to
  * pcm_out[out_offsets[u] .. out_offsets[u] + out_counts[u]); out_offsets has
  * n_utts+1 entries, each a multiple of 8 samples, and
- * out_offsets[u+1]-out_offsets[u] must be >= ctts_gpu_plan_bounds()[u]. */
+ * out_offsets[u+1]-out_offsets[u] must be >= ctts_gpu_plan_bounds()[u].  Samples of a slot past
+ * out_counts[u] are unspecified (they may hold PCM of an earlier call on this context). */
 int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan,
                          const ctts_assembly_params* params, int16_t* pcm_out,
                          const uint64_t* out_offsets, uint32_t* out_counts);
@@ -69,13 +70,38 @@ int ctts_gpu_synth_batch(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan,
  * utterance order, as soon as the PCM and the counts of utterances [utt_begin, utt_end) are in host
  * memory -- while the device is still working on later utterances -- so the caller can write WAV files
  * (ctts_write_wav, ctts.c:809) or hand audio on without waiting for the batch (the output path of a
- * 65 536-paragraph batch is 87 GB of PCM).  A device-side error for an utterance is
- * reported by the return value after the last callback.  on_chunk == NULL: ctts_gpu_synth_batch. */
+ * 65 536-paragraph batch is 87 GB of PCM).  A range that holds an utterance with a device-side
+ * error is not handed over, nor is any range after it; the error is the return value.
+ * on_chunk == NULL: ctts_gpu_synth_batch. */
 typedef void (*ctts_gpu_chunk_fn)(void* user, uint32_t utt_begin, uint32_t utt_end);
 int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan,
                                 const ctts_assembly_params* params, int16_t* pcm_out,
                                 const uint64_t* out_offsets, uint32_t* out_counts,
                                 ctts_gpu_chunk_fn on_chunk, void* user);
+
+/* ---- sessions: ONE batch fed in pieces --------------------------------------------------------------
+ * The reference interleaves text work and sample work inside one call (ctts.c:3638-3655, :3689-3871).  A
+ * session gives the batch equivalent: the caller plans piece c+1 (the text front end, on host threads)
+ * while the device assembles piece c and piece c-1 travels to pcm_out.  ctts_gpu_synth_batch(_stream) is a
+ * session over the pieces of one plan; ctts_b200_synth_texts (ctts_b200.h) is a session fed by the front end.
+ *
+ * begin    pcm_out (page-locked for full copy speed) holds `capacity` samples; on_piece (may be NULL) is called
+ *          on the submitting thread, in order, with the session-wide utterance range of every piece whose PCM
+ *          and counts have arrived.
+ * submit   asynchronous: returns as soon as the piece is compiled and enqueued (up to three pieces are in
+ *          flight; a fourth waits for the oldest).  out_offsets[i] (n entries, written before the call
+ *          returns) is where utterance i of the piece will land: packed 16-byte aligned slots sized by the
+ *          bounds, appended to what earlier pieces took.  out_counts[i] (n entries) is written when the
+ *          piece has arrived, at the latest by ctts_gpu_session_end; the plan may be freed when submit returns.
+ * end      waits for everything, returns the first error of the session; *samples_used (may be NULL) is
+ *          the slot space taken in pcm_out.
+ * One session per context at a time.  Samples of a slot past out_counts[i] are unspecified. */
+typedef struct ctts_gpu_session ctts_gpu_session;
+int ctts_gpu_session_begin(ctts_gpu_ctx* ctx, const ctts_assembly_params* params, int16_t* pcm_out,
+                           uint64_t capacity, ctts_gpu_chunk_fn on_piece, void* user, ctts_gpu_session** out);
+int ctts_gpu_session_submit(ctts_gpu_session* s, const ctts_batch_plan* piece, uint64_t* out_offsets,
+                            uint32_t* out_counts);
+int ctts_gpu_session_end(ctts_gpu_session* s, uint64_t* samples_used);
 
 /* ---- resident-plan path: upload once, run many times, PCM stays in HBM ---- */
 

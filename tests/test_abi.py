@@ -9,7 +9,7 @@ import pytest
 def _declared(header: str) -> list[str]:
     text = open(header).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(ctts_(?:gpu|front)_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(ctts_(?:gpu|front|b200)_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_gpu_library_exports_header_symbols(H):
@@ -27,6 +27,28 @@ def test_front_library_exports_header_symbols(H):
     assert len(names) >= 12
     for n in names:
         assert hasattr(L, n), n
+
+
+def test_pipeline_library_exports_header_symbols(H):
+    """libctts_b200.so (texts -> PCM over the two libraries): loads without a device, exports ctts_b200.h."""
+    pipe = H.importlib.import_module("2026-simple-c-tts_b200.pipeline")
+    L = pipe.lib()
+    names = _declared(os.path.join(H.ROOT, "include", "ctts_b200.h"))
+    assert names == ["ctts_b200_capacity_hint", "ctts_b200_synth_texts"]
+    for n in names:
+        assert hasattr(L, n), n
+    assert C.sizeof(pipe.Timing) == 5 * 8 and C.sizeof(pipe.Options) == 24
+
+
+def test_capacity_hint_covers_the_bounds(H, small_db, front_small):
+    """ctts_b200_capacity_hint (no planning) must not be smaller than the slot space the planned batch needs."""
+    pipe = H.importlib.import_module("2026-simple-c-tts_b200.pipeline")
+    texts = H.corpus.batch(40, seed=5, target_chars=150) + ["", "1234567 e 89", "a"]
+    speeds = [1.0, 0.5, 2.0, 0.7] * 10 + [1.0, 0.5, 0.5]
+    plan = front_small.plan(texts, speeds)
+    _, out, _ = front_small.bounds(plan)
+    need = int(sum((int(b) + 7) // 8 * 8 + 8 for b in out))
+    assert pipe.capacity_hint(front_small, pipe.TextBatch(texts, speeds)) >= need
 
 
 def test_plan_op_abi_is_32_bytes(H):

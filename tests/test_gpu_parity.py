@@ -538,3 +538,51 @@ def test_streaming_call_hands_over_finished_ranges(H, gpu, small_db, oracle_smal
             want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))
             _assert_same(snap[u], want, f"utt {u} at callback time")
             _assert_same(pcm[int(off[u]):int(off[u]) + int(cnt[u])], want, f"utt {u} at return")
+
+
+def test_session_pieces_equal_one_batch(H, gpu, synth_small, oracle_small, front_small):
+    """ctts_gpu_session_*: a batch fed as pieces of different sizes (more pieces than lanes, an empty piece,
+    plain and stretched utterances) lands in packed slots and equals the oracle bit for bit."""
+    prm = front_small.params()
+    texts = H.corpus.batch(23, seed=131, target_chars=90) + ["", "olá mundo"]
+    speeds = [1.0, 1.5, 1.0, 0.6, 1.0, 2.0, 1.0, 1.0, 0.9, 1.0] * 2 + [1.3, 1.0, 1.0, 1.0, 1.5]
+    plan = front_small.plan(texts, speeds)
+    cuts = [0, 1, 4, 4, 9, 10, 17, 24, 25]   # (4, 4): an empty piece
+    pieces = [plan.select(range(a, b)) for a, b in zip(cuts[:-1], cuts[1:])]
+    cap = int(synth_small.layout(plan)[-1])
+    pcm = np.zeros(cap + 64, dtype=np.int16)
+    off, cnt = synth_small.synth_pieces(pieces, prm, pcm)
+    assert len(off) == plan.n_utts and (off % 8 == 0).all() and (np.diff(off.astype(np.int64)) > 0).all()
+    for u in range(plan.n_utts):
+        want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))
+        _assert_same(pcm[int(off[u]):int(off[u]) + int(cnt[u])], want, f"session utt {u}")
+    # a buffer that is too small is an argument error, not a crash
+    with pytest.raises(gpu.GpuError):
+        synth_small.synth_pieces(pieces, prm, np.zeros(cap // 2, dtype=np.int16))
+    # ... and the context is usable afterwards
+    off2, cnt2 = synth_small.synth_pieces(pieces[:3], prm, pcm)
+    assert np.array_equal(cnt2, cnt[:4])
+
+
+def test_text_pipeline_equals_the_planned_batch(H, gpu, synth_small, front_small, oracle_small):
+    """ctts_b200_synth_texts (planner threads feeding a device session, the text -> PCM drop-in for N calls of
+    ctts_synthesize, ctts.c:3623): for every piece size / thread count the PCM, the counts and the unit
+    statistics equal those of the batch planned in one go and run through ctts_gpu_synth_batch -- and the oracle."""
+    pipe = H.importlib.import_module("2026-simple-c-tts_b200.pipeline")
+    prm = front_small.params()
+    texts = H.corpus.batch(61, seed=977, target_chars=100) + ["", "olá mundo", "São 1234 casas, não é?"]
+    speeds = list(H.corpus.mixed_speeds(64, seed=3))
+    speeds[::3] = [1.0] * len(speeds[::3])
+    plan = front_small.plan(texts, speeds)
+    ref = synth_small.synth_list(plan, prm)
+    for u in (0, 7, 33, 62, 63):
+        want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))
+        _assert_same(ref[u], want, f"utt {u}")
+    batch = pipe.TextBatch(texts, speeds)
+    pcm = np.zeros(pipe.capacity_hint(front_small, batch), dtype=np.int16)
+    for piece_utts, threads in ((1, 3), (7, 1), (16, 4), (0, 0), (1000, 2)):
+        off, cnt, used, tm, stats = pipe.synth_texts(front_small, synth_small, batch, pcm, piece_utts, threads, want_stats=True)
+        assert used <= pcm.size and tm.done_s >= tm.all_submitted_s >= 0
+        assert np.array_equal(stats[:, 0], plan.found) and np.array_equal(stats[:, 1], plan.missing)
+        for u in range(plan.n_utts):
+            _assert_same(pcm[int(off[u]):int(off[u]) + int(cnt[u])], ref[u], f"pieces of {piece_utts}, {threads} threads, utt {u}")

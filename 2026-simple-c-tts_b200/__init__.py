@@ -6,6 +6,6 @@ C-ABI `ctts_gpu_synth_batch()` (gpu.py -> csrc/gpu), and the voice.db / corpus
 helpers tests and bench use.  The directory name is not a Python identifier;
 import it with importlib.import_module("2026-simple-c-tts_b200").
 """
-from . import _build, corpus, front, sharding, voicedb  # noqa: F401  (gpu / pipeline load CUDA libraries: import them explicitly)
+from . import _build, corpus, front, hostgather, sharding, voicedb  # noqa: F401  (gpu / pipeline load CUDA libraries: import them explicitly)
 
-__all__ = ["_build", "corpus", "front", "sharding", "voicedb"]
+__all__ = ["_build", "corpus", "front", "hostgather", "sharding", "voicedb"]

@@ -4,7 +4,7 @@
  *
  * The reference's ctts_synthesize (ctts.c:3623) does, per utterance, normalisation (:3638-3655), the walk
  * with unit selection (:3689-3871, :1406) and every sample loop in one call on one core.  Here:
- *   planner threads   take pieces (128 utterances) off a shared counter and plan them with the unchanged
+ *   planner threads   take pieces (8, 16, .. 128 utterances) off a shared counter and plan them with the unchanged
  *                     front end (ctts_front_plan_batch_threads(..., 1, ...): re-entrant, the handle is only
  *                     read), at most LOOKAHEAD pieces ahead of the device;
  *   the calling thread submits finished plans in order to a ctts_gpu_session (asynchronous: up to three
@@ -32,7 +32,8 @@ typedef struct {
     const char* const* texts;
     const float* speeds;
     uint32_t* stats;
-    uint32_t n, piece_utts, n_pieces;
+    uint32_t n, n_pieces;
+    uint32_t* piece_begin;     /* n_pieces + 1: the first pieces are small so that the device starts early */
     piece_slot* slots;
     pthread_mutex_t mu;
     pthread_cond_t cv_ready;   /* a piece became ready */
@@ -61,7 +62,7 @@ static void* planner(void* arg) {
         }
         const uint32_t i = P->next++;
         pthread_mutex_unlock(&P->mu);
-        const uint32_t u0 = i * P->piece_utts, cnt = (u0 + P->piece_utts <= P->n ? P->piece_utts : P->n - u0);
+        const uint32_t u0 = P->piece_begin[i], cnt = P->piece_begin[i + 1] - u0;
         ctts_batch_plan pl;
         int rc = ctts_front_plan_batch_threads(P->front, P->texts + u0, P->speeds ? P->speeds + u0 : NULL, cnt, 1, &pl,
                                                P->stats ? P->stats + 2 * (size_t)u0 : NULL);
@@ -110,8 +111,20 @@ int ctts_b200_synth_texts(ctts_front* front, ctts_gpu_ctx* gpu, const char* cons
     P.speeds = speeds;
     P.stats = stats;
     P.n = n;
-    P.piece_utts = opt && opt->piece_utts ? opt->piece_utts : 128;
-    P.n_pieces = (n + P.piece_utts - 1) / P.piece_utts;
+    /* piece sizes 8, 16, 32, .. up to piece_utts: the first plan reaches the device after ~1 ms of planning
+     * instead of ~10, the later pieces are large enough to keep the kernels efficient */
+    const uint32_t piece_utts = opt && opt->piece_utts ? opt->piece_utts : 128;
+    P.piece_begin = malloc(((size_t)n + 2) * sizeof *P.piece_begin);
+    if (!P.piece_begin) return CTTS_GPU_ERR_OUT_OF_MEMORY;
+    {
+        uint32_t u = 0, sz = piece_utts < 8 ? piece_utts : 8;
+        P.piece_begin[0] = 0;
+        while (u < n) {
+            u += sz < n - u ? sz : n - u;
+            P.piece_begin[++P.n_pieces] = u;
+            sz = 2 * sz < piece_utts ? 2 * sz : piece_utts;
+        }
+    }
     P.t0 = now_s();
     long cores = sysconf(_SC_NPROCESSORS_ONLN);
     uint32_t T = opt && opt->threads ? opt->threads : (uint32_t)(cores > 1 ? cores - 1 : 1);
@@ -123,12 +136,16 @@ int ctts_b200_synth_texts(ctts_front* front, ctts_gpu_ctx* gpu, const char* cons
     ctts_front_params(front, &prm);
     ctts_gpu_session* ses = NULL;
     int rc = ctts_gpu_session_begin(gpu, &prm, pcm_out, capacity, opt ? opt->on_piece : NULL, opt ? opt->user : NULL, &ses);
-    if (rc) return rc;
+    if (rc) {
+        free(P.piece_begin);
+        return rc;
+    }
     P.slots = calloc(P.n_pieces ? P.n_pieces : 1, sizeof *P.slots);
     pthread_t* tids = calloc(T, sizeof *tids);
     if (!P.slots || !tids) {
         free(P.slots);
         free(tids);
+        free(P.piece_begin);
         ctts_gpu_session_end(ses, NULL);
         return CTTS_GPU_ERR_OUT_OF_MEMORY;
     }
@@ -151,7 +168,7 @@ int ctts_b200_synth_texts(ctts_front* front, ctts_gpu_ctx* gpu, const char* cons
             rc = st;
             break;
         }
-        const uint32_t u0 = i * P.piece_utts;
+        const uint32_t u0 = P.piece_begin[i];
         rc = ctts_gpu_session_submit(ses, &P.slots[i].plan, out_offsets + u0, out_counts + u0);
         ctts_front_plan_free(&P.slots[i].plan);   /* the session keeps nothing of the plan */
         P.slots[i].state = 2;
@@ -182,5 +199,6 @@ int ctts_b200_synth_texts(ctts_front* front, ctts_gpu_ctx* gpu, const char* cons
     pthread_cond_destroy(&P.cv_room);
     free(P.slots);
     free(tids);
+    free(P.piece_begin);
     return rc;
 }

@@ -1526,4 +1526,108 @@ int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, 
     return rc ? rc : rc_end;
 }
 
+
+// ---------------------------------------------------------------- one batch on several GPUs
+
+// Utterances are independent (no state crosses ctts_synthesize calls, ctts.c:3623, except the read-only
+// voice): the batch is partitioned by utterance -- greedy longest-processing-time on the host-known slot
+// sizes, every device holding its own replica of the voice (one context each) -- and every shard is run
+// by its own host thread as a session that delivers straight into the caller's buffer at the
+// utterance's own slot: the host gather is the layout itself, there is no data-path collective.
+int ctts_gpu_multi_synth_batch(ctts_gpu_ctx* const* ctxs, uint32_t n_ctx, const ctts_batch_plan* plan,
+                               const ctts_assembly_params* params, int16_t* pcm_out, const uint64_t* out_offsets,
+                               uint32_t* out_counts, uint32_t* shard_of) {
+    if (!ctxs || !n_ctx || !plan || !params || !pcm_out || !out_offsets || !out_counts) return CTTS_GPU_ERR_INVALID_ARG;
+    for (uint32_t d = 0; d < n_ctx; d++)
+        if (!ctxs[d]) return CTTS_GPU_ERR_INVALID_ARG;
+    if (plan->n_utts && (!plan->utt_op_begin || !plan->speed)) return CTTS_GPU_ERR_INVALID_ARG;
+    const uint32_t n = plan->n_utts;
+    for (uint32_t u = 0; u < n; u++)
+        if (out_offsets[u + 1] < out_offsets[u] || plan->utt_op_begin[u + 1] < plan->utt_op_begin[u] || plan->utt_op_begin[u + 1] > plan->n_ops)
+            return fail(ctxs[0], CTTS_GPU_ERR_INVALID_ARG, "offsets of utterance %u are not ascending", u);
+    // ---- LPT partition; the cost of an utterance is its slot size (what has to cross PCIe), plus its
+    //      pre-stretch length when it goes through WSOLA
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::vector<uint64_t> cost(n);
+    for (uint32_t u = 0; u < n; u++) {
+        cost[u] = out_offsets[u + 1] - out_offsets[u];
+        uint32_t hop = 0;
+        if (needs_stretch(plan->speed[u], &hop)) cost[u] += (cost[u] * 128) / std::max<uint32_t>(hop, 1);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
+    std::vector<std::vector<uint32_t>> shard(n_ctx);
+    {
+        std::vector<uint64_t> load(n_ctx, 0);
+        for (const uint32_t u : order) {
+            const uint32_t d = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+            shard[d].push_back(u);
+            load[d] += cost[u];
+        }
+        for (std::vector<uint32_t>& sh : shard) std::sort(sh.begin(), sh.end());   // batch order inside a shard
+    }
+    if (shard_of)
+        for (uint32_t d = 0; d < n_ctx; d++)
+            for (const uint32_t u : shard[d]) shard_of[u] = d;
+
+    // ---- one host thread per device
+    std::vector<int> rcs(n_ctx, 0);
+    auto run_shard = [&](uint32_t d) {
+        ctts_gpu_ctx* ctx = ctxs[d];
+        const std::vector<uint32_t>& mine = shard[d];
+        const uint32_t m = (uint32_t)mine.size();
+        if (!m) return;
+        // the shard as a plan of its own (CSR needs contiguous ops) and the slots of its utterances
+        std::vector<uint32_t> begin((size_t)m + 1, 0);
+        std::vector<float> speed(m);
+        std::vector<uint64_t> off(m), cap(m);
+        std::vector<uint32_t> counts(m, 0);
+        uint64_t n_ops = 0;
+        for (uint32_t i = 0; i < m; i++) n_ops += plan->utt_op_begin[mine[i] + 1] - plan->utt_op_begin[mine[i]];
+        if (n_ops > 0xffffffffull) { rcs[d] = CTTS_GPU_ERR_INVALID_ARG; return; }
+        std::vector<ctts_plan_op> ops((size_t)std::max<uint64_t>(n_ops, 1));
+        uint32_t at = 0;
+        for (uint32_t i = 0; i < m; i++) {
+            const uint32_t u = mine[i], b = plan->utt_op_begin[u], e = plan->utt_op_begin[u + 1];
+            if (e > b) memcpy(ops.data() + at, plan->ops + b, (size_t)(e - b) * sizeof(ctts_plan_op));
+            at += e - b;
+            begin[i + 1] = at;
+            speed[i] = plan->speed[u];
+            off[i] = out_offsets[u];
+            cap[i] = out_offsets[u + 1] - out_offsets[u];
+        }
+        ctts_batch_plan sub{m, (uint32_t)n_ops, begin.data(), speed.data(), ops.data()};
+        ctts_gpu_session* s = nullptr;
+        int rc = ctts_gpu_session_begin(ctx, params, pcm_out, out_offsets[n], nullptr, nullptr, &s);
+        if (rc) { rcs[d] = rc; return; }
+        const uint64_t chunk = ctx->knobs.chunk_samples;
+        uint64_t acc = 0;
+        for (uint32_t i0 = 0, i = 0; i < m && !rc; i++) {
+            acc += cap[i];
+            if (acc >= chunk || i + 1 == m) {
+                ctts_batch_plan piece = sub;
+                piece.n_utts = i + 1 - i0;
+                piece.utt_op_begin = begin.data() + i0;
+                piece.speed = speed.data() + i0;
+                rc = submit_piece(s, &piece, off.data() + i0, cap.data() + i0, nullptr, counts.data() + i0);
+                i0 = i + 1;
+                acc = 0;
+            }
+        }
+        const int rc_end = ctts_gpu_session_end(s, nullptr);
+        rcs[d] = rc ? rc : rc_end;
+        for (uint32_t i = 0; i < m; i++) out_counts[mine[i]] = counts[i];
+    };
+    std::vector<std::thread> th;
+    for (uint32_t d = 1; d < n_ctx; d++) th.emplace_back(run_shard, d);
+    run_shard(0);
+    for (std::thread& t : th) t.join();
+    for (uint32_t d = 0; d < n_ctx; d++)
+        if (rcs[d]) {
+            if (d) snprintf(ctxs[0]->err, sizeof ctxs[0]->err, "device %u: %s", d, ctxs[d]->err);
+            return rcs[d];
+        }
+    return CTTS_GPU_OK;
+}
+
 }  // extern "C"

@@ -68,6 +68,8 @@ def lib(build: bool = True) -> C.CDLL:
         L.ctts_gpu_session_begin.argtypes = [vp, C.POINTER(AssemblyParams), vp, C.c_uint64, vp, vp, C.POINTER(vp)]
         L.ctts_gpu_session_submit.argtypes = [vp, C.POINTER(CBatchPlan), vp, vp]
         L.ctts_gpu_session_end.argtypes = [vp, u64p]
+        L.ctts_gpu_multi_synth_batch.argtypes = [C.POINTER(vp), C.c_uint32, C.POINTER(CBatchPlan), C.POINTER(AssemblyParams),
+                                                 vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -258,3 +260,23 @@ class GpuSynth:
             off_ptr = out_offsets.ctypes.data
         self._check(lib().ctts_gpu_plan_create(self._h, C.byref(cp), C.byref(params), off_ptr, C.byref(h)))
         return ResidentPlan(self, h, plan.n_utts)
+
+
+def multi_synth_batch(ctxs: list[GpuSynth], plan: BatchPlan, params: AssemblyParams, pcm_out: np.ndarray | None = None,
+                      out_offsets: np.ndarray | None = None):
+    """ctts_gpu_multi_synth_batch: one batch partitioned over several contexts (one per GPU), every shard
+    delivered into the caller's buffer at the utterance's own slot.  Returns (pcm, offsets, counts, shard_of)."""
+    if out_offsets is None:
+        out_offsets = ctxs[0].layout(plan)
+    out_offsets = np.ascontiguousarray(out_offsets, dtype=np.uint64)
+    total = int(out_offsets[-1])
+    if pcm_out is None:
+        pcm_out = np.empty(max(total, 1), dtype=np.int16)
+    assert pcm_out.dtype == np.int16 and pcm_out.size >= total and pcm_out.flags["C_CONTIGUOUS"]
+    counts = np.zeros(max(plan.n_utts, 1), dtype=np.uint32)
+    shard_of = np.zeros(max(plan.n_utts, 1), dtype=np.uint32)
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    cp = plan.as_c()
+    ctxs[0]._check(lib().ctts_gpu_multi_synth_batch(arr, len(ctxs), C.byref(cp), C.byref(params), pcm_out.ctypes.data,
+                                                     out_offsets.ctypes.data, counts.ctypes.data, shard_of.ctypes.data))
+    return pcm_out, out_offsets, counts[:plan.n_utts], shard_of[:plan.n_utts]

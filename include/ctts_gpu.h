@@ -103,6 +103,17 @@ int ctts_gpu_session_submit(ctts_gpu_session* s, const ctts_batch_plan* piece, u
                             uint32_t* out_counts);
 int ctts_gpu_session_end(ctts_gpu_session* s, uint64_t* samples_used);
 
+/* ---- one batch on several GPUs of one box ---------------------------------------------------------
+ * ctxs[d] is a context on device d (each holds its own replica of the voice: ctts_gpu_init per device).
+ * The batch is partitioned by utterance (greedy longest-processing-time on the slot sizes, WSOLA
+ * utterances weighted up), every shard runs on its own host thread and device and delivers straight into
+ * the caller's buffer at the utterance's slot: the host-side gather of BASELINE's multi-GPU configuration,
+ * no data-path collective.  Arguments as ctts_gpu_synth_batch; shard_of (may be NULL, n_utts entries)
+ * receives the device every utterance ran on.  The contexts must not be in use by other threads. */
+int ctts_gpu_multi_synth_batch(ctts_gpu_ctx* const* ctxs, uint32_t n_ctx, const ctts_batch_plan* plan,
+                               const ctts_assembly_params* params, int16_t* pcm_out,
+                               const uint64_t* out_offsets, uint32_t* out_counts, uint32_t* shard_of);
+
 /* ---- resident-plan path: upload once, run many times, PCM stays in HBM ---- */
 
 /* Uploads the plan, derives the region tasks and output layout

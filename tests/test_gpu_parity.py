@@ -586,3 +586,37 @@ def test_text_pipeline_equals_the_planned_batch(H, gpu, synth_small, front_small
         assert np.array_equal(stats[:, 0], plan.found) and np.array_equal(stats[:, 1], plan.missing)
         for u in range(plan.n_utts):
             _assert_same(pcm[int(off[u]):int(off[u]) + int(cnt[u])], ref[u], f"pieces of {piece_utts}, {threads} threads, utt {u}")
+
+
+def _multi_check(H, gpu, devices, small_db, oracle_small, front_small):
+    prm = front_small.params()
+    texts = H.corpus.batch(37, seed=211, target_chars=90) + ["", "olá mundo", "a"]
+    speeds = list(H.corpus.mixed_speeds(40, seed=17))
+    speeds[::2] = [1.0] * len(speeds[::2])
+    plan = front_small.plan(texts, speeds)
+    ctxs = [gpu.GpuSynth(small_db, d) for d in devices]
+    pcm, off, cnt, shard_of = gpu.multi_synth_batch(ctxs, plan, prm)
+    assert set(shard_of.tolist()) == set(range(len(devices)))          # every device got work
+    slot = np.diff(off.astype(np.int64))
+    loads = [int(slot[shard_of == d].sum()) for d in range(len(devices))]
+    assert max(loads) - min(loads) <= 3 * int(slot.max())             # LPT balance (costs weigh WSOLA up)
+    for u in range(plan.n_utts):
+        want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))
+        _assert_same(pcm[int(off[u]):int(off[u]) + int(cnt[u])], want, f"multi utt {u} on device {shard_of[u]}")
+    # the same contexts are usable one by one afterwards
+    one = ctxs[-1].synth_list(plan, prm)
+    assert all(np.array_equal(one[u], pcm[int(off[u]):int(off[u]) + int(cnt[u])]) for u in range(plan.n_utts))
+
+
+def test_multi_device_entry_two_contexts_on_one_gpu(H, gpu, small_db, oracle_small, front_small):
+    """ctts_gpu_multi_synth_batch (BASELINE's multi-GPU configuration: one batch sharded by utterance, host-side
+    gather into the caller's buffer): partition, per-shard host threads and scattered slots, exercised with
+    three contexts on device 0 so that it runs on a one-GPU box."""
+    _multi_check(H, gpu, [0, 0, 0], small_db, oracle_small, front_small)
+
+
+def test_multi_device_entry_on_two_gpus(H, gpu, small_db, oracle_small, front_small):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    _multi_check(H, gpu, list(range(min(torch.cuda.device_count(), 8))), small_db, oracle_small, front_small)

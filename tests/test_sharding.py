@@ -75,3 +75,63 @@ def test_two_rank_sharding_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert ret.get() is True
+
+
+def _gather_worker(rank: int, world: int, port: int, name: str, ret):
+    """The host-side gather of bench.py's strong-scaling leg with a stand-in for the device: every rank writes
+    its shard's (fake) PCM into its own region of the shared buffer and publishes offsets / counts in batch order."""
+    import harness as H
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        hg, sh = H.pkg.hostgather, H.pkg.sharding
+        texts = H.corpus.batch(64, seed=9, target_chars=60)
+        speeds = H.corpus.mixed_speeds(64, seed=2)
+        shards = sh.shard_indices(hg.text_costs(texts, speeds), world)
+        mine = shards[rank]
+        counts = np.array([100 + 3 * len(texts[i]) for i in mine], dtype=np.int64)       # "samples" of my utterances
+        slots = (counts + 7) // 8 * 8 + 8
+        used = int(slots.sum())
+        all_used = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(all_used, torch.tensor([used]))
+        bases = hg.region_bases([int(u) for u in all_used])
+        if rank == 0:
+            sb = hg.SharedBatch(name, len(texts), int(bases[-1]), create=True)
+        dist.barrier()
+        if rank != 0:
+            sb = hg.SharedBatch(name, len(texts), int(bases[-1]), create=False)
+        region = sb.region(bases[rank], bases[rank] + used)
+        off = np.concatenate([[0], np.cumsum(slots)[:-1]])
+        for k, i in enumerate(mine):
+            region[off[k]:off[k] + counts[k]] = (np.arange(counts[k]) + 7 * i) % 30000
+        sb.publish(mine, int(bases[rank]), off, counts)
+        dist.barrier()
+        ok = True
+        if rank == 0:
+            for i in range(len(texts)):
+                want = (np.arange(100 + 3 * len(texts[i])) + 7 * i) % 30000
+                ok = ok and np.array_equal(sb.utterance(i), want.astype(np.int16))
+            ret.put(bool(ok))
+        dist.barrier()
+        sb.close(unlink=rank == 0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_host_gather_through_shared_memory():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.SimpleQueue()
+    name = f"ctts_b200_test_{os.getpid()}"
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, name, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get() is True
+    assert not os.path.exists(os.path.join("/dev/shm", name))

@@ -4,7 +4,7 @@
  *
  * The reference's ctts_synthesize (ctts.c:3623) does, per utterance, normalisation (:3638-3655), the walk
  * with unit selection (:3689-3871, :1406) and every sample loop in one call on one core.  Here:
- *   planner threads   take pieces (8, 16, .. 128 utterances) off a shared counter and plan them with the unchanged
+ *   planner threads   take pieces (16, 32, .. 128 utterances) off a shared counter and plan them with the unchanged
  *                     front end (ctts_front_plan_batch_threads(..., 1, ...): re-entrant, the handle is only
  *                     read), at most LOOKAHEAD pieces ahead of the device;
  *   the calling thread submits finished plans in order to a ctts_gpu_session (asynchronous: up to three
@@ -20,7 +20,7 @@
 
 #include "ctts_b200.h"
 
-#define LOOKAHEAD 24   /* pieces planned ahead of the one being submitted (bounds the memory held in plans) */
+#define LOOKAHEAD 64   /* pieces planned ahead of the one being submitted (bounds the memory held in plans) */
 
 typedef struct {
     ctts_batch_plan plan;
@@ -111,24 +111,29 @@ int ctts_b200_synth_texts(ctts_front* front, ctts_gpu_ctx* gpu, const char* cons
     P.speeds = speeds;
     P.stats = stats;
     P.n = n;
-    /* piece sizes 8, 16, 32, .. up to piece_utts: the first plan reaches the device after ~1 ms of planning
-     * instead of ~10, the later pieces are large enough to keep the kernels efficient */
+    /* A piece is planned by ONE thread (~100 us per utterance) while the device->host copy alone consumes an
+     * utterance every ~25 us: pieces handed over in order starve the device at the start unless the first
+     * ones are small.  So: pieces of 16 utterances for the first two rounds of the planner pool, then 32, 64,
+     * .. up to piece_utts -- by then the planners are a few dozen pieces ahead. */
     const uint32_t piece_utts = opt && opt->piece_utts ? opt->piece_utts : 128;
-    P.piece_begin = malloc(((size_t)n + 2) * sizeof *P.piece_begin);
-    if (!P.piece_begin) return CTTS_GPU_ERR_OUT_OF_MEMORY;
-    {
-        uint32_t u = 0, sz = piece_utts < 8 ? piece_utts : 8;
-        P.piece_begin[0] = 0;
-        while (u < n) {
-            u += sz < n - u ? sz : n - u;
-            P.piece_begin[++P.n_pieces] = u;
-            sz = 2 * sz < piece_utts ? 2 * sz : piece_utts;
-        }
-    }
-    P.t0 = now_s();
     long cores = sysconf(_SC_NPROCESSORS_ONLN);
     uint32_t T = opt && opt->threads ? opt->threads : (uint32_t)(cores > 1 ? cores - 1 : 1);
     if (T > 32) T = 32;
+    if (T < 1) T = 1;
+    P.piece_begin = malloc(((size_t)n + 2) * sizeof *P.piece_begin);
+    if (!P.piece_begin) return CTTS_GPU_ERR_OUT_OF_MEMORY;
+    {
+        uint32_t u = 0;
+        P.piece_begin[0] = 0;
+        while (u < n) {
+            uint32_t shift = P.n_pieces / (2 * T);
+            uint32_t sz = shift > 8 ? piece_utts : 16u << shift;
+            if (sz > piece_utts) sz = piece_utts;
+            u += sz < n - u ? sz : n - u;
+            P.piece_begin[++P.n_pieces] = u;
+        }
+    }
+    P.t0 = now_s();
     if (T > P.n_pieces) T = P.n_pieces;
     if (T < 1) T = 1;
 

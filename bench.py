@@ -101,13 +101,14 @@ def strong_scaling_leg(args, rank, local_rank, world, fr, g, prm, pkg, gpu, sync
     my_counts = rp.counts().astype(np.int64)
     steps = max(3, min(args.steps, 10))
     sync_all()
-    stream = torch.cuda.current_stream(local_rank)
+    stream = torch.cuda.Stream(device=local_rank)   # the context launches on this stream; the events go on it too
     g.set_stream(stream.cuda_stream)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(steps):
-        rp.run(d_out.data_ptr())
-    e1.record(stream)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(steps):
+            rp.run(d_out.data_ptr())
+        e1.record(stream)
     sync_all()
     dev_ms = e0.elapsed_time(e1) / steps
     ws = rp.wsola_stats()

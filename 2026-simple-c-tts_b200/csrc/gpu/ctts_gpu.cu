@@ -192,13 +192,16 @@ struct ctts_gpu_plan {
 
 namespace {
 
+// why the last ctts_gpu_init of this thread failed (there is no context to hold the text then):
+// ctts_gpu_last_error(NULL) returns it
+thread_local char g_init_err[512] = "no context";
+
 int fail(ctts_gpu_ctx* c, int code, const char* fmt, ...) {
-    if (c) {
-        va_list ap;
-        va_start(ap, fmt);
-        vsnprintf(c->err, sizeof c->err, fmt, ap);
-        va_end(ap);
-    }
+    va_list ap;
+    va_start(ap, fmt);
+    if (c) vsnprintf(c->err, sizeof c->err, fmt, ap);
+    else vsnprintf(g_init_err, sizeof g_init_err, fmt, ap);
+    va_end(ap);
     return code;
 }
 
@@ -362,19 +365,23 @@ int scan_plan(const ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, uint64_t big
 extern "C" {
 
 int ctts_gpu_init(ctts_gpu_ctx** out, const void* voice_db, size_t db_size, int device_ordinal) {
-    if (!out || !voice_db || db_size < sizeof(DbHeader)) return CTTS_GPU_ERR_INVALID_ARG;
+    if (!out || !voice_db || db_size < sizeof(DbHeader)) return fail(nullptr, CTTS_GPU_ERR_INVALID_ARG, "ctts_gpu_init: invalid argument");
     *out = nullptr;
     DbHeader h;
     memcpy(&h, voice_db, sizeof h);
-    if (h.magic != 0x53545443u) return CTTS_GPU_ERR_INVALID_FORMAT;
-    if (h.version != 1u) return CTTS_GPU_ERR_VERSION;
+    if (h.magic != 0x53545443u) return fail(nullptr, CTTS_GPU_ERR_INVALID_FORMAT, "ctts_gpu_init: not a voice.db (magic %08x)", h.magic);
+    if (h.version != 1u) return fail(nullptr, CTTS_GPU_ERR_VERSION, "ctts_gpu_init: voice.db version %u", h.version);
     if ((uint64_t)h.index_offset + (uint64_t)h.unit_count * sizeof(DbEntry) > db_size ||
         (uint64_t)h.audio_offset + 2ull * h.total_samples > db_size)
-        return CTTS_GPU_ERR_INVALID_FORMAT;
+        return fail(nullptr, CTTS_GPU_ERR_INVALID_FORMAT, "ctts_gpu_init: voice.db is truncated (%zu bytes)", db_size);
 
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device_ordinal < 0 || device_ordinal >= ndev)
-        return CTTS_GPU_ERR_CUDA;  // no CPU fallback by design
+    {
+        const cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev <= 0 || device_ordinal < 0 || device_ordinal >= ndev)   // no CPU fallback by design
+            return fail(nullptr, CTTS_GPU_ERR_CUDA, "ctts_gpu_init: no CUDA device %d (%d visible%s%s): the back end has no CPU fallback",
+                        device_ordinal, ndev, e != cudaSuccess ? ", " : "", e != cudaSuccess ? cudaGetErrorString(e) : "");
+    }
 
     ctts_gpu_ctx* ctx = new ctts_gpu_ctx();
     ctx->device = device_ordinal;
@@ -387,7 +394,7 @@ int ctts_gpu_init(ctts_gpu_ctx** out, const void* voice_db, size_t db_size, int 
     do {                                                                     \
         cudaError_t e_ = (call);                                             \
         if (e_ != cudaSuccess) {                                             \
-            fprintf(stderr, "ctts_gpu_init: %s: %s\n", #call, cudaGetErrorString(e_)); \
+            fail(nullptr, CTTS_GPU_ERR_CUDA, "ctts_gpu_init: %s: %s", #call, cudaGetErrorString(e_)); \
             return bail(CTTS_GPU_ERR_CUDA);                                  \
         }                                                                    \
     } while (0)
@@ -412,12 +419,18 @@ int ctts_gpu_init(ctts_gpu_ctx** out, const void* voice_db, size_t db_size, int 
     for (uint32_t u = 0; u < h.unit_count; u++) {
         DbEntry e;
         memcpy(&e, base + h.index_offset + (size_t)u * sizeof(DbEntry), sizeof e);
-        if ((uint64_t)e.audio_offset + e.sample_count > h.total_samples) return bail(CTTS_GPU_ERR_INVALID_FORMAT);
+        if ((uint64_t)e.audio_offset + e.sample_count > h.total_samples) {
+            fail(nullptr, CTTS_GPU_ERR_INVALID_FORMAT, "ctts_gpu_init: unit %u lies outside the PCM pool", u);
+            return bail(CTTS_GPU_ERR_INVALID_FORMAT);
+        }
         ctx->unit_cnt[u] = e.sample_count;
         unit_off[u] = (uint32_t)packed;
         packed += up8(e.sample_count);
         ctx->max_unit = std::max(ctx->max_unit, e.sample_count);
-        if (packed > 0xffffffffull) return bail(CTTS_GPU_ERR_INVALID_FORMAT);
+        if (packed > 0xffffffffull) {
+            fail(nullptr, CTTS_GPU_ERR_INVALID_FORMAT, "ctts_gpu_init: more than 2^32 samples");
+            return bail(CTTS_GPU_ERR_INVALID_FORMAT);
+        }
     }
     std::vector<int16_t> pool(std::max<uint64_t>(packed, 8), 0);
     for (uint32_t u = 0; u < h.unit_count; u++) {
@@ -487,7 +500,7 @@ int ctts_gpu_set_stream(ctts_gpu_ctx* ctx, void* cuda_stream) {
     return CTTS_GPU_OK;
 }
 
-const char* ctts_gpu_last_error(const ctts_gpu_ctx* ctx) { return ctx ? ctx->err : "no context"; }
+const char* ctts_gpu_last_error(const ctts_gpu_ctx* ctx) { return ctx ? ctx->err : g_init_err; }
 
 void* ctts_gpu_host_alloc(size_t bytes) {
     void* p = nullptr;

@@ -153,7 +153,8 @@ class GpuSynth:
         buf = (C.c_char * len(voice_db)).from_buffer_copy(voice_db)
         rc = L.ctts_gpu_init(C.byref(h), C.addressof(buf), len(voice_db), device)
         if rc != 0:
-            raise GpuError(f"ctts_gpu_init failed: {rc} (no CUDA device? the back end has no CPU fallback)")
+            why = L.ctts_gpu_last_error(None)
+            raise GpuError(f"ctts_gpu_init failed: {rc}: {why.decode(errors='replace') if why else ''}")
         self._h = h
         self.device = device
 

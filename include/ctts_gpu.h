@@ -48,6 +48,7 @@ void ctts_gpu_free(ctts_gpu_ctx* ctx);
 /* Kernels and copies are issued on `cuda_stream` (a cudaStream_t); NULL
  * restores the context's own stream. */
 int ctts_gpu_set_stream(ctts_gpu_ctx* ctx, void* cuda_stream);
+/* Text of the last error of a context; ctx == NULL: why the calling thread's last ctts_gpu_init failed. */
 const char* ctts_gpu_last_error(const ctts_gpu_ctx* ctx);
 
 /* Upper bound, per utterance, of the samples ctts_gpu_synth_batch may write

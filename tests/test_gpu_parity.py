@@ -272,29 +272,6 @@ def test_bounds_are_upper_bounds_and_tighter_than_the_sum(H, synth_small, oracle
         assert len(pcm) <= tight[u], (u, len(pcm), tight[u])
 
 
-def test_cli_synth_writes_the_reference_wav(H, small_db, golden, tmp_path, monkeypatch):
-    """`synth` of the drop-in CLI: same 44-byte container as ctts_write_wav (ctts.c:809) around the PCM the
-    compiled reference produced for 'olá mundo' at 1.0 and 1.5 (BASELINE configs[0] and [1])."""
-    import shutil
-    import struct
-    cli = H.importlib.import_module("2026-simple-c-tts_b200.cli")
-    monkeypatch.chdir(tmp_path)
-    shutil.copy(H.SHIPPED_YAML, tmp_path / "config.yaml")
-    shutil.copy(H.NORM_CSV, tmp_path / "normalization.csv")
-    (tmp_path / "voice.db").write_bytes(small_db)
-    for k, speed in enumerate((1.0, 1.5)):
-        assert cli.main(["synth", "voice.db", "olá mundo", f"o{k}.wav", str(speed)]) == 0
-        raw = (tmp_path / f"o{k}.wav").read_bytes()
-        want = golden[f"e2e_pcm_{k}"]
-        assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt " and raw[36:40] == b"data"
-        assert struct.unpack("<IHHIIHH", raw[16:36]) == (16, 1, 1, 22050, 44100, 2, 16)
-        assert struct.unpack("<I", raw[4:8])[0] == 36 + 2 * len(want) and struct.unpack("<I", raw[40:44])[0] == 2 * len(want)
-        assert np.array_equal(np.frombuffer(raw[44:], dtype="<i2"), want)
-    (tmp_path / "t.tsv").write_text("1.0\tolá mundo\n1.5\tolá mundo\n", encoding="utf-8")
-    assert cli.main(["synth-batch", "voice.db", "t.tsv", "out"]) == 0
-    assert (tmp_path / "out" / "000001.wav").read_bytes() == (tmp_path / "o1.wav").read_bytes()
-
-
 def test_two_resident_plans_with_different_windows(H, gpu, synth_small, oracle_small, front_small):
     """Plans whose shared-memory windows differ (a tiny batch next to a large region) stay runnable in
     any order: the dynamic shared-memory limit is a per-device setting, not a per-plan one."""
@@ -493,6 +470,7 @@ def test_c_command_line_writes_the_reference_wav(H, small_db, golden, tmp_path):
     `synth` at 1.0 and 1.5 must write byte for byte the WAV the compiled reference writes (44-byte header
     of ctts_write_wav, ctts.c:809, + its PCM: BASELINE configs[0] and [1]); `synth-batch` the same files."""
     import shutil
+    import struct
     import subprocess
     b = H.importlib.import_module("2026-simple-c-tts_b200._build")
     exe = b.build_cli()
@@ -505,6 +483,8 @@ def test_c_command_line_writes_the_reference_wav(H, small_db, golden, tmp_path):
         raw = (tmp_path / f"o{k}.wav").read_bytes()
         want = golden[f"e2e_pcm_{k}"]
         assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt " and raw[36:40] == b"data" and len(raw) == 44 + 2 * len(want)
+        assert struct.unpack("<IHHIIHH", raw[16:36]) == (16, 1, 1, 22050, 44100, 2, 16)
+        assert struct.unpack("<I", raw[4:8])[0] == 36 + 2 * len(want) and struct.unpack("<I", raw[40:44])[0] == 2 * len(want)
         assert np.array_equal(np.frombuffer(raw[44:], dtype="<i2"), want)
         assert f"Synthesized {len(want)} samples" in r.stdout and "missing: 0" in r.stdout
     (tmp_path / "t.tsv").write_text("1.0\tolá mundo\n1.5\tolá mundo\n", encoding="utf-8")

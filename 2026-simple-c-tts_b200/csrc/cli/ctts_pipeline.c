@@ -4,11 +4,15 @@
  *
  * The reference's ctts_synthesize (ctts.c:3623) does, per utterance, normalisation (:3638-3655), the walk
  * with unit selection (:3689-3871, :1406) and every sample loop in one call on one core.  Here:
- *   planner threads   take pieces (16, 32, .. 128 utterances) off a shared counter and plan them with the unchanged
+ *   planner threads   take small groups of utterances (16) off a shared counter and plan them with the unchanged
  *                     front end (ctts_front_plan_batch_threads(..., 1, ...): re-entrant, the handle is only
- *                     read), at most LOOKAHEAD pieces ahead of the device;
- *   the calling thread submits finished plans in order to a ctts_gpu_session (asynchronous: up to three
- *                     pieces are compiled / assembled / copied at any time) and frees them.
+ *                     read), at most LOOKAHEAD groups ahead of the device;
+ *   the calling thread takes, in order, every plan that is ready -- up to piece_utts utterances -- joins them
+ *                     into one piece and submits it to a ctts_gpu_session (asynchronous: several pieces are
+ *                     compiled / assembled / copied at any time).  So the first piece reaches the device after
+ *                     ~1.5 ms of planning (a group is planned by one thread at ~100 us per utterance, while
+ *                     the device->host copy alone consumes an utterance every ~25 us), and once the planners
+ *                     are ahead the pieces are large enough to keep the kernels and the copies efficient.
  * Nothing here touches a sample.
  */
 #define _POSIX_C_SOURCE 200809L
@@ -20,7 +24,8 @@
 
 #include "ctts_b200.h"
 
-#define LOOKAHEAD 64   /* pieces planned ahead of the one being submitted (bounds the memory held in plans) */
+#define LOOKAHEAD 96   /* groups planned ahead of the one being submitted (bounds the memory held in plans) */
+#define GROUP_UTTS 16  /* utterances per planner job */
 
 typedef struct {
     ctts_batch_plan plan;
@@ -111,28 +116,16 @@ int ctts_b200_synth_texts(ctts_front* front, ctts_gpu_ctx* gpu, const char* cons
     P.speeds = speeds;
     P.stats = stats;
     P.n = n;
-    /* A piece is planned by ONE thread (~100 us per utterance) while the device->host copy alone consumes an
-     * utterance every ~25 us: pieces handed over in order starve the device at the start unless the first
-     * ones are small.  So: pieces of 16 utterances for the first two rounds of the planner pool, then 32, 64,
-     * .. up to piece_utts -- by then the planners are a few dozen pieces ahead. */
     const uint32_t piece_utts = opt && opt->piece_utts ? opt->piece_utts : 128;
+    const uint32_t group = piece_utts < GROUP_UTTS ? piece_utts : GROUP_UTTS;
     long cores = sysconf(_SC_NPROCESSORS_ONLN);
     uint32_t T = opt && opt->threads ? opt->threads : (uint32_t)(cores > 1 ? cores - 1 : 1);
     if (T > 32) T = 32;
     if (T < 1) T = 1;
-    P.piece_begin = malloc(((size_t)n + 2) * sizeof *P.piece_begin);
+    P.n_pieces = (n + group - 1) / group;
+    P.piece_begin = malloc(((size_t)P.n_pieces + 1) * sizeof *P.piece_begin);
     if (!P.piece_begin) return CTTS_GPU_ERR_OUT_OF_MEMORY;
-    {
-        uint32_t u = 0;
-        P.piece_begin[0] = 0;
-        while (u < n) {
-            uint32_t shift = P.n_pieces / (2 * T);
-            uint32_t sz = shift > 8 ? piece_utts : 16u << shift;
-            if (sz > piece_utts) sz = piece_utts;
-            u += sz < n - u ? sz : n - u;
-            P.piece_begin[++P.n_pieces] = u;
-        }
-    }
+    for (uint32_t i = 0; i <= P.n_pieces; i++) P.piece_begin[i] = (uint64_t)i * group < n ? i * group : n;
     P.t0 = now_s();
     if (T > P.n_pieces) T = P.n_pieces;
     if (T < 1) T = 1;
@@ -161,12 +154,23 @@ int ctts_b200_synth_texts(ctts_front* front, ctts_gpu_ctx* gpu, const char* cons
     for (; started < T; started++)
         if (pthread_create(&tids[started], NULL, planner, &P) != 0) break;
     double waited = 0.0, all_submitted = 0.0;
+    uint32_t n_submitted = 0;
     if (started == 0 && P.n_pieces) rc = CTTS_GPU_ERR_OUT_OF_MEMORY;
-    for (uint32_t i = 0; i < P.n_pieces && !rc; i++) {
+    ctts_batch_plan joined;                 /* the piece being submitted when it spans several plans */
+    uint32_t* j_begin = NULL;
+    float* j_speed = NULL;
+    ctts_plan_op* j_ops = NULL;
+    size_t j_utts_cap = 0, j_ops_cap = 0;
+    for (uint32_t i = 0; i < P.n_pieces && !rc;) {
         const double w0 = now_s();
         pthread_mutex_lock(&P.mu);
         while (P.slots[i].state == 0) pthread_cond_wait(&P.cv_ready, &P.mu);
-        const int st = P.slots[i].state;
+        /* every further plan that is ready right now, up to piece_utts utterances */
+        uint32_t j = i + 1;
+        while (j < P.n_pieces && P.slots[j].state != 0 && P.piece_begin[j + 1] - P.piece_begin[i] <= piece_utts) j++;
+        int st = 1;
+        for (uint32_t k = i; k < j; k++)
+            if (P.slots[k].state < 0) st = P.slots[k].state;
         pthread_mutex_unlock(&P.mu);
         waited += now_s() - w0;
         if (st < 0) {
@@ -174,15 +178,64 @@ int ctts_b200_synth_texts(ctts_front* front, ctts_gpu_ctx* gpu, const char* cons
             break;
         }
         const uint32_t u0 = P.piece_begin[i];
-        rc = ctts_gpu_session_submit(ses, &P.slots[i].plan, out_offsets + u0, out_counts + u0);
-        ctts_front_plan_free(&P.slots[i].plan);   /* the session keeps nothing of the plan */
-        P.slots[i].state = 2;
+        const ctts_batch_plan* piece = &P.slots[i].plan;
+        if (j > i + 1) {
+            size_t nu = 0, no = 0;
+            for (uint32_t k = i; k < j; k++) {
+                nu += P.slots[k].plan.n_utts;
+                no += P.slots[k].plan.n_ops;
+            }
+            if (nu + 1 > j_utts_cap) {
+                j_utts_cap = 2 * (nu + 1);
+                free(j_begin);
+                free(j_speed);
+                j_begin = malloc(j_utts_cap * sizeof *j_begin);
+                j_speed = malloc(j_utts_cap * sizeof *j_speed);
+            }
+            if (no + 1 > j_ops_cap) {
+                j_ops_cap = 2 * (no + 1);
+                free(j_ops);
+                j_ops = malloc(j_ops_cap * sizeof *j_ops);
+            }
+            if (!j_begin || !j_speed || !j_ops || no > 0xffffffffu) {
+                rc = CTTS_GPU_ERR_OUT_OF_MEMORY;
+                break;
+            }
+            uint32_t au = 0, ao = 0;
+            for (uint32_t k = i; k < j; k++) {
+                const ctts_batch_plan* q = &P.slots[k].plan;
+                for (uint32_t u = 0; u < q->n_utts; u++) {
+                    j_begin[au + u] = ao + q->utt_op_begin[u];
+                    j_speed[au + u] = q->speed[u];
+                }
+                if (q->n_ops) memcpy(j_ops + ao, q->ops, (size_t)q->n_ops * sizeof *j_ops);
+                au += q->n_utts;
+                ao += q->n_ops;
+            }
+            j_begin[au] = ao;
+            joined.n_utts = au;
+            joined.n_ops = ao;
+            joined.utt_op_begin = j_begin;
+            joined.speed = j_speed;
+            joined.ops = j_ops;
+            piece = &joined;
+        }
+        rc = ctts_gpu_session_submit(ses, piece, out_offsets + u0, out_counts + u0);
+        for (uint32_t k = i; k < j; k++) {
+            ctts_front_plan_free(&P.slots[k].plan);   /* the session keeps nothing of the plan */
+            P.slots[k].state = 2;
+        }
         pthread_mutex_lock(&P.mu);
-        P.consumed = i + 1;
+        P.consumed = j;
         pthread_cond_broadcast(&P.cv_room);
         pthread_mutex_unlock(&P.mu);
         all_submitted = now_s() - P.t0;
+        n_submitted++;
+        i = j;
     }
+    free(j_begin);
+    free(j_speed);
+    free(j_ops);
     pthread_mutex_lock(&P.mu);
     P.stop = 1;
     pthread_cond_broadcast(&P.cv_room);
@@ -198,6 +251,7 @@ int ctts_b200_synth_texts(ctts_front* front, ctts_gpu_ctx* gpu, const char* cons
         timing->all_submitted_s = all_submitted;
         timing->done_s = now_s() - P.t0;
         timing->wait_for_plans_s = waited;
+        timing->pieces = n_submitted;
     }
     pthread_mutex_destroy(&P.mu);
     pthread_cond_destroy(&P.cv_ready);

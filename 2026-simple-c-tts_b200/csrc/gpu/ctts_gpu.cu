@@ -111,10 +111,10 @@ struct ctts_gpu_ctx {
     int sm_count = 0;
     int smem_per_sm = 0;
     int smem_optin = 0;
-    // A batch is worked on in PIECES (contiguous utterance ranges); up to kLanes pieces are in flight: the
+    // A batch is worked on in PIECES (contiguous utterance ranges); up to kLanes (4) pieces are in flight: the
     // host compiles piece c+1 while the device assembles piece c and piece c-1 is copied to the caller.
     // Every lane owns grow-only workspaces (no cudaMalloc / cudaFree per call).
-    static constexpr int kLanes = 3;
+    static constexpr int kLanes = 4;
     struct Lane {
         Arena arena;                       // device workspace + pinned staging of the plan upload
         int16_t* d_out = nullptr;          // the piece's output slots

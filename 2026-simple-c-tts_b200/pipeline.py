@@ -18,7 +18,7 @@ class Options(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("first_plan_s", C.c_double), ("all_plans_s", C.c_double), ("all_submitted_s", C.c_double),
-                ("done_s", C.c_double), ("wait_for_plans_s", C.c_double)]
+                ("done_s", C.c_double), ("wait_for_plans_s", C.c_double), ("pieces", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 _lib = None

@@ -449,7 +449,7 @@ def main() -> int:
                "audio_s": float(c3.astype(np.int64).sum()) / SAMPLE_RATE, "plan_to_pcm_s": plan_s_e2e,
                "timing": {"first_piece_planned_ms": 1e3 * tm.first_plan_s, "all_planned_ms": 1e3 * tm.all_plans_s,
                           "all_submitted_ms": 1e3 * tm.all_submitted_s, "done_ms": 1e3 * tm.done_s,
-                          "submitter_waited_for_plans_ms": 1e3 * tm.wait_for_plans_s}}
+                          "submitter_waited_for_plans_ms": 1e3 * tm.wait_for_plans_s, "device_pieces": int(tm.pieces)}}
 
     # ---- reduce over ranks: time = max, work = sum
     t_rank = torch.tensor([total_ms, audio_s, e2e["seconds_per_step"] if e2e else 0.0,

@@ -5,10 +5,10 @@
  * Exported by libctts_b200.so (plain C over the two C-ABI libraries; what the `ctts_b200` command line and
  * a CTTS maintainer's batch driver link).  The reference does text work and sample work of one utterance
  * inside one call (ctts.c:3638-3655 normalisation, :3689-3871 the walk with unit selection :1406); here the
- * batch is cut into pieces of utterances, a pool of planner threads turns pieces into plans
- * (ctts_front_plan_batch_threads) while the calling thread feeds finished plans, in order, to a
- * ctts_gpu_session: planning of piece c+1 overlaps the kernels of piece c and the device->host copy of
- * piece c-1.  Plans are byte-identical to what ctts_front_plan_batch returns for the whole batch.
+ * batch is cut into groups of 16 utterances, a pool of planner threads turns groups into plans
+ * (ctts_front_plan_batch_threads) while the calling thread joins the plans that are ready, in order, into
+ * pieces and feeds them to a ctts_gpu_session: planning of piece c+1 overlaps the kernels of piece c and the
+ * device->host copy of piece c-1.  Plans are byte-identical to what ctts_front_plan_batch returns for the whole batch.
  */
 #ifndef CTTS_B200_H
 #define CTTS_B200_H
@@ -21,7 +21,7 @@ extern "C" {
 #endif
 
 typedef struct ctts_b200_options {
-    uint32_t piece_utts;     /* utterances per piece (0: 128) */
+    uint32_t piece_utts;     /* most utterances per device piece (0: 128); planner jobs are groups of 16 */
     uint32_t threads;        /* planner threads (0: host cores - 1, at least 1, at most 32) */
     ctts_gpu_chunk_fn on_piece;   /* may be NULL: called in order as utterance ranges arrive in pcm_out */
     void* user;
@@ -34,6 +34,8 @@ typedef struct ctts_b200_timing {
     double all_submitted_s;  /* last piece handed to the device */
     double done_s;           /* everything in pcm_out */
     double wait_for_plans_s; /* time the submitting thread spent waiting for the planners */
+    uint32_t pieces;         /* pieces submitted to the device */
+    uint32_t reserved;
 } ctts_b200_timing;
 
 /* N texts -> PCM.  pcm_out (ctts_gpu_host_alloc) holds `capacity` samples; utterance u lands at

@@ -89,8 +89,8 @@ int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan,
  * begin    pcm_out (page-locked for full copy speed) holds `capacity` samples; on_piece (may be NULL) is called
  *          on the submitting thread, in order, with the session-wide utterance range of every piece whose PCM
  *          and counts have arrived.
- * submit   asynchronous: returns as soon as the piece is compiled and enqueued (up to three pieces are in
- *          flight; a fourth waits for the oldest).  out_offsets[i] (n entries, written before the call
+ * submit   asynchronous: returns as soon as the piece is compiled and enqueued (up to four pieces are in
+ *          flight; a fifth waits for the oldest).  out_offsets[i] (n entries, written before the call
  *          returns) is where utterance i of the piece will land: packed 16-byte aligned slots sized by the
  *          bounds, appended to what earlier pieces took.  out_counts[i] (n entries) is written when the
  *          piece has arrived, at the latest by ctts_gpu_session_end; the plan may be freed when submit returns.

@@ -37,7 +37,7 @@ def test_pipeline_library_exports_header_symbols(H):
     assert names == ["ctts_b200_capacity_hint", "ctts_b200_synth_texts"]
     for n in names:
         assert hasattr(L, n), n
-    assert C.sizeof(pipe.Timing) == 5 * 8 and C.sizeof(pipe.Options) == 24
+    assert C.sizeof(pipe.Timing) == 6 * 8 and C.sizeof(pipe.Options) == 24
 
 
 def test_capacity_hint_covers_the_bounds(H, small_db, front_small):

@@ -279,3 +279,35 @@ def small_db() -> bytes:
 
 def shipped_config():
     return front.load_config(SHIPPED_YAML)
+
+
+def golden_corpus() -> dict:
+    """tests/golden/ref_corpus.json: SHA-1 / length of the compiled reference's PCM (make_golden_corpus.py)."""
+    import json
+    with open(os.path.join(GOLDEN, "ref_corpus.json"), encoding="utf-8") as f:
+        return json.load(f)
+
+
+def masked_sha1(pcm: np.ndarray, mask: np.ndarray) -> str:
+    import hashlib
+    x = np.ascontiguousarray(pcm, dtype="<i2").copy()
+    x[mask[:len(x)]] = 0
+    return hashlib.sha1(x.tobytes()).hexdigest()
+
+
+def odd_offset_voice() -> bytes:
+    """The small voice plus one unit whose text makes the string pool's size odd, so that the PCM pool starts
+    at an odd byte offset of voice.db (ctts.c:1001-1004, :1159).  Same construction as make_golden_corpus.py."""
+    key = "odd"
+    if key not in _db_cache:
+        vdb = voicedb.parse_voice_db(small_db())
+        units = [(vdb.unit_text(i), vdb.unit_pcm(i)) for i in range(vdb.unit_count)]
+        rng = np.random.default_rng(4)
+        for extra in ("zzq", "zzqq"):
+            db = voicedb.build_voice_db(units + [(extra, (rng.normal(0, 2000, 3000)).astype(np.int16))])
+            if voicedb.parse_voice_db(db).audio_offset % 2 == 1:
+                _db_cache[key] = db
+                break
+        else:
+            raise AssertionError("could not make the audio offset odd")
+    return _db_cache[key]

@@ -178,3 +178,38 @@ def test_oracle_vs_live_reference(H, oracle_small, front_small, reference_small)
             elif st.ub_spans == 0:
                 assert np.array_equal(got, want), (t, sp)
     assert diff / max(total, 1) < 1e-4
+
+
+def test_oracle_matches_reference_hashes_of_corpus_sentences(H, small_db, front_small, oracle_small):
+    """tests/golden/ref_corpus.json holds SHA-1 + length of the COMPILED REFERENCE's PCM for 48 sentences of the
+    benchmark corpus (32 at speed 1.0, 16 stretched) -- made where the reference tree exists, checked here (and
+    against the CUDA path in test_gpu_parity.py) where it does not."""
+    import hashlib
+    G = H.golden_corpus()
+    assert G["voice_sha256"] == hashlib.sha256(small_db).hexdigest()
+    rows = G["corpus"]
+    assert len(rows) >= 48 and sum(r["speed"] != 1.0 for r in rows) >= 16
+    prm = front_small.params()
+    plan = front_small.plan([r["text"] for r in rows], [r["speed"] for r in rows])
+    for u, r in enumerate(rows):
+        got, st = oracle_small.synth(prm, plan.utt_ops(u), r["speed"])
+        assert len(got) == r["samples"], r["text"]
+        assert H.masked_sha1(got, H.ub_mask(st, len(got))) == r["sha1"], r["text"]
+
+
+def test_oracle_on_a_voice_with_an_odd_pcm_offset(H):
+    """voice.db whose PCM pool starts at an odd byte offset (the reference reads it through a misaligned
+    int16_t*, ctts.c:1159): the oracle reproduces the compiled reference's hashes."""
+    import hashlib
+    db = H.odd_offset_voice()
+    assert H.voicedb.parse_voice_db(db).audio_offset % 2 == 1
+    G = H.golden_corpus()
+    assert G["odd_voice_sha256"] == hashlib.sha256(db).hexdigest()
+    fr = H.front.Front(db, H.shipped_config(), H.NORM_CSV)
+    prm = fr.params()
+    orc = H.Oracle(db)
+    rows = G["odd_voice"]
+    plan = fr.plan([r["text"] for r in rows], [r["speed"] for r in rows])
+    for u, r in enumerate(rows):
+        got, st = orc.synth(prm, plan.utt_ops(u), r["speed"])
+        assert len(got) == r["samples"] and H.masked_sha1(got, H.ub_mask(st, len(got))) == r["sha1"], r["text"]

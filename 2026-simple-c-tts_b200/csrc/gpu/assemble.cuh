@@ -166,5 +166,63 @@ __global__ void __launch_bounds__(ASM_THREADS, 3) assemble_kernel(const AsmArgs 
     }
 }
 
-}  // namespace ctts
+// ---------------------------------------------------------------- packed output (device prefix sum + gather)
 
+// Utterance slots are spaced by host-known upper bounds; what the caller wants are the samples that exist.
+// pack_scan_kernel: exclusive prefix sum of the counts rounded up to 8 samples (every utterance starts on a
+// 16-byte boundary) -> pack_off[0..n].  One CTA.
+constexpr int PACK_THREADS = 256;
+__global__ void __launch_bounds__(1024) pack_scan_kernel(const uint32_t* __restrict__ counts, uint32_t n, unsigned long long* __restrict__ pack_off) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0ull;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t u = base + (uint32_t)tid;
+        const unsigned long long v = u < n ? (((unsigned long long)counts[u] + 7ull) & ~7ull) : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        unsigned long long pre = s_carry;
+        for (int w = 0; w < warp; w++) pre += wsum[w];
+        if (u < n) pack_off[u] = pre + inc - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = pre + inc;
+        __syncthreads();
+    }
+    if (tid == 0) pack_off[n] = s_carry;
+}
+
+// pack_copy_kernel: utterance blockIdx.y, tile blockIdx.x of 8 * PACK_THREADS * 4 samples: slot -> packed
+// position, 16-byte vectors (both sides are 16-byte aligned); the <= 7 samples of padding are written as zeros.
+constexpr uint32_t PACK_TILE = 8u * PACK_THREADS * 4u;
+__global__ void __launch_bounds__(PACK_THREADS) pack_copy_kernel(const int16_t* __restrict__ slots, const unsigned long long* __restrict__ slot_off,
+                                                                 const uint32_t* __restrict__ counts, const unsigned long long* __restrict__ pack_off,
+                                                                 int16_t* __restrict__ packed) {
+    const uint32_t u = blockIdx.y;
+    const uint32_t cnt = counts[u];
+    const uint32_t t0 = blockIdx.x * PACK_TILE;
+    if (t0 >= cnt) return;
+    const int4* src = reinterpret_cast<const int4*>(slots + slot_off[u]);
+    int4* dst = reinterpret_cast<int4*>(packed + pack_off[u]);
+    const uint32_t nvec = (cnt + 7u) >> 3;
+    const uint32_t v1 = min(nvec, (t0 + PACK_TILE) >> 3);
+    for (uint32_t v = (t0 >> 3) + threadIdx.x; v < v1; v += PACK_THREADS) {
+        int4 q = __ldcs(src + v);
+        if (8u * v + 8u > cnt) {   // the last vector: zero the padding
+            int16_t* e = reinterpret_cast<int16_t*>(&q);
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (8u * v + (uint32_t)k >= cnt) e[k] = 0;
+        }
+        __stcs(dst + v, q);
+    }
+}
+
+}  // namespace ctts

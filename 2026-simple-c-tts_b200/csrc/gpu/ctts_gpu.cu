@@ -119,16 +119,23 @@ struct ctts_gpu_ctx {
         Arena arena;                       // device workspace + pinned staging of the plan upload
         int16_t* d_out = nullptr;          // the piece's output slots
         uint64_t d_out_cap = 0;
-        uint32_t* h_res = nullptr;         // pinned: counts [n], then device error flags [n]
-        size_t h_res_cap = 0;
-        cudaEvent_t kernels_done = nullptr, copied = nullptr;
+        int16_t* d_pack = nullptr;         // packed mode: the utterances' samples back to back
+        uint64_t d_pack_cap = 0;
+        unsigned long long* d_pack_off = nullptr;   // n + 1 (+ the n + 1 slot offsets behind them)
+        size_t d_pack_off_cap = 0;
+        uint32_t* h_res = nullptr;         // pinned: counts [n], then device error flags [n], then (8-byte aligned) slot offsets [n + 1]
+        size_t h_res_cap = 0;              // in 4-byte words
+        cudaEvent_t kernels_done = nullptr, counts_ready = nullptr, copied = nullptr;
         ctts_gpu_plan* plan = nullptr;     // piece in flight
         uint32_t* user_counts = nullptr;   // where its counts go
+        uint64_t* user_offsets = nullptr;  // packed mode: where its offsets go
+        bool copy_pending = false;         // packed mode: the PCM copy is enqueued once the counts are on the host
         uint32_t utt_base = 0, n = 0;      // its utterances in the session's numbering
         bool busy = false;
     };
     Lane lane[kLanes];
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t ctl_stream = nullptr;     // counts / flags travel here, ahead of the PCM queued on copy_stream
     ctts_gpu_session* session = nullptr;   // at most one at a time
     char err[512] = {0};
 };
@@ -485,11 +492,15 @@ void ctts_gpu_free(ctts_gpu_ctx* ctx) {
         cudaFree(l.arena.d);
         if (l.arena.h) cudaFreeHost(l.arena.h);
         cudaFree(l.d_out);
+        cudaFree(l.d_pack);
+        cudaFree(l.d_pack_off);
         if (l.h_res) cudaFreeHost(l.h_res);
         if (l.kernels_done) cudaEventDestroy(l.kernels_done);
+        if (l.counts_ready) cudaEventDestroy(l.counts_ready);
         if (l.copied) cudaEventDestroy(l.copied);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ctl_stream) cudaStreamDestroy(ctx->ctl_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1298,6 +1309,7 @@ struct ctts_gpu_session {
     uint64_t capacity = 0;        // samples
     uint64_t cursor = 0;          // next free sample (library-chosen layout)
     uint32_t submitted = 0, harvested = 0;   // pieces
+    uint32_t copy_next = 0;       // packed mode: first piece whose PCM copy is not enqueued yet
     uint32_t utts = 0;            // utterances submitted so far
     ctts_gpu_chunk_fn on_piece = nullptr;
     void* user = nullptr;
@@ -1310,8 +1322,13 @@ namespace {
 
 void drain(ctts_gpu_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->ctl_stream) cudaStreamSynchronize(ctx->ctl_stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
 }
+
+// Packed mode: the counts of the lane's piece are (or will shortly be) on the host; lay its utterances out
+// back to back at the session's cursor and enqueue ONE copy of exactly the samples that exist.
+int enqueue_packed_copy(ctts_gpu_session* s, ctts_gpu_ctx::Lane& l);
 
 // Wait for the oldest piece in flight, hand its counts (and the piece itself) to the caller, free its lane.
 int harvest_one(ctts_gpu_session* s) {
@@ -1319,9 +1336,11 @@ int harvest_one(ctts_gpu_session* s) {
     ctts_gpu_ctx::Lane& l = ctx->lane[s->harvested % ctts_gpu_ctx::kLanes];
     s->harvested++;
     if (!l.busy) return CTTS_GPU_OK;
-    cudaError_t e = cudaEventSynchronize(l.copied);
     int rc = CTTS_GPU_OK;
-    if (e != cudaSuccess) rc = fail(ctx, CTTS_GPU_ERR_CUDA, "piece of utterances %u..%u: %s", l.utt_base, l.utt_base + l.n, cudaGetErrorString(e));
+    if (l.copy_pending) rc = enqueue_packed_copy(s, l);
+    if (s->copy_next < s->harvested) s->copy_next = s->harvested;
+    cudaError_t e = cudaEventSynchronize(l.copied);
+    if (e != cudaSuccess && !rc) rc = fail(ctx, CTTS_GPU_ERR_CUDA, "piece of utterances %u..%u: %s", l.utt_base, l.utt_base + l.n, cudaGetErrorString(e));
     if (!rc) {
         const uint32_t* h_cnt = l.h_res;
         const uint32_t* h_err = l.h_res + l.n;
@@ -1362,63 +1381,86 @@ int submit_piece(ctts_gpu_session* s, const ctts_batch_plan* piece, const uint64
         ctts_gpu_plan_destroy(p);
         return code;
     };
-    std::vector<uint64_t> lib_off, lib_cap;
-    if (!slot_off) {
-        lib_off.resize(std::max<uint32_t>(n, 1));
-        lib_cap.resize(std::max<uint32_t>(n, 1));
-        for (uint32_t u = 0; u < n; u++) {
-            lib_off[u] = s->cursor + p->offsets[u];
-            lib_cap[u] = p->offsets[u + 1] - p->offsets[u];
-            if (offsets_out) offsets_out[u] = lib_off[u];
-        }
-        slot_off = lib_off.data();
-        slot_cap = lib_cap.data();
-        if (s->cursor + p->offsets[n] > s->capacity)
-            return bail(fail(ctx, CTTS_GPU_ERR_BOUNDS, "output buffer too small: %llu samples needed so far",
-                             (unsigned long long)(s->cursor + p->offsets[n])));
-    }
-    for (uint32_t u = 0; u < n; u++)
+    const bool packed = slot_off == nullptr;   // library layout: exactly the samples that exist, back to back
+    for (uint32_t u = 0; u < n && !packed; u++)
         if ((slot_off[u] & 7) || slot_cap[u] < p->bounds[u] || slot_off[u] + slot_cap[u] > s->capacity)
             return bail(fail(ctx, CTTS_GPU_ERR_BOUNDS, "output slot of utterance %u is misaligned, outside the buffer or smaller than its bound %llu",
                              s->utts + u, (unsigned long long)p->bounds[u]));
     const uint64_t total = p->offsets[n];
-    if (total > l.d_out_cap) {
-        cudaFree(l.d_out);
-        l.d_out = nullptr;
-        l.d_out_cap = 0;
+    auto grow = [&](int16_t** buf, uint64_t* cap_now) -> int {
+        if (total <= *cap_now) return 0;
+        cudaFree(*buf);
+        *buf = nullptr;
+        *cap_now = 0;
         const uint64_t cap = std::max<uint64_t>(total + total / 8, 8);
-        if (cudaMalloc(reinterpret_cast<void**>(&l.d_out), cap * sizeof(int16_t)) != cudaSuccess)
-            return bail(fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "output buffer of %llu samples", (unsigned long long)cap));
+        if (cudaMalloc(reinterpret_cast<void**>(buf), cap * sizeof(int16_t)) != cudaSuccess)
+            return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "output buffer of %llu samples", (unsigned long long)cap);
         // never-written slot tails must not carry an earlier allocation's bytes to the host
-        if (cudaMemsetAsync(l.d_out, 0, cap * sizeof(int16_t), ctx->stream) != cudaSuccess) return bail(fail(ctx, CTTS_GPU_ERR_CUDA, "memset"));
-        l.d_out_cap = cap;
-    }
-    if (2 * (size_t)n > l.h_res_cap) {
+        if (cudaMemsetAsync(*buf, 0, cap * sizeof(int16_t), ctx->stream) != cudaSuccess) return fail(ctx, CTTS_GPU_ERR_CUDA, "memset");
+        *cap_now = cap;
+        return 0;
+    };
+    if ((rc = grow(&l.d_out, &l.d_out_cap)) != 0) return bail(rc);
+    if (packed && (rc = grow(&l.d_pack, &l.d_pack_cap)) != 0) return bail(rc);
+    const size_t res_words = 2 * (size_t)n + 2 + 2 * ((size_t)n + 1);   // counts, flags, (aligned) slot offsets
+    if (res_words > l.h_res_cap) {
         if (l.h_res) cudaFreeHost(l.h_res);
         l.h_res = nullptr;
         l.h_res_cap = 0;
-        const size_t cap = 2 * (size_t)n + 1024;
+        const size_t cap = res_words + 4096;
         if (cudaHostAlloc(reinterpret_cast<void**>(&l.h_res), cap * 4, cudaHostAllocDefault) != cudaSuccess)
             return bail(fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "pinned counts"));
         l.h_res_cap = cap;
     }
+    if (packed && 2 * ((size_t)n + 1) > l.d_pack_off_cap) {
+        cudaFree(l.d_pack_off);
+        l.d_pack_off = nullptr;
+        l.d_pack_off_cap = 0;
+        const size_t cap = 2 * ((size_t)n + 1) + 4096;
+        if (cudaMalloc(reinterpret_cast<void**>(&l.d_pack_off), cap * 8) != cudaSuccess)
+            return bail(fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "pack offsets"));
+        l.d_pack_off_cap = cap;
+    }
     if (!l.kernels_done) {
         cudaError_t e = cudaEventCreateWithFlags(&l.kernels_done, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.copied, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.counts_ready, cudaEventDisableTiming);
         if (e != cudaSuccess) return bail(fail(ctx, CTTS_GPU_ERR_CUDA, "event: %s", cudaGetErrorString(e)));
     }
     p->d_out_last = l.d_out;
+    l.copy_pending = false;
     if (n) {
         rc = begin_run(ctx, p);
         if (!rc) rc = build_chunk(ctx, p, 0, ctx->stream);
         if (!rc) rc = launch_chunk(ctx, p, 0, l.d_out, ctx->stream);
         if (!rc) rc = launch_stretch(ctx, p, 0, l.d_out, ctx->stream);
         if (rc) return bail(rc);
-        cudaError_t e = cudaEventRecord(l.kernels_done, ctx->stream);
+        cudaError_t e = cudaSuccess;
+        if (packed) {
+            // device prefix sum of the counts -> packed positions -> gather; the counts travel on the control
+            // stream (not behind the PCM of earlier pieces), the PCM copy is enqueued once they are here
+            unsigned long long* h_slot = reinterpret_cast<unsigned long long*>(l.h_res + ((2 * (size_t)n + 1) & ~(size_t)1));
+            for (uint32_t u = 0; u <= n; u++) h_slot[u] = p->offsets[u];
+            unsigned long long* d_slot = l.d_pack_off + (n + 1);
+            e = cudaMemcpyAsync(d_slot, h_slot, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) {
+                ctts::pack_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p->d_counts, n, l.d_pack_off);
+                uint64_t max_slot = 0;
+                for (uint32_t u = 0; u < n; u++) max_slot = std::max<uint64_t>(max_slot, p->offsets[u + 1] - p->offsets[u]);
+                for (uint32_t u0 = 0; u0 < n && e == cudaSuccess; u0 += 65535u) {   // grid.y limit
+                    const dim3 grid((unsigned)((max_slot + ctts::PACK_TILE - 1) / ctts::PACK_TILE), std::min<uint32_t>(n - u0, 65535u));
+                    ctts::pack_copy_kernel<<<grid, ctts::PACK_THREADS, 0, ctx->stream>>>(l.d_out, d_slot + u0, p->d_counts + u0, l.d_pack_off + u0, l.d_pack);
+                    e = cudaGetLastError();
+                }
+            }
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(l.kernels_done, ctx->stream);
+        cudaStream_t res_stream = packed ? ctx->ctl_stream : ctx->copy_stream;
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, l.kernels_done, 0);
-        // device slots are packed (up8(bound) + 8 each); runs of utterances whose host slots are packed the
-        // same way go in one copy
-        for (uint32_t u = 0; u < n && e == cudaSuccess;) {
+        if (e == cudaSuccess && packed) e = cudaStreamWaitEvent(ctx->ctl_stream, l.kernels_done, 0);
+        // slots mode: device slots are packed by their bounds (up8(bound) + 8 each); runs of utterances whose
+        // host slots are laid out the same way go in one copy
+        for (uint32_t u = 0; u < n && e == cudaSuccess && !packed;) {
             uint32_t v = u;
             while (v + 1 < n && slot_off[v + 1] == slot_off[v] + (p->offsets[v + 1] - p->offsets[v]) &&
                    slot_cap[v] >= p->offsets[v + 1] - p->offsets[v])
@@ -1428,29 +1470,71 @@ int submit_piece(ctts_gpu_session* s, const ctts_batch_plan* piece, const uint64
             s->d2h_samples += len;
             u = v + 1;
         }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(l.h_res, p->d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->copy_stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(l.h_res + n, p->d_err, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->copy_stream);
-        if (e == cudaSuccess) e = cudaEventRecord(l.copied, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(l.h_res, p->d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, res_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(l.h_res + n, p->d_err, (size_t)n * 4, cudaMemcpyDeviceToHost, res_stream);
+        if (e == cudaSuccess && packed) e = cudaEventRecord(l.counts_ready, ctx->ctl_stream);
+        if (e == cudaSuccess && !packed) e = cudaEventRecord(l.copied, ctx->copy_stream);
         if (e != cudaSuccess) return bail(fail(ctx, CTTS_GPU_ERR_CUDA, "enqueue: %s", cudaGetErrorString(e)));
+        l.copy_pending = packed;
     } else {
         cudaError_t e = cudaEventRecord(l.copied, ctx->copy_stream);
         if (e != cudaSuccess) return bail(fail(ctx, CTTS_GPU_ERR_CUDA, "enqueue: %s", cudaGetErrorString(e)));
     }
     l.plan = p;
     l.user_counts = out_counts;
+    l.user_offsets = offsets_out;
     l.utt_base = s->utts;
     l.n = n;
     l.busy = true;
     s->submitted++;
     s->utts += n;
-    if (!lib_off.empty()) s->cursor += p->offsets[n];
+    // packed mode: enqueue the PCM copies of the pieces whose counts have arrived (in order; never blocks)
+    while (s->copy_next < s->submitted) {
+        ctts_gpu_ctx::Lane& c = ctx->lane[s->copy_next % ctts_gpu_ctx::kLanes];
+        if (c.busy && c.copy_pending) {
+            if (cudaEventQuery(c.counts_ready) != cudaSuccess) break;
+            enqueue_packed_copy(s, c);
+        }
+        s->copy_next++;
+    }
     // hand over whatever has arrived in the meantime (never blocks)
     while (s->harvested < s->submitted) {
         ctts_gpu_ctx::Lane& h = ctx->lane[s->harvested % ctts_gpu_ctx::kLanes];
-        if (h.busy && cudaEventQuery(h.copied) != cudaSuccess) break;
+        if (h.busy && (h.copy_pending || cudaEventQuery(h.copied) != cudaSuccess)) break;
         harvest_one(s);
     }
     return s->error;
+}
+
+int enqueue_packed_copy(ctts_gpu_session* s, ctts_gpu_ctx::Lane& l) {
+    ctts_gpu_ctx* ctx = s->ctx;
+    l.copy_pending = false;
+    cudaError_t e = cudaEventSynchronize(l.counts_ready);
+    if (e != cudaSuccess) {
+        if (!s->error) s->error = fail(ctx, CTTS_GPU_ERR_CUDA, "piece of utterances %u..%u: %s", l.utt_base, l.utt_base + l.n, cudaGetErrorString(e));
+        return s->error;
+    }
+    const uint32_t* h_cnt = l.h_res;
+    uint64_t o = s->cursor;
+    for (uint32_t u = 0; u < l.n; u++) {
+        if (l.user_offsets) l.user_offsets[u] = o;
+        o += up8(h_cnt[u]);
+    }
+    const uint64_t len = o - s->cursor;
+    if (o > s->capacity) {
+        if (!s->error)
+            s->error = fail(ctx, CTTS_GPU_ERR_BOUNDS, "output buffer too small: %llu samples needed up to utterance %u", (unsigned long long)o, l.utt_base + l.n);
+        return s->error;
+    }
+    if (len) e = cudaMemcpyAsync(s->pcm_out + s->cursor, l.d_pack, len * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(l.copied, ctx->copy_stream);
+    if (e != cudaSuccess) {
+        if (!s->error) s->error = fail(ctx, CTTS_GPU_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
+        return s->error;
+    }
+    s->d2h_samples += len;
+    s->cursor = o;
+    return CTTS_GPU_OK;
 }
 
 }  // namespace
@@ -1464,6 +1548,7 @@ int ctts_gpu_session_begin(ctts_gpu_ctx* ctx, const ctts_assembly_params* params
     if (ctx->session) return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "a session is already open on this context");
     CU(ctx, cudaSetDevice(ctx->device));
     if (!ctx->copy_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->ctl_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->ctl_stream, cudaStreamNonBlocking));
     ctts_gpu_session* s = new ctts_gpu_session();
     s->ctx = ctx;
     s->prm = *params;

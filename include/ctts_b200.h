@@ -39,8 +39,8 @@ typedef struct ctts_b200_timing {
 } ctts_b200_timing;
 
 /* N texts -> PCM.  pcm_out (ctts_gpu_host_alloc) holds `capacity` samples; utterance u lands at
- * pcm_out[out_offsets[u] .. out_offsets[u] + out_counts[u]) (out_offsets: n entries, packed 16-byte aligned
- * slots sized by the back end's bounds; *samples_used, may be NULL, = slot space taken).  speeds may be NULL
+ * pcm_out[out_offsets[u] .. out_offsets[u] + out_counts[u]) (out_offsets: n entries; the utterances are
+ * packed back to back, each starting 16-byte aligned; *samples_used, may be NULL, = space taken).  speeds may be NULL
  * (all 1.0); stats may be NULL (2n: units found, missing per utterance, ctts.c:3861, :3866).
  * Returns 0 or the first CTTS_FRONT_ERR_* / CTTS_GPU_ERR_* code.  CTTS_GPU_ERR_BOUNDS: capacity too small
  * (ctts_b200_capacity_hint gives a safe size). */

@@ -90,13 +90,16 @@ int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan,
  *          on the submitting thread, in order, with the session-wide utterance range of every piece whose PCM
  *          and counts have arrived.
  * submit   asynchronous: returns as soon as the piece is compiled and enqueued (up to four pieces are in
- *          flight; a fifth waits for the oldest).  out_offsets[i] (n entries, written before the call
- *          returns) is where utterance i of the piece will land: packed 16-byte aligned slots sized by the
- *          bounds, appended to what earlier pieces took.  out_counts[i] (n entries) is written when the
- *          piece has arrived, at the latest by ctts_gpu_session_end; the plan may be freed when submit returns.
+ *          flight; a fifth waits for the oldest).  The output is PACKED: a device prefix sum of the counts
+ *          places every utterance right behind the one before it (rounded up to 8 samples, so every utterance
+ *          starts 16-byte aligned; the padding is zero), a device gather moves the samples there, and exactly
+ *          those samples cross PCIe.  out_offsets[i] and out_counts[i] (n entries each) are written when the
+ *          piece has arrived -- before on_piece is called for it, at the latest by ctts_gpu_session_end; the
+ *          plan may be freed when submit returns.  A buffer that turns out too small ends the session with
+ *          CTTS_GPU_ERR_BOUNDS (ctts_gpu_plan_bounds gives what is always enough).
  * end      waits for everything, returns the first error of the session; *samples_used (may be NULL) is
- *          the slot space taken in pcm_out.
- * One session per context at a time.  Samples of a slot past out_counts[i] are unspecified. */
+ *          the space taken in pcm_out.
+ * One session per context at a time. */
 typedef struct ctts_gpu_session ctts_gpu_session;
 int ctts_gpu_session_begin(ctts_gpu_ctx* ctx, const ctts_assembly_params* params, int16_t* pcm_out,
                            uint64_t capacity, ctts_gpu_chunk_fn on_piece, void* user, ctts_gpu_session** out);

@@ -1330,15 +1330,29 @@ void drain(ctts_gpu_ctx* ctx) {
 // back to back at the session's cursor and enqueue ONE copy of exactly the samples that exist.
 int enqueue_packed_copy(ctts_gpu_session* s, ctts_gpu_ctx::Lane& l);
 
+// Packed mode: enqueue, in order, the PCM copies of the pieces whose counts have arrived; pieces up to and
+// including `must` (a piece index, or none: 0xffffffff... never) are waited for.  Keeps the copy stream fed
+// while the host is about to block on an older piece.
+void pump_copies(ctts_gpu_session* s, uint32_t must_upto) {
+    ctts_gpu_ctx* ctx = s->ctx;
+    while (s->copy_next < s->submitted) {
+        ctts_gpu_ctx::Lane& c = ctx->lane[s->copy_next % ctts_gpu_ctx::kLanes];
+        if (c.busy && c.copy_pending) {
+            if (s->copy_next >= must_upto && cudaEventQuery(c.counts_ready) != cudaSuccess) break;
+            enqueue_packed_copy(s, c);
+        }
+        s->copy_next++;
+    }
+}
+
 // Wait for the oldest piece in flight, hand its counts (and the piece itself) to the caller, free its lane.
 int harvest_one(ctts_gpu_session* s) {
     ctts_gpu_ctx* ctx = s->ctx;
     ctts_gpu_ctx::Lane& l = ctx->lane[s->harvested % ctts_gpu_ctx::kLanes];
+    pump_copies(s, s->harvested + 1);   // this piece's copy for sure, and every later one that is ready
     s->harvested++;
     if (!l.busy) return CTTS_GPU_OK;
-    int rc = CTTS_GPU_OK;
-    if (l.copy_pending) rc = enqueue_packed_copy(s, l);
-    if (s->copy_next < s->harvested) s->copy_next = s->harvested;
+    int rc = s->error;
     cudaError_t e = cudaEventSynchronize(l.copied);
     if (e != cudaSuccess && !rc) rc = fail(ctx, CTTS_GPU_ERR_CUDA, "piece of utterances %u..%u: %s", l.utt_base, l.utt_base + l.n, cudaGetErrorString(e));
     if (!rc) {
@@ -1489,14 +1503,7 @@ int submit_piece(ctts_gpu_session* s, const ctts_batch_plan* piece, const uint64
     s->submitted++;
     s->utts += n;
     // packed mode: enqueue the PCM copies of the pieces whose counts have arrived (in order; never blocks)
-    while (s->copy_next < s->submitted) {
-        ctts_gpu_ctx::Lane& c = ctx->lane[s->copy_next % ctts_gpu_ctx::kLanes];
-        if (c.busy && c.copy_pending) {
-            if (cudaEventQuery(c.counts_ready) != cudaSuccess) break;
-            enqueue_packed_copy(s, c);
-        }
-        s->copy_next++;
-    }
+    pump_copies(s, 0);
     // hand over whatever has arrived in the meantime (never blocks)
     while (s->harvested < s->submitted) {
         ctts_gpu_ctx::Lane& h = ctx->lane[s->harvested % ctts_gpu_ctx::kLanes];

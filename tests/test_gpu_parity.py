@@ -618,7 +618,9 @@ def test_session_pieces_equal_one_batch(H, gpu, synth_small, oracle_small, front
     cap = int(synth_small.layout(plan)[-1])
     pcm = np.zeros(cap + 64, dtype=np.int16)
     off, cnt = synth_small.synth_pieces(pieces, prm, pcm)
-    assert len(off) == plan.n_utts and (off % 8 == 0).all() and (np.diff(off.astype(np.int64)) > 0).all()
+    # packed: every utterance right behind the one before it, rounded up to 8 samples
+    assert len(off) == plan.n_utts and off[0] == 0
+    assert np.array_equal(np.diff(off.astype(np.int64)), (cnt[:-1].astype(np.int64) + 7) // 8 * 8)
     for u in range(plan.n_utts):
         want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))
         _assert_same(pcm[int(off[u]):int(off[u]) + int(cnt[u])], want, f"session utt {u}")

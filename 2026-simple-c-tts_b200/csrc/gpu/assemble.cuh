@@ -170,9 +170,12 @@ __global__ void __launch_bounds__(ASM_THREADS, 3) assemble_kernel(const AsmArgs 
 
 // Utterance slots are spaced by host-known upper bounds; what the caller wants are the samples that exist.
 // pack_scan_kernel: exclusive prefix sum of the counts rounded up to 8 samples (every utterance starts on a
-// 16-byte boundary) -> pack_off[0..n].  One CTA.
+// 16-byte boundary) -> pack_off[0..n].  One CTA.  It also stores counts and error flags straight into
+// page-locked host memory (h_res: counts [n], flags [n]): the host needs them to size the PCM copy, and a
+// device->host copy of them would queue behind the PCM of earlier pieces on the copy engine.
 constexpr int PACK_THREADS = 256;
-__global__ void __launch_bounds__(1024) pack_scan_kernel(const uint32_t* __restrict__ counts, uint32_t n, unsigned long long* __restrict__ pack_off) {
+__global__ void __launch_bounds__(1024) pack_scan_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ err, uint32_t n,
+                                                         unsigned long long* __restrict__ pack_off, uint32_t* h_res) {
     __shared__ unsigned long long wsum[32];
     __shared__ unsigned long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -191,12 +194,17 @@ __global__ void __launch_bounds__(1024) pack_scan_kernel(const uint32_t* __restr
         __syncthreads();
         unsigned long long pre = s_carry;
         for (int w = 0; w < warp; w++) pre += wsum[w];
-        if (u < n) pack_off[u] = pre + inc - v;
+        if (u < n) {
+            pack_off[u] = pre + inc - v;
+            h_res[u] = counts[u];
+            h_res[n + u] = err[u];
+        }
         __syncthreads();
         if (tid == 1023) s_carry = pre + inc;
         __syncthreads();
     }
     if (tid == 0) pack_off[n] = s_carry;
+    __threadfence_system();
 }
 
 // pack_copy_kernel: utterance blockIdx.y, tile blockIdx.x of 8 * PACK_THREADS * 4 samples: slot -> packed

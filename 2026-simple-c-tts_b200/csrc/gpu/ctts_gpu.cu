@@ -135,7 +135,6 @@ struct ctts_gpu_ctx {
     };
     Lane lane[kLanes];
     cudaStream_t copy_stream = nullptr;
-    cudaStream_t ctl_stream = nullptr;     // counts / flags travel here, ahead of the PCM queued on copy_stream
     ctts_gpu_session* session = nullptr;   // at most one at a time
     char err[512] = {0};
 };
@@ -500,7 +499,6 @@ void ctts_gpu_free(ctts_gpu_ctx* ctx) {
         if (l.copied) cudaEventDestroy(l.copied);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->ctl_stream) cudaStreamDestroy(ctx->ctl_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1322,7 +1320,6 @@ namespace {
 
 void drain(ctts_gpu_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->ctl_stream) cudaStreamSynchronize(ctx->ctl_stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
 }
 
@@ -1451,14 +1448,16 @@ int submit_piece(ctts_gpu_session* s, const ctts_batch_plan* piece, const uint64
         if (rc) return bail(rc);
         cudaError_t e = cudaSuccess;
         if (packed) {
-            // device prefix sum of the counts -> packed positions -> gather; the counts travel on the control
-            // stream (not behind the PCM of earlier pieces), the PCM copy is enqueued once they are here
+            // device prefix sum of the counts -> packed positions -> gather; the scan kernel also stores counts
+            // and flags into page-locked host memory, and the PCM copy is enqueued once they are here
             unsigned long long* h_slot = reinterpret_cast<unsigned long long*>(l.h_res + ((2 * (size_t)n + 1) & ~(size_t)1));
             for (uint32_t u = 0; u <= n; u++) h_slot[u] = p->offsets[u];
             unsigned long long* d_slot = l.d_pack_off + (n + 1);
             e = cudaMemcpyAsync(d_slot, h_slot, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
             if (e == cudaSuccess) {
-                ctts::pack_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p->d_counts, n, l.d_pack_off);
+                ctts::pack_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p->d_counts, p->d_err, n, l.d_pack_off, l.h_res);
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaEventRecord(l.counts_ready, ctx->stream);   // counts and flags are on the host
                 uint64_t max_slot = 0;
                 for (uint32_t u = 0; u < n; u++) max_slot = std::max<uint64_t>(max_slot, p->offsets[u + 1] - p->offsets[u]);
                 for (uint32_t u0 = 0; u0 < n && e == cudaSuccess; u0 += 65535u) {   // grid.y limit
@@ -1469,9 +1468,7 @@ int submit_piece(ctts_gpu_session* s, const ctts_batch_plan* piece, const uint64
             }
         }
         if (e == cudaSuccess) e = cudaEventRecord(l.kernels_done, ctx->stream);
-        cudaStream_t res_stream = packed ? ctx->ctl_stream : ctx->copy_stream;
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, l.kernels_done, 0);
-        if (e == cudaSuccess && packed) e = cudaStreamWaitEvent(ctx->ctl_stream, l.kernels_done, 0);
         // slots mode: device slots are packed by their bounds (up8(bound) + 8 each); runs of utterances whose
         // host slots are laid out the same way go in one copy
         for (uint32_t u = 0; u < n && e == cudaSuccess && !packed;) {
@@ -1484,10 +1481,11 @@ int submit_piece(ctts_gpu_session* s, const ctts_batch_plan* piece, const uint64
             s->d2h_samples += len;
             u = v + 1;
         }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(l.h_res, p->d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, res_stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(l.h_res + n, p->d_err, (size_t)n * 4, cudaMemcpyDeviceToHost, res_stream);
-        if (e == cudaSuccess && packed) e = cudaEventRecord(l.counts_ready, ctx->ctl_stream);
-        if (e == cudaSuccess && !packed) e = cudaEventRecord(l.copied, ctx->copy_stream);
+        if (e == cudaSuccess && !packed) {
+            e = cudaMemcpyAsync(l.h_res, p->d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(l.h_res + n, p->d_err, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(l.copied, ctx->copy_stream);
+        }
         if (e != cudaSuccess) return bail(fail(ctx, CTTS_GPU_ERR_CUDA, "enqueue: %s", cudaGetErrorString(e)));
         l.copy_pending = packed;
     } else {
@@ -1555,7 +1553,6 @@ int ctts_gpu_session_begin(ctts_gpu_ctx* ctx, const ctts_assembly_params* params
     if (ctx->session) return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "a session is already open on this context");
     CU(ctx, cudaSetDevice(ctx->device));
     if (!ctx->copy_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    if (!ctx->ctl_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->ctl_stream, cudaStreamNonBlocking));
     ctts_gpu_session* s = new ctts_gpu_session();
     s->ctx = ctx;
     s->prm = *params;

@@ -69,7 +69,8 @@ constexpr int WS_RING = 1024;    // samples kept: a double-mapped ring makes eve
 constexpr int WS_MAXC = 72;      // candidates of one decision
 constexpr float WS_EPS = 1e-4f;
 constexpr int OLA_THREADS = 256;
-constexpr int OLA_SPT = 8;  // samples per thread
+constexpr int OLA_SPT = 16; // rows (output samples) per thread
+constexpr int OLA_QMAX = 8;  // frames that can cover one output sample: 512 / 64 (hop >= 64 on the tiled path)
 
 struct StretchTask {
     uint32_t utt;
@@ -893,7 +894,7 @@ __host__ __device__ inline uint32_t ola_block_span(uint32_t hop) {
 // norm in (the int16 accumulator wraps, ctts.c:3577: it is the 32-bit sum mod 2^16).
 constexpr int OLA_STAGE = WS_HOP * (OLA_THREADS / 64) * OLA_SPT + 1536;   // input samples an interior block can touch (hop >= 64)
 
-__global__ void __launch_bounds__(OLA_THREADS) wsola_ola_kernel(const WsolaArgs A) {
+__global__ void __launch_bounds__(OLA_THREADS, 4) wsola_ola_kernel(const WsolaArgs A) {
     __shared__ int s_last[OLA_THREADS / 32];
     __shared__ float win[WS_FRAME];
     __shared__ uint32_t sfp[(OLA_THREADS / 64) * OLA_SPT + 8];
@@ -945,11 +946,11 @@ __global__ void __launch_bounds__(OLA_THREADS) wsola_ola_kernel(const WsolaArgs 
         const uint32_t g = (uint32_t)tid / hop, c = (uint32_t)tid - g * hop;
         if (g < groups) {
             const uint32_t rowbase = row0 + g * OLA_SPT;
-            // positions (relative to the staged span) of frames rowbase - 7 .. rowbase + 7
-            int fpr[2 * OLA_SPT - 1];
+            // positions (relative to the staged span) of frames rowbase - 7 .. rowbase + OLA_SPT - 1
+            int fpr[OLA_SPT + OLA_QMAX - 1];
             bool inside = true;
 #pragma unroll
-            for (int k = 0; k < 2 * OLA_SPT - 1; k++) {
+            for (int k = 0; k < OLA_SPT + OLA_QMAX - 1; k++) {
                 fpr[k] = (int)(sfp[g * OLA_SPT + k] - s0);
                 inside &= fpr[k] >= 0 && fpr[k] + WS_FRAME <= (int)span;
             }
@@ -959,7 +960,7 @@ __global__ void __launch_bounds__(OLA_THREADS) wsola_ola_kernel(const WsolaArgs 
 #pragma unroll
             for (int r = 0; r < OLA_SPT; r++) acc[r] = 0;
 #pragma unroll
-            for (int q = OLA_SPT - 1; q >= 0; q--) {
+            for (int q = OLA_QMAX - 1; q >= 0; q--) {
                 const uint32_t i = (uint32_t)q * hop + c;
                 if (q <= qmax && i < (uint32_t)WS_FRAME) {
                     const float wv = win[i];
@@ -967,11 +968,11 @@ __global__ void __launch_bounds__(OLA_THREADS) wsola_ola_kernel(const WsolaArgs 
                     if (inside) {
 #pragma unroll
                         for (int r = 0; r < OLA_SPT; r++)   // |x * w| <= 32767: the int32 truncation is the int16 value
-                            acc[r] += (int)(xin[fpr[r - q + OLA_SPT - 1] + (int)i] * wv);
+                            acc[r] += (int)(xin[fpr[r - q + OLA_QMAX - 1] + (int)i] * wv);
                     } else {                          // (a frame outside the analytic span: cannot happen, kept for safety)
 #pragma unroll
                         for (int r = 0; r < OLA_SPT; r++)
-                            acc[r] += (int)((float)in[sfp[g * OLA_SPT + r - q + OLA_SPT - 1] + i] * wv);
+                            acc[r] += (int)((float)in[sfp[g * OLA_SPT + r - q + OLA_QMAX - 1] + i] * wv);
                     }
                 }
             }

@@ -506,17 +506,20 @@ __global__ void __launch_bounds__(WS_THREADS, WS_CTAS_PER_SM) wsola_search_kerne
 // ---------------------------------------------------------------- speculation: scan + verify
 
 constexpr int WV_THREADS = 256;
-constexpr int WV_FRAMES = 26;                                  // frames per tile: 26 * 19 items = 494 = 2 per thread
+constexpr int WV_FRAMES = 24;                                  // frames per tile: (24 + 2) block positions * 19 items = 494 = 2 per thread
 constexpr int WV_SPAN = WS_HOP * WV_FRAMES + (WS_RANGE - WS_HOP);   // samples a tile sees: 3840
 constexpr int WV_QUADS = WV_SPAN / 4;
-constexpr int WV_NB = 4;                                       // tier-1 blocks ...
-constexpr int WV_BL = 8;                                       // ... of this many terms (multiple of 4)
-constexpr int WV_B0 = 44;                                      // first term of block 0
-constexpr int WV_BSTEP = 96;                                   // block spacing
+constexpr int WV_NB = 3;                                       // tier-1 blocks ...
+constexpr int WV_BL = 12;                                      // ... of this many terms (multiple of 4)
+constexpr int WV_B0 = 48;                                      // first term of block 0 (multiple of 16: static offsets in the padded layout)
+constexpr int WV_BSTEP = WS_HOP;                               // block spacing = the analysis hop: block b of frame k IS block b-1 of frame k+1
+constexpr int WV_NJ = WV_FRAMES + WV_NB - 1;                   // block positions a tile's frames use (one hypothesis)
+constexpr int WV_DC = 72;                                      // dot products kept per block position: 65 coarse lags, 3 + 3 fine, 1 pad
 constexpr int WV_ITEMS = 19;   // per frame: 16 coarse groups of 4, the 65th candidate, fine below, fine above
 constexpr int WV_LIST = 768;                                   // tier-2 list entries per tile
 constexpr float WV_THR = 2.5e-4f;   // tier 1 rejects when the partial sum of (x^ - t^)^2 exceeds this (5 x the bound, see below)
-static_assert(WV_SPAN % 4 == 0 && WV_BL % 4 == 0 && WV_B0 % 4 == 0 && WV_BSTEP % 4 == 0, "float4 alignment");
+static_assert(WV_SPAN % 4 == 0 && WV_BL % 4 == 0 && WV_B0 % 16 == 0 && WV_BSTEP % 16 == 0, "float4 alignment, static padded offsets");
+static_assert(WV_NJ * 16 + 96 <= 2 * WV_THREADS && WV_NJ <= 32 && (WV_NJ * 16) % 32 == 0, "two items per thread, kinds on warp boundaries");
 static_assert(WV_B0 + (WV_NB - 1) * WV_BSTEP + WV_BL <= WS_OVERLAP, "blocks inside the window");
 
 // Shared-memory layout of the staged samples: 4 floats of padding after every 16, so that the 16-float
@@ -530,7 +533,10 @@ struct WvSmem {
     alignas(16) float e4[WV_QUADS + 4];        // energy of quad j (float of the exact integer)
     alignas(16) float W4[WV_QUADS];            // window energy at 4j (float of the exact integer)
     alignas(16) float G4[WV_QUADS];            // energy of the tier-1 blocks of the window at 4j
+    alignas(16) float D[WV_NJ * WV_DC];        // partial dot products per (block position, lag)
+    float Sl[WV_NJ * 8];                       // per block position: block energy of the fine lags minus that of the lag they are slid from
     float Et[WV_FRAMES], Bt[WV_FRAMES];        // target: energy, block energy / energy
+    uint32_t has_hyp[2];                       // tile has live frames under hypothesis -128 / 0
     int hyp[WV_FRAMES];                        // speculated previous offset; INT_MIN: frame needs no check
     int room[WV_FRAMES];                       // largest offset in bounds
     unsigned long long wtot[WV_THREADS / 32];
@@ -578,45 +584,41 @@ __global__ void __launch_bounds__(256) wsola_scan_kernel(const WsolaArgs A) {
     }
 }
 
-// tier 1 for one item = 4 candidates (window starts yb + SHIFT + STRIDE * j, yb a multiple of 16 in the tile)
-// against the target at tb0 (a multiple of 16): the cross terms of the WV_NB blocks, one FMA each, operand loads
-// shared by the 4 candidates.  y_head / y_tail: the first / last 3 squares sums needed to slide a block energy
-// by 1..3 samples (STRIDE == 1 only).
+// tier 1, one item: the WV_BL cross terms of ONE block for 4 candidates (candidate blocks start at
+// yb + SHIFT + STRIDE * j, yb a multiple of 16 in the tile) against the target block at tb (a multiple of 16):
+// one FMA per term, operand loads shared by the 4 candidates.  slide[j] (STRIDE == 1): energy of candidate
+// block j minus that of candidate block 0.
 template <int STRIDE, int SHIFT>
-__device__ __forceinline__ void wv_dots(const float* __restrict__ xs, int tb0, int yb, float (&d)[4], float (&slide)[4]) {
+__device__ __forceinline__ void wv_block_dots(const float* __restrict__ xs, int tb, int yb, float (&d)[4], float (&slide)[4]) {
     d[0] = d[1] = d[2] = d[3] = 0.0f;
     slide[0] = slide[1] = slide[2] = slide[3] = 0.0f;
-    constexpr int TC = WV_BL / 4;                                 // target chunks per block
-    constexpr int YC = STRIDE == 4 ? TC + 3 : TC + 1;             // candidate chunks per block
-    const float* tp = xs + wv_phys(tb0);
+    constexpr int TC = WV_BL / 4;                                 // target chunks
+    constexpr int YC = STRIDE == 4 ? TC + 3 : TC + 1;             // candidate chunks
+    const float* tp = xs + wv_phys(tb);
     const float* yp = xs + wv_phys(yb);
+    float y[4 * YC];
 #pragma unroll
-    for (int b = 0; b < WV_NB; b++) {
-        float y[4 * YC];
+    for (int m = 0; m < YC; m++) {
+        const float4 v = *reinterpret_cast<const float4*>(yp + wv_phys(SHIFT + 4 * m));
+        y[4 * m] = v.x; y[4 * m + 1] = v.y; y[4 * m + 2] = v.z; y[4 * m + 3] = v.w;
+    }
 #pragma unroll
-        for (int m = 0; m < YC; m++) {
-            const float4 v = *reinterpret_cast<const float4*>(yp + wv_phys(SHIFT + WV_B0 + b * WV_BSTEP + 4 * m));
-            y[4 * m] = v.x; y[4 * m + 1] = v.y; y[4 * m + 2] = v.z; y[4 * m + 3] = v.w;
+    for (int m = 0; m < TC; m++) {
+        const float4 t = *reinterpret_cast<const float4*>(tp + wv_phys(4 * m));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            d[j] = __fmaf_rn(t.x, y[STRIDE * j + 4 * m], d[j]);
+            d[j] = __fmaf_rn(t.y, y[STRIDE * j + 4 * m + 1], d[j]);
+            d[j] = __fmaf_rn(t.z, y[STRIDE * j + 4 * m + 2], d[j]);
+            d[j] = __fmaf_rn(t.w, y[STRIDE * j + 4 * m + 3], d[j]);
         }
+    }
+    if (STRIDE == 1) {
+        float acc = 0.0f;
 #pragma unroll
-        for (int m = 0; m < TC; m++) {
-            const float4 t = *reinterpret_cast<const float4*>(tp + wv_phys(WV_B0 + b * WV_BSTEP + 4 * m));
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                d[j] = __fmaf_rn(t.x, y[STRIDE * j + 4 * m], d[j]);
-                d[j] = __fmaf_rn(t.y, y[STRIDE * j + 4 * m + 1], d[j]);
-                d[j] = __fmaf_rn(t.z, y[STRIDE * j + 4 * m + 2], d[j]);
-                d[j] = __fmaf_rn(t.w, y[STRIDE * j + 4 * m + 3], d[j]);
-            }
-        }
-        if (STRIDE == 1) {
-            // block energy of candidate j = that of candidate 0 + sum_{i<j} (y[BL + i]^2 - y[i]^2)
-            float acc = 0.0f;
-#pragma unroll
-            for (int j = 1; j < 4; j++) {
-                acc += y[WV_BL + j - 1] * y[WV_BL + j - 1] - y[j - 1] * y[j - 1];
-                slide[j] += acc;
-            }
+        for (int j = 1; j < 4; j++) {
+            acc += y[WV_BL + j - 1] * y[WV_BL + j - 1] - y[j - 1] * y[j - 1];
+            slide[j] = acc;
         }
     }
 }
@@ -633,9 +635,9 @@ __device__ __forceinline__ void wv_dots(const float* __restrict__ xs, int tb0, i
 // Error budget of tier 1.  With x^ = x/|x|, t^ = t/|t| (exact real arithmetic) the true correlation is
 // rho = 1 - |x^ - t^|^2 / 2 <= 1 - S/2, S = sum over the blocks of (x^_i - t^_i)^2 = A + B - 2C,
 // A = E_blocks(x)/E(x), B = E_blocks(t)/E(t) (window energies exact integers from the prefix sum, block
-// energies float sums of <= 32 exact squares, approximate reciprocal: relative error < 3e-6 each incl. the
-// slid energies of the fine candidates), C = dot/sqrt(E(x)E(t)) (32 FMA terms, rsqrt.approx:
-// |error| <= (gamma_32 + 2^-22 + 3u) sqrt(AB) < 2.5e-6).  So |S~ - S| < 1e-5 (A, B <= 1), and the
+// energies float sums of <= 36 exact squares, approximate reciprocal: relative error < 3e-6 each incl. the
+// slid energies of the fine candidates), C = dot/sqrt(E(x)E(t)) (36 FMA terms in three partial sums, rsqrt.approx:
+// |error| <= (gamma_14 + 2^-22 + 5u) sqrt(AB) < 1.5e-6).  So |S~ - S| < 1e-5 (A, B <= 1), and the
 // reference's score r satisfies |r - rho| <= 2e-5, hence r <= 1 - S~/2 + 5e-6 + 2e-5 < 1
 // whenever S~ > 5e-5.  WV_THR is 2.5e-4.
 __global__ void __launch_bounds__(WV_THREADS, 4) wsola_verify_kernel(const WsolaArgs A) {
@@ -658,6 +660,7 @@ __global__ void __launch_bounds__(WV_THREADS, 4) wsola_verify_kernel(const Wsola
         sm.n_list = 0;
         sm.bad = 0xffffffffu;
         sm.PQ[0] = 0ull;
+        sm.has_hyp[0] = sm.has_hyp[1] = 0u;
     }
     if (tid >= WV_QUADS / 4 && tid < WV_QUADS / 4 + 4) {
         const int z = tid - WV_QUADS / 4;
@@ -751,6 +754,7 @@ __global__ void __launch_bounds__(WV_THREADS, 4) wsola_verify_kernel(const Wsola
             } else {
                 sm.Et[tid] = et;
                 sm.Bt[tid] = __fdividef(sm.G4[ts >> 2], et);
+                sm.has_hyp[h == 0 ? 1 : 0] = 1u;
             }
             if (A.force_bad && k % A.force_bad == 0) atomicMin(&sm.bad, k);
             A.frame_pos[task.pos_off + k] = pos;
@@ -761,67 +765,113 @@ __global__ void __launch_bounds__(WV_THREADS, 4) wsola_verify_kernel(const Wsola
     }
     __syncthreads();
 
-    // ---- tier 1
-    for (int it = tid; it < WV_FRAMES * WV_ITEMS; it += WV_THREADS) {
-        const int f = it / WV_ITEMS, g = it - f * WV_ITEMS;
-        const int h = sm.hyp[f];
-        if (h == INT_MIN) continue;
-        const int v = WS_HOP * f;                 // view of the frame in the tile
-        const int ts = v + WS_SHIFT + h;
-        const int room = sm.room[f];
-        const float et = sm.Et[f], bt = sm.Bt[f];
-        int o0, stride;
-        uint32_t live;                            // which of the 4 candidates count
-        if (g < 16) { o0 = -WS_SHIFT + 16 * g; stride = 4; live = 0xfu; }
-        else if (g == 16) { o0 = WS_SHIFT; stride = 4; live = 0x1u; }             // +128 alone (the other three would lie outside the search range)
-        else if (g == 17) { o0 = h - 4; stride = 1; live = h - 3 >= -WS_SHIFT ? 0xeu : 0u; }   // h-3 .. h-1
-        else { o0 = h; stride = 1; live = 0xeu; }                                   // h+1 .. h+3
-        if (!live) continue;
-        const int yb = v + WS_SHIFT + o0;
-        float d[4], w[4], gb[4], slide[4];
-        float w4base = 0.0f;
-        if (stride == 4) {
-            wv_dots<4, 0>(sm.xs, ts, yb, d, slide);
-            const float4 w4 = *reinterpret_cast<const float4*>(sm.W4 + (yb >> 2));
-            const float4 g4 = *reinterpret_cast<const float4*>(sm.G4 + (yb >> 2));
-            w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
-            gb[0] = g4.x; gb[1] = g4.y; gb[2] = g4.z; gb[3] = g4.w;
-        } else {
-            if (g == 17) wv_dots<1, 12>(sm.xs, ts, yb - 12, d, slide);   // yb = 12 mod 16
-            else wv_dots<1, 0>(sm.xs, ts, yb, d, slide);
-            // energies of the windows at yb + 1 .. yb + 3 from the one at yb (a multiple of 4):
-            // drop the first j samples, take j more at the end
-            const float4 x0 = *reinterpret_cast<const float4*>(sm.xs + wv_phys(yb));
-            const float4 x1 = *reinterpret_cast<const float4*>(sm.xs + wv_phys(yb + WS_OVERLAP));
-            const float wb = sm.W4[yb >> 2], gq = sm.G4[yb >> 2];
-            w4base = wb;
-            w[0] = gb[0] = 0.0f;
-            w[1] = wb + (x1.x * x1.x - x0.x * x0.x);
-            w[2] = w[1] + (x1.y * x1.y - x0.y * x0.y);
-            w[3] = w[2] + (x1.z * x1.z - x0.z * x0.z);
-#pragma unroll
-            for (int j = 1; j < 4; j++) gb[j] = gq + slide[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int o = o0 + stride * j;
-            if (!((live >> j) & 1u) || o == h || o > room) continue;   // not a candidate / the target itself / out of bounds
-            // zero energy: the score is exactly 0 (ctts.c:3426).  (A slid energy is a float difference: anything
-            // below one sample's worth is treated as inconclusive rather than trusted.)
-            if (stride == 4 && w[j] == 0.0f) continue;
-            // (a slid window energy is trusted only while it has not lost most of the energy it was slid
-            // from -- cancellation: its relative error is then < 8 * 3 * 2^-24)
-            float s = -1.0f;
-            if (w[j] >= 1.0f && (stride == 4 || w[j] >= 0.125f * w4base))
-                s = __fdividef(gb[j], w[j]) + bt - 2.0f * d[j] * rsqrt_approx(w[j] * et);
-            if (!(s > WV_THR)) {
-                const uint32_t slot = atomicAdd(&sm.n_list, 1u);
-                if (slot < (uint32_t)WV_LIST) sm.list[slot] = ((uint32_t)f << 16) | (uint32_t)(o + WS_SHIFT);
-                else atomicMin(&sm.bad, k0 + (uint32_t)f);             // no room to look closer: let the chain walk decide
+    // ---- tier 1.  The blocks are one analysis hop apart, so the partial dot product of block b of frame k
+    //      at a given lag IS that of block b-1 of frame k+1 (same samples, as long as both frames have the
+    //      same speculated offset): they are formed once per (block position, lag) -- D -- and every
+    //      (frame, candidate) then adds its three.  A tile that holds the one frame where the speculated
+    //      offset changes does this twice, once per offset.
+    for (int pass = 0; pass < 2; pass++) {
+        if (!sm.has_hyp[pass]) continue;                          // CTA-uniform
+        const int hp = pass ? 0 : -WS_SHIFT;                      // the speculated offset of this pass
+        const int j_lo = pass;                                    // first block position used: frame f, block b sits at f + b + j_lo
+        // items are ordered by KIND so that a warp runs one kind of code: 16 coarse groups per block position
+        // (WV_NJ * 16 = 13 warps), then -- 32 slots each -- the 65th candidate, the fine lags below, the fine lags above
+        for (int it = tid; it < WV_NJ * 16 + 96; it += WV_THREADS) {
+            float d[4], slide[4];
+            if (it < WV_NJ * 16) {                                // lags 16 g - 128 - hp + {0, 4, 8, 12}
+                const int jl = it >> 4, g = it & 15;
+                const int tb = WS_HOP * (jl + j_lo) + WV_B0;      // target block (multiple of 16)
+                wv_block_dots<4, 0>(sm.xs, tb, tb + 16 * g - WS_SHIFT - hp, d, slide);
+                *reinterpret_cast<float4*>(sm.D + jl * WV_DC + 4 * g) = make_float4(d[0], d[1], d[2], d[3]);
+                continue;
+            }
+            const int kind = (it - WV_NJ * 16) >> 5, jl = (it - WV_NJ * 16) & 31;
+            if (jl >= WV_NJ) continue;
+            const int tb = WS_HOP * (jl + j_lo) + WV_B0;
+            float* Dj = sm.D + jl * WV_DC;
+            if (kind == 0) {                                      // the 65th coarse candidate alone
+                wv_block_dots<4, 0>(sm.xs, tb, tb + WS_SHIFT - hp, d, slide);
+                Dj[64] = d[0];
+            } else if (kind == 1) {                               // fine, below: lags -3, -2, -1 (slid from -4)
+                wv_block_dots<1, 12>(sm.xs, tb, tb - 16, d, slide);
+                Dj[65] = d[1]; Dj[66] = d[2]; Dj[67] = d[3];
+                sm.Sl[8 * jl] = slide[1]; sm.Sl[8 * jl + 1] = slide[2]; sm.Sl[8 * jl + 2] = slide[3];
+            } else {                                              // fine, above: lags 1, 2, 3 (slid from 0)
+                wv_block_dots<1, 0>(sm.xs, tb, tb, d, slide);
+                Dj[68] = d[1]; Dj[69] = d[2]; Dj[70] = d[3];
+                sm.Sl[8 * jl + 3] = slide[1]; sm.Sl[8 * jl + 4] = slide[2]; sm.Sl[8 * jl + 5] = slide[3];
             }
         }
+        __syncthreads();
+        auto inconclusive = [&](int f, int o) {
+            const uint32_t slot = atomicAdd(&sm.n_list, 1u);
+            if (slot < (uint32_t)WV_LIST) sm.list[slot] = ((uint32_t)f << 16) | (uint32_t)(o + WS_SHIFT);
+            else atomicMin(&sm.bad, k0 + (uint32_t)f);             // no room to look closer: let the chain walk decide
+        };
+        // (frame, group of 4 coarse candidates): three float4 of partial dots, one each of window / block energies
+        for (int it = tid; it < WV_FRAMES * 16; it += WV_THREADS) {
+            const int f = it >> 4, g = it & 15;
+            if (sm.hyp[f] != hp) continue;
+            const int room = sm.room[f];
+            const float et = sm.Et[f], bt = sm.Bt[f];
+            const float4 d0 = *reinterpret_cast<const float4*>(sm.D + f * WV_DC + 4 * g);
+            const float4 d1 = *reinterpret_cast<const float4*>(sm.D + (f + 1) * WV_DC + 4 * g);
+            const float4 d2 = *reinterpret_cast<const float4*>(sm.D + (f + 2) * WV_DC + 4 * g);
+            const int q = (WS_HOP * f + 16 * g) >> 2;             // window of offset -128 + 16 g: tile sample 128 f + 16 g
+            const float4 w4 = *reinterpret_cast<const float4*>(sm.W4 + q);
+            const float4 g4 = *reinterpret_cast<const float4*>(sm.G4 + q);
+            const float dot[4] = {d0.x + d1.x + d2.x, d0.y + d1.y + d2.y, d0.z + d1.z + d2.z, d0.w + d1.w + d2.w};
+            const float w[4] = {w4.x, w4.y, w4.z, w4.w}, gb[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int o = -WS_SHIFT + 16 * g + 4 * j;
+                if (o == hp || o > room || w[j] == 0.0f) continue;   // the target itself / out of bounds / score exactly 0 (ctts.c:3426)
+                const float sres = __fdividef(gb[j], w[j]) + bt - 2.0f * dot[j] * rsqrt_approx(w[j] * et);
+                if (!(sres > WV_THR)) inconclusive(f, o);
+            }
+        }
+        // (frame, one of: the 65th coarse candidate, 3 fine lags below, 3 above): 8 slots per frame
+        for (int it = tid; it < WV_FRAMES * 8; it += WV_THREADS) {
+            const int f = it >> 3, c7 = it & 7;
+            if (sm.hyp[f] != hp || c7 == 7) continue;
+            const int ts = WS_HOP * f + WS_SHIFT + hp;            // the target in the tile
+            const int room = sm.room[f];
+            const int c = 64 + c7;
+            int o;
+            float w, gb;
+            if (c7 == 0) {
+                o = WS_SHIFT;
+                if (o > room) continue;
+                const int q = (WS_HOP * f + 2 * WS_SHIFT) >> 2;
+                w = sm.W4[q];
+                gb = sm.G4[q];
+                if (w == 0.0f) continue;
+            } else {
+                const int below = c7 < 4, j = below ? c7 : c7 - 3;               // slid by j = 1..3 samples
+                o = hp + (below ? j - 4 : j);
+                if (o < -WS_SHIFT || o > WS_SHIFT || o > room) continue;
+                const int p0 = ts + (below ? -4 : 0);             // the window the energies are slid from (multiple of 4)
+                const float wb = sm.W4[p0 >> 2];
+                const float4 x0 = *reinterpret_cast<const float4*>(sm.xs + wv_phys(p0));
+                const float4 x1 = *reinterpret_cast<const float4*>(sm.xs + wv_phys(p0 + WS_OVERLAP));
+                w = wb + (x1.x * x1.x - x0.x * x0.x);
+                if (j > 1) w += x1.y * x1.y - x0.y * x0.y;
+                if (j > 2) w += x1.z * x1.z - x0.z * x0.z;
+                const int k = (below ? 0 : 3) + j - 1;
+                gb = sm.G4[p0 >> 2] + sm.Sl[8 * f + k] + sm.Sl[8 * (f + 1) + k] + sm.Sl[8 * (f + 2) + k];
+                // a slid window energy is trusted only while it has not lost most of the energy it was slid from
+                // (cancellation: its relative error is then < 8 * 3 * 2^-24); else the candidate is looked at closely
+                if (!(w >= 1.0f && w >= 0.125f * wb)) w = -1.0f;
+            }
+            float sres = -1.0f;
+            if (w > 0.0f) {
+                const float dot = sm.D[f * WV_DC + c] + sm.D[(f + 1) * WV_DC + c] + sm.D[(f + 2) * WV_DC + c];
+                sres = __fdividef(gb, w) + sm.Bt[f] - 2.0f * dot * rsqrt_approx(w * sm.Et[f]);
+            }
+            if (!(sres > WV_THR)) inconclusive(f, o);
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- tiers 2 and 3: one warp per candidate tier 1 could not reject
     const uint32_t n_list = min(sm.n_list, (uint32_t)WV_LIST);

@@ -881,11 +881,21 @@ __global__ void __launch_bounds__(WV_THREADS, 4) wsola_verify_kernel(const Wsola
         const int f = (int)(ent >> 16), xo = (int)(ent & 0xffffu);   // xo = offset + 128: window start inside the view
         const int tg = WS_HOP * f + WS_SHIFT + sm.hyp[f], xc = WS_HOP * f + xo;
         float dot = 0.0f, ea = 0.0f;
+        if ((xc & 3) == 0) {   // a coarse candidate: 16-byte vectors (the padding never splits an aligned quad)
 #pragma unroll
-        for (int q = 0; q < WS_OVERLAP / 32; q++) {
-            const float a = sm.xs[wv_phys(xc + lane + 32 * q)];
-            dot = __fmaf_rn(sm.xs[wv_phys(tg + lane + 32 * q)], a, dot);
-            ea = __fmaf_rn(a, a, ea);
+            for (int q = 0; q < WS_OVERLAP / 128; q++) {
+                const float4 a = *reinterpret_cast<const float4*>(sm.xs + wv_phys(xc + 4 * lane + 128 * q));
+                const float4 t = *reinterpret_cast<const float4*>(sm.xs + wv_phys(tg + 4 * lane + 128 * q));
+                dot = __fmaf_rn(t.x, a.x, dot); dot = __fmaf_rn(t.y, a.y, dot);
+                dot = __fmaf_rn(t.z, a.z, dot); dot = __fmaf_rn(t.w, a.w, dot);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < WS_OVERLAP / 32; q++) {
+                const float a = sm.xs[wv_phys(xc + lane + 32 * q)];
+                dot = __fmaf_rn(sm.xs[wv_phys(tg + lane + 32 * q)], a, dot);
+                ea = __fmaf_rn(a, a, ea);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

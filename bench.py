@@ -509,7 +509,7 @@ def main() -> int:
                 "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 # the same on DRAM-counter bytes (the pool gather is served by L2, so this is about half of frac)
-                "frac_dram": (traffic / (kern_ms / 1e3) / 1e9 / peak) if traffic and args.workload != "mixed" else None,
+                "frac_dram": (traffic / (kern_ms / 1e3) / 1e9 / peak) if traffic and args.workload == "speed1" and args.utts == 4096 else None,
                 # the stage is instruction-issue bound, so the issue-slot utilisation is the fraction that
                 # says how far the kernel is from ITS ceiling (ncu, committed captures; FP32 pipe utilisation beside it)
                 "issue_active_pct": facts.get("issue_active_pct"), "fma_pipe_pct": facts.get("fma_pipe_pct"),

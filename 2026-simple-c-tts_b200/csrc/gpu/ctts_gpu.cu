@@ -857,7 +857,8 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
         if (!stasks.empty())
             d_need += PlanAlloc::up256(stasks.size() * sizeof(ctts::StretchTask)) + 2 * PlanAlloc::up256(ola_task.size() * 4 + 4) +
                       PlanAlloc::up256(pre_total * 2 + 16) + PlanAlloc::up256(pos_total * 4 + 4) + PlanAlloc::up256(stasks.size() * 20) + 4096;
-        const size_t h_need = PlanAlloc::up256(ops_bytes) + PlanAlloc::up256(tasks_bytes) + 4096;
+        const size_t st_bytes = PlanAlloc::up256(stasks.size() * sizeof(ctts::StretchTask)) + 2 * PlanAlloc::up256(ola_task.size() * 4 + 4);
+        const size_t h_need = PlanAlloc::up256(ops_bytes) + PlanAlloc::up256(tasks_bytes) + st_bytes + 4096;
         rc = ensure_arena(ctx, arena, d_need, h_need);
         if (rc) { delete p; return rc; }
         p->h_ops = reinterpret_cast<ctts_plan_op*>(arena->h);
@@ -899,10 +900,24 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
     cudaStream_t st = ctx->stream;
     CUP(cudaMemsetAsync(p->d_chain, 0, tasks_cap * 8, st));
     if (p->n_stretch) {
-        CUP(cudaMemcpyAsync(p->d_stasks, stasks.data(), stasks.size() * sizeof(ctts::StretchTask), cudaMemcpyHostToDevice, st));
-        CUP(cudaMemcpyAsync(p->d_ola_task, ola_task.data(), ola_task.size() * 4, cudaMemcpyHostToDevice, st));
-        CUP(cudaMemcpyAsync(p->d_ola_first, ola_first.data(), ola_first.size() * 4, cudaMemcpyHostToDevice, st));
-        CUP(cudaStreamSynchronize(st));   // the vectors above are about to go out of scope
+        const void *h_st = stasks.data(), *h_ot = ola_task.data(), *h_of = ola_first.data();
+        if (arena) {
+            // through the lane's pinned staging: truly asynchronous, no stream drain per piece (the staging is
+            // reused only after the lane's piece has completed)
+            char* at = arena->h + PlanAlloc::up256(ops_bytes) + PlanAlloc::up256(tasks_bytes);
+            memcpy(at, stasks.data(), stasks.size() * sizeof(ctts::StretchTask));
+            h_st = at;
+            at += PlanAlloc::up256(stasks.size() * sizeof(ctts::StretchTask));
+            memcpy(at, ola_task.data(), ola_task.size() * 4);
+            h_ot = at;
+            at += PlanAlloc::up256(ola_task.size() * 4 + 4);
+            memcpy(at, ola_first.data(), ola_first.size() * 4);
+            h_of = at;
+        }
+        CUP(cudaMemcpyAsync(p->d_stasks, h_st, stasks.size() * sizeof(ctts::StretchTask), cudaMemcpyHostToDevice, st));
+        CUP(cudaMemcpyAsync(p->d_ola_task, h_ot, ola_task.size() * 4, cudaMemcpyHostToDevice, st));
+        CUP(cudaMemcpyAsync(p->d_ola_first, h_of, ola_first.size() * 4, cudaMemcpyHostToDevice, st));
+        if (!arena) CUP(cudaStreamSynchronize(st));   // pageable vectors that are about to go out of scope
     }
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctts::assemble_kernel, ctts::ASM_THREADS, p->smem_bytes) != cudaSuccess || occ < 1)

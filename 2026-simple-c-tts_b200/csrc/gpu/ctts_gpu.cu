@@ -1644,6 +1644,37 @@ int ctts_gpu_synth_batch_stream(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, 
 }
 
 
+// The same batch call with the library choosing the layout: packed output (exactly the samples that exist
+// cross PCIe), offsets returned.  A session over the pieces of the plan.
+int ctts_gpu_synth_batch_packed(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_assembly_params* params,
+                                int16_t* pcm_out, uint64_t capacity, uint64_t* out_offsets, uint32_t* out_counts,
+                                uint64_t* samples_used) {
+    if (!ctx || !plan || !params || !out_offsets || !out_counts || (capacity && !pcm_out)) return CTTS_GPU_ERR_INVALID_ARG;
+    if (plan->n_utts && (!plan->utt_op_begin || !plan->speed)) return CTTS_GPU_ERR_INVALID_ARG;
+    const uint32_t n = plan->n_utts;
+    for (uint32_t u = 0; u < n; u++)
+        if (plan->utt_op_begin[u + 1] < plan->utt_op_begin[u] || plan->utt_op_begin[u + 1] > plan->n_ops)
+            return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "ops of utterance %u are not ascending", u);
+    ctts_gpu_session* s = nullptr;
+    int rc = ctts_gpu_session_begin(ctx, params, pcm_out, capacity, nullptr, nullptr, &s);
+    if (rc) return rc;
+    // pieces of about chunk_samples / 2400 utterances ... by ops: an op appends at most a few thousand samples, so
+    // cut by op count (no bounds are known before a piece is compiled): ~45 k ops ~ 128 sentences of 200 characters
+    const uint64_t ops_per_piece = std::max<uint64_t>(ctx->knobs.chunk_samples / 2800, 64);
+    for (uint32_t u0 = 0, u = 0; u < n && !rc; u++) {
+        if (plan->utt_op_begin[u + 1] - plan->utt_op_begin[u0] >= ops_per_piece || u + 1 == n) {
+            ctts_batch_plan piece = *plan;
+            piece.n_utts = u + 1 - u0;
+            piece.utt_op_begin = plan->utt_op_begin + u0;
+            piece.speed = plan->speed + u0;
+            rc = submit_piece(s, &piece, nullptr, nullptr, out_offsets + u0, out_counts + u0);
+            u0 = u + 1;
+        }
+    }
+    const int rc_end = ctts_gpu_session_end(s, samples_used);
+    return rc ? rc : rc_end;
+}
+
 // ---------------------------------------------------------------- one batch on several GPUs
 
 // Utterances are independent (no state crosses ctts_synthesize calls, ctts.c:3623, except the read-only

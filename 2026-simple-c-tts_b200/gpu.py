@@ -68,6 +68,7 @@ def lib(build: bool = True) -> C.CDLL:
         L.ctts_gpu_session_begin.argtypes = [vp, C.POINTER(AssemblyParams), vp, C.c_uint64, vp, vp, C.POINTER(vp)]
         L.ctts_gpu_session_submit.argtypes = [vp, C.POINTER(CBatchPlan), vp, vp]
         L.ctts_gpu_session_end.argtypes = [vp, u64p]
+        L.ctts_gpu_synth_batch_packed.argtypes = [vp, C.POINTER(CBatchPlan), C.POINTER(AssemblyParams), vp, C.c_uint64, vp, vp, u64p]
         L.ctts_gpu_multi_synth_batch.argtypes = [C.POINTER(vp), C.c_uint32, C.POINTER(CBatchPlan), C.POINTER(AssemblyParams),
                                                  vp, vp, vp, vp]
         _lib = L
@@ -205,6 +206,18 @@ class GpuSynth:
         self._check(lib().ctts_gpu_synth_batch(self._h, C.byref(cp), C.byref(params), pcm_out.ctypes.data,
                                                out_offsets.ctypes.data, counts.ctypes.data))
         return pcm_out, out_offsets, counts[:plan.n_utts]
+
+    def synth_batch_packed(self, plan: BatchPlan, params: AssemblyParams, pcm_out: np.ndarray):
+        """ctts_gpu_synth_batch_packed: library-chosen packed layout. Returns (offsets[n], counts[n], samples_used)."""
+        assert pcm_out.dtype == np.int16 and pcm_out.flags["C_CONTIGUOUS"]
+        n = plan.n_utts
+        off = np.zeros(max(n, 1), dtype=np.uint64)
+        cnt = np.zeros(max(n, 1), dtype=np.uint32)
+        used = C.c_uint64()
+        cp = plan.as_c()
+        self._check(lib().ctts_gpu_synth_batch_packed(self._h, C.byref(cp), C.byref(params), pcm_out.ctypes.data, pcm_out.size,
+                                                       off.ctypes.data, cnt.ctypes.data, C.byref(used)))
+        return off[:n], cnt[:n], int(used.value)
 
     def synth_batch_stream(self, plan: BatchPlan, params: AssemblyParams, on_chunk, pcm_out: np.ndarray | None = None,
                            out_offsets: np.ndarray | None = None):

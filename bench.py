@@ -435,6 +435,13 @@ def main() -> int:
             _, _, c2 = g.synth_batch(plan, prm, host_np, offsets)
         torch.cuda.synchronize(local_rank)
         plan_s_e2e = (time.perf_counter() - te) / e2e_steps
+        g.synth_batch_packed(plan, prm, host_np)
+        sync_all()
+        te = time.perf_counter()
+        for _ in range(e2e_steps):
+            g.synth_batch_packed(plan, prm, host_np)
+        torch.cuda.synchronize(local_rank)
+        plan_packed_s = (time.perf_counter() - te) / e2e_steps
         tb = pipe.TextBatch(texts, speeds)
         pipe.synth_texts(fr, g, tb, host_np)          # warm-up
         sync_all()
@@ -448,6 +455,7 @@ def main() -> int:
         d2h = int(used * 2 + 8 * plan.n_utts)
         e2e = {"seconds_per_step": e2e_s, "h2d": h2d, "d2h": d2h, "steps": e2e_steps,
                "audio_s": float(c3.astype(np.int64).sum()) / SAMPLE_RATE, "plan_to_pcm_s": plan_s_e2e,
+               "plan_to_pcm_packed_ms": 1e3 * plan_packed_s,
                "timing": {"first_piece_planned_ms": 1e3 * tm.first_plan_s, "all_planned_ms": 1e3 * tm.all_plans_s,
                           "all_submitted_ms": 1e3 * tm.all_submitted_s, "done_ms": 1e3 * tm.done_s,
                           "submitter_waited_for_plans_ms": 1e3 * tm.wait_for_plans_s, "device_pieces": int(tm.pieces)}}
@@ -540,7 +548,9 @@ def main() -> int:
                            "host_threads": cores, "rank0_timing": e2e["timing"],
                            "d2h_GBps_all_gpus": 1e-9 * world * e2e["d2h"] / e2e_s_all,
                            "plan_to_pcm": {"value": e2e_audio_all / e2e_plan_s_all, "ms_per_step": 1e3 * e2e_plan_s_all,
-                                           "call": "ctts_gpu_synth_batch on a ready plan (the back end alone)"}}
+                                           "call": "ctts_gpu_synth_batch on a ready plan (the back end alone; caller-defined slots, span copies)",
+                                           "rank0_packed_ms_per_step": e2e["plan_to_pcm_packed_ms"],
+                                           "packed_call": "ctts_gpu_synth_batch_packed (library layout, exact-size copies)"}}
         if strong:
             line["strong"] = strong
         if not args.no_cpu_baseline:

@@ -688,3 +688,30 @@ def test_multi_device_entry_on_two_gpus(H, gpu, small_db, oracle_small, front_sm
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two CUDA devices")
     _multi_check(H, gpu, list(range(min(torch.cuda.device_count(), 8))), small_db, oracle_small, front_small)
+
+
+def test_packed_batch_call(H, gpu, synth_small, oracle_small, front_small, monkeypatch):
+    """ctts_gpu_synth_batch_packed: the batch call with a library-chosen, packed layout (device prefix sum of the
+    counts + gather; exactly the samples that exist cross PCIe), several pieces, plain and stretched utterances."""
+    monkeypatch.setenv("CTTS_GPU_CHUNK_SAMPLES", "2000000")
+    g = gpu.GpuSynth(small_db_bytes(H), 0)
+    prm = front_small.params()
+    texts = H.corpus.batch(30, seed=333, target_chars=90) + ["", "olá mundo"]
+    speeds = [1.0, 1.5, 1.0, 0.6, 1.0, 2.0, 1.0, 1.0] * 4
+    plan = front_small.plan(texts, speeds)
+    cap = int(g.layout(plan)[-1])
+    pcm = np.full(cap, 12345, dtype=np.int16)
+    off, cnt, used = g.synth_batch_packed(plan, prm, pcm)
+    assert off[0] == 0 and np.array_equal(np.diff(off.astype(np.int64)), (cnt[:-1].astype(np.int64) + 7) // 8 * 8)
+    assert used == int(off[-1]) + (int(cnt[-1]) + 7) // 8 * 8 and used < cap
+    for u in range(plan.n_utts):
+        want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))
+        _assert_same(pcm[int(off[u]):int(off[u]) + int(cnt[u])], want, f"packed utt {u}")
+        assert not pcm[int(off[u]) + int(cnt[u]):int(off[u]) + (int(cnt[u]) + 7) // 8 * 8].any()      # zero padding
+    assert (pcm[used:] == 12345).all()                                                        # nothing written past the end
+    with pytest.raises(gpu.GpuError):
+        g.synth_batch_packed(plan, prm, np.zeros(used - 8, dtype=np.int16))
+
+
+def small_db_bytes(H):
+    return H.small_db()

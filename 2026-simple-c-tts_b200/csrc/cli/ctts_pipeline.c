@@ -27,6 +27,206 @@
 #define LOOKAHEAD 96   /* groups planned ahead of the one being submitted (bounds the memory held in plans) */
 #define GROUP_UTTS 16  /* utterances per planner job */
 
+/* ------------------------------------------------------------------ plan cache
+ * The plan of an utterance depends on its text alone (and on the front end handle: voice index, config, rules) --
+ * the speed travels beside the ops -- so a server that is asked for the same sentences again can skip the text
+ * half entirely.  Entries are immutable and never evicted (the cache stops taking entries when it is full), so a
+ * reader needs the lock only while it probes the table. */
+typedef struct {
+    uint64_t hash;
+    char* text;
+    ctts_plan_op* ops;
+    uint32_t n_ops, found, missing;
+} cache_entry;
+
+struct ctts_b200_plan_cache {
+    pthread_mutex_t mu;
+    cache_entry** table;   /* open addressing */
+    size_t slots, entries;
+    size_t bytes, max_bytes;
+    uint64_t hits, misses;
+};
+
+static uint64_t fnv1a64(const char* s) {
+    uint64_t h = 1469598103934665603ull;
+    for (; *s; s++) h = (h ^ (unsigned char)*s) * 1099511628211ull;
+    return h;
+}
+
+ctts_b200_plan_cache* ctts_b200_plan_cache_create(size_t max_bytes) {
+    ctts_b200_plan_cache* c = calloc(1, sizeof *c);
+    if (!c) return NULL;
+    c->max_bytes = max_bytes;
+    c->slots = 1024;
+    while (c->slots < max_bytes / 2048) c->slots *= 2;   /* a plan of a 200-character sentence is ~11 KB */
+    c->table = calloc(c->slots, sizeof *c->table);
+    if (!c->table || pthread_mutex_init(&c->mu, NULL) != 0) {
+        free(c->table);
+        free(c);
+        return NULL;
+    }
+    return c;
+}
+
+void ctts_b200_plan_cache_destroy(ctts_b200_plan_cache* c) {
+    if (!c) return;
+    for (size_t i = 0; i < c->slots; i++)
+        if (c->table[i]) {
+            free(c->table[i]->text);
+            free(c->table[i]->ops);
+            free(c->table[i]);
+        }
+    free(c->table);
+    pthread_mutex_destroy(&c->mu);
+    free(c);
+}
+
+void ctts_b200_plan_cache_stats(ctts_b200_plan_cache* c, uint64_t* hits, uint64_t* misses, uint64_t* entries, uint64_t* bytes) {
+    if (!c) return;
+    pthread_mutex_lock(&c->mu);
+    if (hits) *hits = c->hits;
+    if (misses) *misses = c->misses;
+    if (entries) *entries = c->entries;
+    if (bytes) *bytes = c->bytes;
+    pthread_mutex_unlock(&c->mu);
+}
+
+static const cache_entry* cache_lookup(ctts_b200_plan_cache* c, const char* text, uint64_t h) {
+    const cache_entry* e = NULL;
+    pthread_mutex_lock(&c->mu);
+    for (size_t i = h & (c->slots - 1), k = 0; k < c->slots && c->table[i]; i = (i + 1) & (c->slots - 1), k++)
+        if (c->table[i]->hash == h && strcmp(c->table[i]->text, text) == 0) {
+            e = c->table[i];
+            break;
+        }
+    if (e) c->hits++;
+    else c->misses++;
+    pthread_mutex_unlock(&c->mu);
+    return e;
+}
+
+static void cache_insert(ctts_b200_plan_cache* c, const char* text, uint64_t h, const ctts_plan_op* ops, uint32_t n_ops,
+                         uint32_t found, uint32_t missing) {
+    const size_t need = strlen(text) + 1 + (size_t)n_ops * sizeof *ops + sizeof(cache_entry);
+    cache_entry* e = malloc(sizeof *e);
+    char* t = strdup(text);
+    ctts_plan_op* o = malloc((n_ops ? n_ops : 1) * sizeof *o);
+    if (!e || !t || !o) {
+        free(e);
+        free(t);
+        free(o);
+        return;
+    }
+    if (n_ops) memcpy(o, ops, (size_t)n_ops * sizeof *o);
+    e->hash = h;
+    e->text = t;
+    e->ops = o;
+    e->n_ops = n_ops;
+    e->found = found;
+    e->missing = missing;
+    int taken = 0;
+    pthread_mutex_lock(&c->mu);
+    if (c->bytes + need <= c->max_bytes && 2 * (c->entries + 1) <= c->slots) {
+        size_t i = h & (c->slots - 1);
+        int dup = 0;
+        while (c->table[i]) {
+            if (c->table[i]->hash == h && strcmp(c->table[i]->text, text) == 0) {
+                dup = 1;
+                break;
+            }
+            i = (i + 1) & (c->slots - 1);
+        }
+        if (!dup) {
+            c->table[i] = e;
+            c->entries++;
+            c->bytes += need;
+            taken = 1;
+        }
+    }
+    pthread_mutex_unlock(&c->mu);
+    if (!taken) {
+        free(e);
+        free(t);
+        free(o);
+    }
+}
+
+/* Plan `cnt` texts: cached utterances are copied, the others planned by the front end (one call for all of them)
+ * and offered to the cache.  The result is byte-identical to planning all of them. */
+static int plan_group(ctts_front* front, ctts_b200_plan_cache* cache, const char* const* texts, const float* speeds,
+                      uint32_t cnt, ctts_batch_plan* out, uint32_t* stats) {
+    if (!cache) return ctts_front_plan_batch_threads(front, texts, speeds, cnt, 1, out, stats);
+    const cache_entry** hit = calloc(cnt ? cnt : 1, sizeof *hit);
+    uint64_t* hash = malloc((cnt ? cnt : 1) * sizeof *hash);
+    const char** miss_text = malloc((cnt ? cnt : 1) * sizeof *miss_text);
+    uint32_t* miss_stats = malloc((cnt ? cnt : 1) * 2 * sizeof *miss_stats);
+    uint32_t* begin = malloc(((size_t)cnt + 1) * sizeof *begin);
+    float* sp = malloc(((size_t)cnt + 1) * sizeof *sp);
+    ctts_batch_plan fresh;
+    memset(&fresh, 0, sizeof fresh);
+    int rc = (hit && hash && miss_text && miss_stats && begin && sp) ? 0 : CTTS_FRONT_ERR_OUT_OF_MEMORY;
+    uint32_t n_miss = 0;
+    for (uint32_t u = 0; u < cnt && !rc; u++) {
+        if (!texts[u]) {
+            rc = CTTS_FRONT_ERR_INVALID_ARG;
+            break;
+        }
+        hash[u] = fnv1a64(texts[u]);
+        hit[u] = cache_lookup(cache, texts[u], hash[u]);
+        if (!hit[u]) miss_text[n_miss++] = texts[u];
+    }
+    if (!rc && n_miss) rc = ctts_front_plan_batch_threads(front, miss_text, NULL, n_miss, 1, &fresh, miss_stats);
+    ctts_plan_op* ops = NULL;
+    if (!rc) {
+        uint64_t total = 0;
+        for (uint32_t u = 0, m = 0; u < cnt; u++)
+            total += hit[u] ? hit[u]->n_ops : fresh.utt_op_begin[m + 1] - fresh.utt_op_begin[m], m += hit[u] ? 0 : 1;
+        ops = malloc((total ? total : 1) * sizeof *ops);
+        if (!ops || total > 0xffffffffull) rc = CTTS_FRONT_ERR_OUT_OF_MEMORY;
+    }
+    if (!rc) {
+        uint32_t at = 0;
+        for (uint32_t u = 0, m = 0; u < cnt; u++) {
+            begin[u] = at;
+            sp[u] = speeds ? speeds[u] : 1.0f;
+            if (hit[u]) {
+                if (hit[u]->n_ops) memcpy(ops + at, hit[u]->ops, (size_t)hit[u]->n_ops * sizeof *ops);
+                at += hit[u]->n_ops;
+                if (stats) {
+                    stats[2 * u] = hit[u]->found;
+                    stats[2 * u + 1] = hit[u]->missing;
+                }
+            } else {
+                const uint32_t b = fresh.utt_op_begin[m], e = fresh.utt_op_begin[m + 1];
+                if (e > b) memcpy(ops + at, fresh.ops + b, (size_t)(e - b) * sizeof *ops);
+                cache_insert(cache, texts[u], hash[u], fresh.ops + b, e - b, miss_stats[2 * m], miss_stats[2 * m + 1]);
+                at += e - b;
+                if (stats) {
+                    stats[2 * u] = miss_stats[2 * m];
+                    stats[2 * u + 1] = miss_stats[2 * m + 1];
+                }
+                m++;
+            }
+        }
+        begin[cnt] = at;
+        out->n_utts = cnt;
+        out->n_ops = at;
+        out->utt_op_begin = begin;
+        out->speed = sp;
+        out->ops = ops;   /* released by ctts_front_plan_free: plain malloc'ed arrays, like the front end's */
+    } else {
+        free(begin);
+        free(sp);
+        free(ops);
+    }
+    if (n_miss) ctts_front_plan_free(&fresh);
+    free(hit);
+    free(hash);
+    free(miss_text);
+    free(miss_stats);
+    return rc;
+}
+
 typedef struct {
     ctts_batch_plan plan;
     int state;   /* 0: not planned, 1: planned, <0: error code */
@@ -34,6 +234,7 @@ typedef struct {
 
 typedef struct {
     ctts_front* front;
+    ctts_b200_plan_cache* cache;
     const char* const* texts;
     const float* speeds;
     uint32_t* stats;
@@ -69,8 +270,8 @@ static void* planner(void* arg) {
         pthread_mutex_unlock(&P->mu);
         const uint32_t u0 = P->piece_begin[i], cnt = P->piece_begin[i + 1] - u0;
         ctts_batch_plan pl;
-        int rc = ctts_front_plan_batch_threads(P->front, P->texts + u0, P->speeds ? P->speeds + u0 : NULL, cnt, 1, &pl,
-                                               P->stats ? P->stats + 2 * (size_t)u0 : NULL);
+        int rc = plan_group(P->front, P->cache, P->texts + u0, P->speeds ? P->speeds + u0 : NULL, cnt, &pl,
+                            P->stats ? P->stats + 2 * (size_t)u0 : NULL);
         pthread_mutex_lock(&P->mu);
         if (rc == 0) {
             P->slots[i].plan = pl;
@@ -112,6 +313,7 @@ int ctts_b200_synth_texts(ctts_front* front, ctts_gpu_ctx* gpu, const char* cons
     pipeline P;
     memset(&P, 0, sizeof P);
     P.front = front;
+    P.cache = opt ? opt->cache : NULL;
     P.texts = texts;
     P.speeds = speeds;
     P.stats = stats;

@@ -13,7 +13,8 @@ from . import gpu as _gpu
 
 
 class Options(C.Structure):
-    _fields_ = [("piece_utts", C.c_uint32), ("threads", C.c_uint32), ("on_piece", C.c_void_p), ("user", C.c_void_p)]
+    _fields_ = [("piece_utts", C.c_uint32), ("threads", C.c_uint32), ("on_piece", C.c_void_p), ("user", C.c_void_p),
+                ("cache", C.c_void_p)]
 
 
 class Timing(C.Structure):
@@ -38,8 +39,39 @@ def lib() -> C.CDLL:
                                             C.POINTER(C.c_uint64), C.POINTER(Options), C.POINTER(Timing)]
         L.ctts_b200_capacity_hint.argtypes = [vp, vp, vp, C.c_uint32]
         L.ctts_b200_capacity_hint.restype = C.c_uint64
+        L.ctts_b200_plan_cache_create.argtypes = [C.c_size_t]
+        L.ctts_b200_plan_cache_create.restype = vp
+        L.ctts_b200_plan_cache_destroy.argtypes = [vp]
+        L.ctts_b200_plan_cache_destroy.restype = None
+        L.ctts_b200_plan_cache_stats.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 4
+        L.ctts_b200_plan_cache_stats.restype = None
         _lib = L
     return _lib
+
+
+class PlanCache:
+    """ctts_b200_plan_cache: plans by text, for callers that see the same sentences again."""
+
+    def __init__(self, max_bytes: int = 256 << 20):
+        self._h = lib().ctts_b200_plan_cache_create(max_bytes)
+        if not self._h:
+            raise MemoryError("ctts_b200_plan_cache_create")
+
+    def stats(self) -> dict:
+        v = [C.c_uint64() for _ in range(4)]
+        lib().ctts_b200_plan_cache_stats(self._h, *[C.byref(x) for x in v])
+        return dict(zip(("hits", "misses", "entries", "bytes"), (int(x.value) for x in v)))
+
+    def close(self) -> None:
+        if self._h:
+            lib().ctts_b200_plan_cache_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class TextBatch:
@@ -62,7 +94,7 @@ def capacity_hint(front, batch: TextBatch) -> int:
 
 
 def synth_texts(front, gpu, batch: TextBatch, pcm_out: np.ndarray, piece_utts: int = 0, threads: int = 0,
-                want_stats: bool = False):
+                want_stats: bool = False, cache: PlanCache | None = None):
     """ctts_b200_synth_texts.  Returns (offsets[n], counts[n], samples_used, Timing[, stats])."""
     assert pcm_out.dtype == np.int16 and pcm_out.flags["C_CONTIGUOUS"]
     n = batch.n
@@ -70,7 +102,7 @@ def synth_texts(front, gpu, batch: TextBatch, pcm_out: np.ndarray, piece_utts: i
     cnt = np.zeros(max(n, 1), dtype=np.uint32)
     stats = np.zeros(2 * max(n, 1), dtype=np.uint32) if want_stats else None
     used = C.c_uint64()
-    opt = Options(piece_utts, threads, None, None)
+    opt = Options(piece_utts, threads, None, None, cache._h if cache is not None else None)
     tm = Timing()
     rc = lib().ctts_b200_synth_texts(front._h, gpu._h, batch.ptrs, batch.speeds_ptr, n, pcm_out.ctypes.data,
                                      pcm_out.size, off.ctypes.data, cnt.ctypes.data,

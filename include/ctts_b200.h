@@ -20,11 +20,22 @@
 extern "C" {
 #endif
 
+/* A plan cache: the plan of an utterance depends on its text alone (for one front end handle: voice index, config,
+ * rules; the speed travels beside the ops), so a caller that sees the same sentences again can skip the text half.
+ * Entries are immutable and never evicted; the cache stops taking entries at max_bytes.  Thread safe.  Use one
+ * cache per front end handle. */
+typedef struct ctts_b200_plan_cache ctts_b200_plan_cache;
+ctts_b200_plan_cache* ctts_b200_plan_cache_create(size_t max_bytes);
+void ctts_b200_plan_cache_destroy(ctts_b200_plan_cache* cache);
+void ctts_b200_plan_cache_stats(ctts_b200_plan_cache* cache, uint64_t* hits, uint64_t* misses, uint64_t* entries,
+                                uint64_t* bytes);
+
 typedef struct ctts_b200_options {
     uint32_t piece_utts;     /* most utterances per device piece (0: 128); planner jobs are groups of 16 */
     uint32_t threads;        /* planner threads (0: host cores - 1, at least 1, at most 32) */
     ctts_gpu_chunk_fn on_piece;   /* may be NULL: called in order as utterance ranges arrive in pcm_out */
     void* user;
+    ctts_b200_plan_cache* cache;  /* may be NULL */
 } ctts_b200_options;
 
 /* Timing of one call, for bench.py and the command line (seconds since the call began). */

@@ -34,10 +34,14 @@ def test_pipeline_library_exports_header_symbols(H):
     pipe = H.importlib.import_module("2026-simple-c-tts_b200.pipeline")
     L = pipe.lib()
     names = _declared(os.path.join(H.ROOT, "include", "ctts_b200.h"))
-    assert names == ["ctts_b200_capacity_hint", "ctts_b200_synth_texts"]
+    assert names == ["ctts_b200_capacity_hint", "ctts_b200_plan_cache_create", "ctts_b200_plan_cache_destroy",
+                     "ctts_b200_plan_cache_stats", "ctts_b200_synth_texts"]
     for n in names:
         assert hasattr(L, n), n
-    assert C.sizeof(pipe.Timing) == 6 * 8 and C.sizeof(pipe.Options) == 24
+    assert C.sizeof(pipe.Timing) == 6 * 8 and C.sizeof(pipe.Options) == 32
+    cache = pipe.PlanCache(1 << 20)
+    assert cache.stats() == {"hits": 0, "misses": 0, "entries": 0, "bytes": 0}
+    cache.close()
 
 
 def test_capacity_hint_covers_the_bounds(H, small_db, front_small):

@@ -648,8 +648,16 @@ def test_text_pipeline_equals_the_planned_batch(H, gpu, synth_small, front_small
         _assert_same(ref[u], want, f"utt {u}")
     batch = pipe.TextBatch(texts, speeds)
     pcm = np.zeros(pipe.capacity_hint(front_small, batch), dtype=np.int16)
-    for piece_utts, threads in ((1, 3), (7, 1), (16, 4), (0, 0), (1000, 2)):
-        off, cnt, used, tm, stats = pipe.synth_texts(front_small, synth_small, batch, pcm, piece_utts, threads, want_stats=True)
+    cache = pipe.PlanCache(64 << 20)
+    for k, (piece_utts, threads) in enumerate(((1, 3), (7, 1), (16, 4), (0, 0), (1000, 2), (0, 0), (5, 3))):
+        # the last two runs go through a plan cache: cold (every text planned and stored), then warm (no text planned)
+        off, cnt, used, tm, stats = pipe.synth_texts(front_small, synth_small, batch, pcm, piece_utts, threads, want_stats=True,
+                                                     cache=cache if k >= 5 else None)
+        if k == 5:
+            assert cache.stats()["hits"] <= 2 and cache.stats()["entries"] >= plan.n_utts - 2      # ("olá mundo" may repeat)
+        if k == 6:
+            st = cache.stats()
+            assert st["hits"] >= plan.n_utts and st["misses"] <= plan.n_utts
         assert used <= pcm.size and tm.done_s >= tm.all_submitted_s >= 0
         assert np.array_equal(stats[:, 0], plan.found) and np.array_equal(stats[:, 1], plan.missing)
         for u in range(plan.n_utts):

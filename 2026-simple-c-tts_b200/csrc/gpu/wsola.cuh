@@ -10,22 +10,25 @@
 //   wsola_scan_kernel    per utterance: the frame count and F = the first frame whose target, with
 //                        every offset before it 0, is all zero.  Speculated offsets: 0 before F,
 //                        -128 from F on.
-//   wsola_verify_kernel  every frame independently (tiles of 26 frames per CTA): under the
+//   wsola_verify_kernel  every frame independently (tiles of 24 frames per CTA): under the
 //                        speculated previous offset h the frame's offset is h again iff every other
 //                        candidate of the coarse and the fine stage scores < 1.0f.  Tier 1 proves that
-//                        with a partial sum: 1 - corr = |x^ - t^|^2 / 2 >= sum over a few short blocks
-//                        of (x^_i - t^_i)^2 (x^, t^ the unit-normalised windows; energies exact, from
-//                        a 64-bit prefix sum of squares), which needs 32 of the 384 terms.  What tier 1
-//                        cannot reject (0.3 candidates per frame) gets the full 384-term FMA filter
-//                        score (tier 2, one warp per candidate), and what that leaves within eps of 1
-//                        the reference's exact loop (tier 3).  A candidate that really reaches 1.0f
+//                        with a partial sum: 1 - corr = |x^ - t^|^2 / 2 >= sum over three 12-term blocks
+//                        of (x^_i - t^_i)^2 (x^, t^ the unit-normalised windows; window energies exact,
+//                        from a 64-bit prefix sum of squares): 36 of the 384 terms -- and, the blocks
+//                        being one analysis hop apart, a partial dot product serves three frames.  What
+//                        tier 1 cannot reject (0.45 candidates per frame) gets the full 384-term FMA
+//                        filter score (tier 2, one warp per candidate), and what that leaves within eps
+//                        of 1 the reference's exact loop (tier 3).  A candidate that really reaches 1.0f
 //                        marks the frame as the utterance's first bad frame.
 //   wsola_search_kernel  the repair: the frame-by-frame chain walk (below), started at the first bad
 //                        frame with the verified position before it; exits at once when the
 //                        speculation held (every utterance of the benchmark workloads).
 //
-// wsola_search_kernel: one CTA per stretched utterance walks the frames in order.  The reference scores <= 65 coarse candidates (offsets -128..128 step 4) and
-//    then <= 6 fine ones around the best, each score a 384-term sequential float loop
+//   wsola_ola_kernel     overlap-add in gather form (below).
+//
+// wsola_search_kernel: one CTA per stretched utterance walks the frames in order.  The reference
+//    scores <= 65 coarse candidates (offsets -128..128 step 4) and then <= 6 fine ones around the best, each score a 384-term sequential float loop
 //    (groups of 4: ((p0+p1)+p2)+p3, then +=, ctts.c:3411-3413) -- 91 % of its run time.
 //    Here every frame is decided in two steps that give the identical result:
 //      FILTER  all candidates get an approximate score: the cross term by FMA in any order
@@ -41,7 +44,7 @@
 //    Consecutive views overlap by 512 samples: the samples (as floats) and the prefix sums live
 //    in rings, a frame appends only its 128 new samples, prefetched while the previous frame is
 //    decided.  Output: the analysis position of every frame.
-// 2. wsola_ola_kernel: embarrassingly parallel gather-form overlap-add.  Each
+// wsola_ola_kernel: embarrassingly parallel gather-form overlap-add.  Each
 //    output sample adds its <= 8 windowed frame contributions in frame order
 //    into an int16 accumulator that wraps exactly like the reference's `+=`
 //    (ctts.c:3577) and a float norm (ctts.c:3578), normalises, and the CTA

@@ -1772,7 +1772,7 @@ int ctts_gpu_multi_synth_batch(ctts_gpu_ctx* const* ctxs, uint32_t n_ctx, const 
     for (std::thread& t : th) t.join();
     for (uint32_t d = 0; d < n_ctx; d++)
         if (rcs[d]) {
-            if (d) snprintf(ctxs[0]->err, sizeof ctxs[0]->err, "device %u: %s", d, ctxs[d]->err);
+            if (d) snprintf(ctxs[0]->err, sizeof ctxs[0]->err, "device %u: %.480s", d, ctxs[d]->err);
             return rcs[d];
         }
     return CTTS_GPU_OK;

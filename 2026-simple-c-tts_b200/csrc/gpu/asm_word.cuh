@@ -452,15 +452,18 @@ __device__ bool pitch_contour(const Smem& sm, int16_t* x, uint32_t n, float f0, 
     return true;
 }
 
-// ctts.c:3693-3713 / :3878-3898: trim then phrase intonation on [word_start, count)
-__device__ void op_word_end(State& s, const Smem& sm, const AsmArgs& A, uint32_t big, const ctts_plan_op& op) {
+// ctts.c:3693-3713 / :3878-3898: trim then phrase intonation on [word_start, count).  The two halves can be
+// run apart: a canonical region stops after the trim, a task that takes its samples from the region store
+// resumes at the intonation.
+__device__ void op_word_end(State& s, const Smem& sm, const AsmArgs& A, uint32_t big, const ctts_plan_op& op,
+                            bool do_trim = true, bool do_inton = true) {
     const int tid = threadIdx.x;
-    if ((op.flags & CTTS_WE_TRIM) && s.cnt > s.word_start) {
+    if (do_trim && (op.flags & CTTS_WE_TRIM) && s.cnt > s.word_start) {
         uint32_t len = s.cnt - s.word_start;
         if (len > A.prm.min_silence_samples)
             s.cnt = s.word_start + trim_region(sm, A, big, s.w + s.word_start, len);
     }
-    if (s.cnt <= s.word_start) return;
+    if (!do_inton || s.cnt <= s.word_start) return;
     const uint32_t n = s.cnt - s.word_start;
     int16_t* x = s.w + s.word_start;
     // device half of apply_phrase_intonation, ctts.c:2740, :2774-2790, :2839-2865

@@ -60,6 +60,46 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
     s.in_smem = true;
     s.w = sm.win;
     s.cap = A.wcap;
+    // ---- word-region deduplication.  What a word region holds right before its contour (units gathered, joined,
+    // DC removed, crossfaded, pauses, trimming) depends on the ops of the region alone, as long as no count clamp
+    // binds (the utterance is at least `thresh` samples long when the region starts) and nothing reaches back past the
+    // region's start (the plan compiler proves that).  Equal regions of a batch are therefore computed ONCE per launch
+    // -- the canonical tasks, first in ticket order, assembled as if the utterance were long -- and every other
+    // occurrence copies the result and resumes at its own contour (whose factors differ from word to word).
+    const bool canon = (task.flags & TASK_CANON) != 0;
+    uint32_t k_first = task.op_begin;
+    bool resumed = false;
+    if (canon) {
+        s.dst = A.region_store + task.dst_off;
+        s.have_base = true;
+        s.base = CANON_BASE;
+    } else if (task.region != NO_REGION) {
+        need_base(s, sm, A);
+        if (s.base >= task.thresh) {
+            if (tid == 0) {   // the canonical task has a smaller ticket: it is running or done
+                const unsigned long long* p = A.region_state + task.region;
+                unsigned long long v;
+                unsigned ns = 20;
+                while ((uint32_t)((v = ld_acquire_u64(p)) >> 32) != A.epoch) {
+                    __nanosleep(ns);
+                    if (ns < 640) ns *= 2;
+                }
+                sm.bcast[2] = (uint32_t)v;
+            }
+            __syncthreads();
+            const uint32_t len = sm.bcast[2];
+            __syncthreads();
+            if (len != NO_REGION && len <= s.cap) {
+                const int4* src = reinterpret_cast<const int4*>(A.region_store + __ldg(A.region_off + task.region));
+                int4* dstw = reinterpret_cast<int4*>(sm.win);
+                for (uint32_t v = tid; v < (len + 7) >> 3; v += ASM_THREADS) dstw[v] = __ldg(src + v);
+                s.cnt = len;
+                k_first = task.w_op;
+                resumed = true;
+                __syncthreads();
+            }
+        }
+    }
     if (task.flags & TASK_GLOBAL) {
         // the region does not fit the shared window: assemble it in place in the HBM slot
         need_base(s, sm, A);
@@ -76,7 +116,7 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
         if ((uint32_t)tid < 2 * n_pref) sm.ops[tid] = __ldg(reinterpret_cast<const int4*>(A.ops + task.op_begin) + tid);
         __syncthreads();
     }
-    for (uint32_t k = task.op_begin; k < task.op_end && !s.err; k++) {
+    for (uint32_t k = k_first; k < task.op_end && !s.err; k++) {
         ctts_plan_op op;
         {
             const uint32_t rel = k - task.op_begin;
@@ -105,7 +145,8 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
                 op_fade_out(s, sm, A, op.a);
                 break;
             case CTTS_OP_WORD_END:
-                op_word_end(s, sm, A, task.big, op);
+                if (canon) op_word_end(s, sm, A, task.big, op, true, false);              // stops in front of the contour
+                else op_word_end(s, sm, A, task.big, op, !(resumed && k == task.w_op), true);
                 break;
             case CTTS_OP_MARK:   // word_start_sample = buf.count, ctts.c:3723, :3765
                 s.word_start = s.cnt;
@@ -115,6 +156,20 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
         }
     }
 
+    if (canon) {
+        // ---- the canonical region goes to the region store; a region that left the window (cannot happen for
+        //      regions the plan compiler accepts) or failed is marked unusable: its occurrences assemble themselves
+        const bool ok = !s.err && s.in_smem && s.cnt <= task.dst_cap;
+        if (ok) {
+            const int4* srcw = reinterpret_cast<const int4*>(sm.win);
+            int4* d = reinterpret_cast<int4*>(s.dst);
+            for (uint32_t v = tid; v < (s.cnt + 7) >> 3; v += ASM_THREADS) d[v] = srcw[v];
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release_u64(A.region_state + task.region, ((unsigned long long)A.epoch << 32) | (ok ? s.cnt : NO_REGION));
+        return;
+    }
     // ---- publish: the region's final position is base, known from the predecessor
     need_base(s, sm, A);
     __syncthreads();

@@ -14,7 +14,9 @@
 #include <cstring>
 #include <chrono>
 #include <numeric>
+#include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -52,6 +54,7 @@ struct Knobs {
     int ctas_per_sm = 3;              // CTTS_GPU_CTAS_PER_SM: occupancy the assembly window is sized for
     int window = 0;                   // CTTS_GPU_WINDOW: shared window in samples (tests: force the HBM-window path)
     uint64_t chunk_samples = 128ull << 20;   // CTTS_GPU_CHUNK_SAMPLES: output samples per launch of ctts_gpu_synth_batch
+    bool region_dedup = true;         // CTTS_GPU_REGION_DEDUP=0: assemble every word region of a batch, equal ones too
     bool wsola_speculate = true;      // CTTS_GPU_WSOLA_SPECULATE=0: walk every WSOLA chain frame by frame
     uint32_t wsola_force_bad = 0;     // CTTS_GPU_WSOLA_FORCE_BAD=N: report every N-th frame as unverified (tests of the repair path)
 
@@ -66,6 +69,7 @@ struct Knobs {
         ctas_per_sm = (int)std::max(1ll, std::min(8ll, num("CTTS_GPU_CTAS_PER_SM", 3)));
         window = (int)std::max(0ll, num("CTTS_GPU_WINDOW", 0));
         chunk_samples = (uint64_t)std::max(1ll, num("CTTS_GPU_CHUNK_SAMPLES", 128ll << 20));
+        region_dedup = num("CTTS_GPU_REGION_DEDUP", 1) != 0;
         wsola_speculate = num("CTTS_GPU_WSOLA_SPECULATE", 1) != 0;
         wsola_force_bad = (uint32_t)std::max(0ll, num("CTTS_GPU_WSOLA_FORCE_BAD", 0));
     }
@@ -163,6 +167,10 @@ struct ctts_gpu_plan {
     ctts::RegionTask* d_tasks = nullptr;
     unsigned long long* d_chain = nullptr;
     uint32_t* d_ticket = nullptr;   // one per chunk
+    int16_t* d_region_store = nullptr;              // canonical word regions (see run_task in assemble.cuh)
+    unsigned long long* d_region_off = nullptr;
+    unsigned long long* d_region_state = nullptr;
+    size_t d_used = 0;              // arena mode: device bytes taken by prepare_plan (build_chunk continues from here)
     std::vector<PlanChunk> chunks;
     uint32_t n_tasks = 0;
     uint32_t n_global_tasks = 0;
@@ -848,12 +856,19 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
 
     // ---- workspace.  The private op copy and the tasks are built directly in (pinned) staging.
     const size_t ops_bytes = std::max<size_t>(n_ops_local, 1) * sizeof(ctts_plan_op);
-    const size_t tasks_cap = (size_t)sc.n_regions + 1;   // merging only lowers the count
+    // merging only lowers the count of region tasks; canonical word regions (each stands for >= 2 tasks) add at most half
+    const size_t tasks_cap = (size_t)sc.n_regions + (size_t)sc.n_regions / 2 + 2;
+    uint64_t pre_sum = 0;
+    for (uint32_t u = 0; u < n; u++) pre_sum += pre[u];
+    // region store: the canonical regions' slots (<= half of all region samples) + their tables
+    const size_t region_bytes = PlanAlloc::up256((pre_sum / 2 + 16 * (sc.n_regions + 1)) * sizeof(int16_t)) +
+                                2 * PlanAlloc::up256((sc.n_regions / 2 + 2) * 8);
     const size_t tasks_bytes = tasks_cap * sizeof(ctts::RegionTask);
     if (arena) {
         // device side: ops, tasks, chain, tickets, counts, pre_counts, err (+ the stretch buffers)
         size_t d_need = PlanAlloc::up256(ops_bytes) + PlanAlloc::up256(tasks_bytes) + PlanAlloc::up256(tasks_cap * 8) +
-                        PlanAlloc::up256((size_t)n_chunks * 4) + 3 * PlanAlloc::up256(std::max<size_t>(n, 1) * 4) + 65536;
+                        PlanAlloc::up256((size_t)n_chunks * 4) + 3 * PlanAlloc::up256(std::max<size_t>(n, 1) * 4) + 65536 +
+                        (ctx->knobs.region_dedup ? region_bytes + 4096 : 0);
         if (!stasks.empty())
             d_need += PlanAlloc::up256(stasks.size() * sizeof(ctts::StretchTask)) + 2 * PlanAlloc::up256(ola_task.size() * 4 + 4) +
                       PlanAlloc::up256(pre_total * 2 + 16) + PlanAlloc::up256(pos_total * 4 + 4) + PlanAlloc::up256(stasks.size() * 20) + 4096;
@@ -897,6 +912,7 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
         ctts_gpu_plan_destroy(p);
         return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "plan workspace: %s", cudaGetErrorString(al.err));
     }
+    p->d_used = al.d_used;
     cudaStream_t st = ctx->stream;
     CUP(cudaMemsetAsync(p->d_chain, 0, tasks_cap * 8, st));
     if (p->n_stretch) {
@@ -1047,11 +1063,131 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
         }
     }
 
-    // ticket order: region-major (task k of every utterance before task k+1 of any), inside a
-    // row longest first (it is the one a successor may have to wait for, and longest-first
+    // ---- word-region deduplication (run_task in assemble.cuh).  A task is ELIGIBLE when the window it holds on
+    // reaching the contour of its first WORD_END is a function of the ops before it alone:
+    //   * no MARK before that WORD_END (the region starts with the task), the task fits the shared window;
+    //   * every join finds its crossfade / energy window min(xf, n) and its pitch-analysis window min(2 xf, n/2)
+    //     inside the region (nothing reaches back into an earlier region), every live fade-out too;
+    //   * the remaining count clamps (count >= 200, count / 2 >= analysis window, ctts.c:1983-1987) do not bind,
+    //     which holds when the utterance is at least `thresh` samples long at the start of the task (checked on
+    //     the device: the first region or two of an utterance usually assemble themselves).
+    // Eligible tasks with equal ops (kind, flags, unit / samples, crossfade; the trim flag of the WORD_END) form a
+    // group; a group of two or more gets a canonical task that computes the region once per launch.
+    struct Dedup { uint32_t w_op = 0, thresh = 0, group = ctts::NO_REGION; };
+    std::vector<Dedup> dd(ht.size());
+    struct Group { uint32_t first_task, count, canon; };
+    std::vector<Group> groups;
+    if (ctx->knobs.region_dedup) {
+        std::unordered_map<std::string, uint32_t> seen;
+        seen.reserve(ht.size() / 8 + 16);
+        std::string sig;
+        for (size_t ti = 0; ti < ht.size(); ti++) {
+            const HostTask& h = ht[ti];
+            if (h.bound > wcap || h.region_max > scr_samples) continue;
+            uint64_t cnt = 0, T = 0;
+            bool ok = true, found = false;
+            sig.clear();
+            uint32_t k = h.op_begin;
+            for (; k < h.op_end && ok && !found; k++) {
+                const ctts_plan_op& op = h_ops[k - op0];
+                switch (op.kind) {
+                    case ctts::OP_NOP:
+                        break;
+                    case CTTS_OP_UNIT: {
+                        const uint32_t nu = ucnt[op.a];
+                        if (nu == 0) break;
+                        if (op.flags & CTTS_UNIT_AFTER_BOUNDARY) { cnt += nu; break; }
+                        if (cnt == 0 || op.b == 0) { ok = false; break; }   // joined or not is decided by the count before the region
+                        const uint32_t m = std::min(op.b, nu);
+                        if (m > cnt) { ok = false; break; }                  // the crossfade would reach back
+                        if (nu >= 200) {
+                            const uint32_t m2 = 2 * op.b < nu / 2 ? 2 * op.b : nu / 2;   // uint32 like the kernel
+                            if (m2 > cnt) { ok = false; break; }             // the pitch analysis would reach back
+                            if (2ull * m2 > cnt) T = std::max<uint64_t>(T, 2ull * m2 - cnt);
+                            if (200 > cnt) T = std::max<uint64_t>(T, 200 - cnt);
+                        }
+                        cnt += nu - m;
+                        break;
+                    }
+                    case CTTS_OP_SILENCE:
+                        cnt += op.a;
+                        break;
+                    case CTTS_OP_FADE_OUT:
+                        if (op.a > cnt) ok = false;                          // acts on samples of an earlier region
+                        break;
+                    case CTTS_OP_WORD_END:
+                        found = true;
+                        break;
+                    default:                                                 // MARK before the first WORD_END
+                        ok = false;
+                }
+                if (ok && !found) sig.append(reinterpret_cast<const char*>(&op), 12);   // kind, flags, a, b
+            }
+            if (!ok || !found || cnt == 0 || T > 0x7fffffffull) continue;
+            const uint32_t w = k - 1;
+            sig.push_back((char)(h_ops[w - op0].flags & CTTS_WE_TRIM));
+            auto it = seen.find(sig);
+            uint32_t gid;
+            if (it == seen.end()) {
+                gid = (uint32_t)groups.size();
+                seen.emplace(sig, gid);
+                groups.push_back(Group{(uint32_t)ti, 0u, ctts::NO_REGION});
+            } else {
+                gid = it->second;
+            }
+            groups[gid].count++;
+            dd[ti].w_op = w;
+            dd[ti].thresh = (uint32_t)T;
+            dd[ti].group = gid;
+        }
+    }
+    // canonical tasks: first in ticket order (an occurrence waits for a SMALLER ticket only), longest first
+    std::vector<uint32_t> canon_groups;
+    for (uint32_t gi = 0; gi < groups.size(); gi++)
+        if (groups[gi].count >= 2) canon_groups.push_back(gi);
+    std::sort(canon_groups.begin(), canon_groups.end(), [&](uint32_t a, uint32_t b) {
+        const uint64_t ba = ht[groups[a].first_task].bound, bb = ht[groups[b].first_task].bound;
+        return ba != bb ? ba > bb : a < b;
+    });
+    std::vector<unsigned long long> region_off(canon_groups.size() + 1, 0);
+    for (uint32_t c = 0; c < canon_groups.size(); c++) {
+        groups[canon_groups[c]].canon = c;
+        region_off[c + 1] = region_off[c] + up8(ht[groups[canon_groups[c]].first_task].bound) + 8;
+    }
+    if (!canon_groups.empty()) {
+        PlanAlloc al{ctx, p};
+        al.d_used = p->d_used;
+        p->d_region_store = al.dev<int16_t>(region_off.back());
+        p->d_region_off = al.dev<unsigned long long>(canon_groups.size());
+        p->d_region_state = al.dev<unsigned long long>(canon_groups.size());
+        p->d_used = al.d_used;
+        if (al.err != cudaSuccess || (p->arena && p->d_used > p->arena->d_cap))
+            return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "region store");
+        CU(ctx, cudaMemsetAsync(p->d_region_state, 0, canon_groups.size() * 8, st));
+    }
+
+    // ticket order: canonical regions, then region-major (task k of every utterance before task k+1 of any),
+    // inside a row longest first (it is the one a successor may have to wait for, and longest-first
     // balances the tail of the launch)
     ch.task_begin = p->n_tasks;
     uint32_t nt = p->n_tasks;
+    for (uint32_t c = 0; c < canon_groups.size(); c++) {
+        const uint32_t ti = groups[canon_groups[c]].first_task;
+        const HostTask& h = ht[ti];
+        ctts::RegionTask t{};
+        t.op_begin = h.op_begin - op0;
+        t.op_end = dd[ti].w_op + 1 - op0;
+        t.bound = (uint32_t)h.bound;
+        t.pred = -1;
+        t.flags = ctts::TASK_CANON;
+        t.dst_cap = (uint32_t)(region_off[c + 1] - region_off[c]);
+        t.dst_off = region_off[c];
+        t.big = 0xffffffffu;
+        t.region = c;
+        t.w_op = dd[ti].w_op - op0;
+        p->h_tasks[nt++] = t;
+    }
+    p->info.n_canon_tasks += (uint32_t)canon_groups.size();
     std::vector<int32_t> last_index(u1 - u0, -1);
     std::vector<uint32_t> row(u1 - u0);
     for (uint32_t k = 0; k < max_rows; k++) {
@@ -1081,6 +1217,17 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
                 if (p->n_big >= p->big_cap) return fail(ctx, CTTS_GPU_ERR_DEVICE, "internal: trim scratch slots");
                 t.big = p->n_big++;
             }
+            t.region = ctts::NO_REGION;
+            {
+                const Dedup& d = dd[ht_begin[ui] + k];
+                if (d.group != ctts::NO_REGION && groups[d.group].canon != ctts::NO_REGION) {
+                    t.region = groups[d.group].canon;
+                    t.thresh = d.thresh;
+                    t.w_op = d.w_op - op0;
+                    p->info.n_dedup_tasks++;
+                    p->info.dedup_bound_samples += h.bound;
+                }
+            }
             last_index[ui] = (int32_t)(nt - ch.task_begin);   // index inside this chunk's launch
             p->h_tasks[nt++] = t;
         }
@@ -1095,6 +1242,10 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
     if (ch.n_tasks)
         CU(ctx, cudaMemcpyAsync(p->d_tasks + ch.task_begin, p->h_tasks + ch.task_begin, (size_t)ch.n_tasks * sizeof(ctts::RegionTask),
                                 cudaMemcpyHostToDevice, st));
+    if (!canon_groups.empty()) {
+        // (pageable source: the copy is staged before the call returns)
+        CU(ctx, cudaMemcpyAsync(p->d_region_off, region_off.data(), canon_groups.size() * 8, cudaMemcpyHostToDevice, st));
+    }
     p->built_chunks++;
     p->info.n_tasks = p->n_tasks;
     p->info.n_global_tasks = p->n_global_tasks;
@@ -1140,6 +1291,9 @@ int launch_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, int16_t* d_pcm
     a.err = p->d_err;
     a.trim_scratch = p->d_trim;
     a.trim_scratch_words = p->trim_words;
+    a.region_store = p->d_region_store;
+    a.region_off = p->d_region_off;
+    a.region_state = p->d_region_state;
     a.chain = p->d_chain + ch.task_begin;
     a.ticket = p->d_ticket + c;
     a.epoch = p->epoch;

@@ -29,6 +29,7 @@ class RunInfo(C.Structure):
         ("halo_samples", C.c_uint32), ("threads", C.c_uint32),
         ("n_tasks", C.c_uint32), ("n_global_tasks", C.c_uint32),
         ("ctas_per_sm", C.c_uint32), ("grid", C.c_uint32),
+        ("n_canon_tasks", C.c_uint32), ("n_dedup_tasks", C.c_uint32), ("dedup_bound_samples", C.c_uint64),
     ]
 
 

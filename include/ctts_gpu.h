@@ -178,6 +178,11 @@ typedef struct ctts_gpu_run_info {
     uint32_t n_global_tasks;     /* of those: regions larger than the window, assembled in the HBM slot */
     uint32_t ctas_per_sm;        /* resident CTAs per SM of the assembly kernel */
     uint32_t grid;               /* persistent CTAs launched */
+    /* word-region deduplication: equal word regions of a batch are assembled once per launch (canonical tasks),
+     * every other occurrence copies the result and runs its own contour */
+    uint32_t n_canon_tasks;      /* distinct regions computed once */
+    uint32_t n_dedup_tasks;      /* region tasks that take their samples from one of those */
+    uint64_t dedup_bound_samples;/* sum of their upper bounds */
 } ctts_gpu_run_info;
 int ctts_gpu_plan_info(const ctts_gpu_plan* plan, ctts_gpu_run_info* info);
 

@@ -723,3 +723,40 @@ def test_packed_batch_call(H, gpu, synth_small, oracle_small, front_small, monke
 
 def small_db_bytes(H):
     return H.small_db()
+
+
+def test_region_dedup_on_and_off(H, gpu, small_db, oracle_small, front_small, monkeypatch):
+    """Word-region deduplication: equal word regions of a batch are assembled once per launch and copied by their
+    other occurrences, which resume at their own contour.  A batch full of repeated words (and of things that must
+    NOT be deduplicated: utterance starts, punctuation-only pieces, hyphens, numbers, stretched utterances) gives
+    the same PCM with the deduplication on and off, and the oracle's."""
+    prm = front_small.params()
+    words = ["casa", "mundo", "olá", "bom", "dia", "rato", "rua", "importante", "água", "trabalho"]
+    rng = np.random.default_rng(12)
+    texts = [" ".join(rng.choice(words, size=int(rng.integers(3, 14)))) + rng.choice([".", "?", "!", ",", ""]) for _ in range(40)]
+    texts += ["casa, casa; casa: casa. casa! casa?", "a casa casa-casa casa", "12 casas e 12 casas", "...", "", "casa", "casa casa"]
+    speeds = [1.0] * len(texts)
+    speeds[3] = 1.5
+    speeds[11] = 0.7
+    plan = front_small.plan(texts, speeds)
+    want = [oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))[0] for u in range(plan.n_utts)]
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("CTTS_GPU_REGION_DEDUP", mode)
+        g = gpu.GpuSynth(small_db, 0)
+        rp = g.create_plan(plan, prm)
+        info = rp.info()
+        if mode == "1":
+            assert info.n_canon_tasks >= 5 and info.n_dedup_tasks > 4 * info.n_canon_tasks, (info.n_canon_tasks, info.n_dedup_tasks)
+        else:
+            assert info.n_canon_tasks == 0 and info.n_dedup_tasks == 0
+        for _ in range(2):          # a second run of the same plan: a new epoch of the region states
+            rp.run()
+        outs[mode] = rp.utterances()
+        for u in range(plan.n_utts):
+            _assert_same(outs[mode][u], want[u], f"dedup {mode} utt {u} {texts[u][:30]!r}")
+        # the drop-in call (pieces) too
+        piece_outs = g.synth_list(plan, prm)
+        for u in range(plan.n_utts):
+            _assert_same(piece_outs[u], want[u], f"dedup {mode}, pieces, utt {u}")
+    monkeypatch.delenv("CTTS_GPU_REGION_DEDUP")

@@ -14,9 +14,7 @@
 #include <cstring>
 #include <chrono>
 #include <numeric>
-#include <string>
 #include <thread>
-#include <unordered_map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -1078,15 +1076,22 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
     struct Group { uint32_t first_task, count, canon; };
     std::vector<Group> groups;
     if (ctx->knobs.region_dedup) {
-        std::unordered_map<std::string, uint32_t> seen;
-        seen.reserve(ht.size() / 8 + 16);
-        std::string sig;
+        // open-addressing table: 64-bit hash of the signature -> group, equality checked on the ops themselves
+        size_t slots = 64;
+        while (slots < 2 * ht.size() + 16) slots *= 2;
+        std::vector<uint32_t> table(slots, ctts::NO_REGION);
+        std::vector<uint64_t> group_hash;
+        auto same_ops = [&](uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {   // ops [a0, a1) vs [b0, b1): first 12 bytes, + trim flag of the WORD_END
+            if (a1 - a0 != b1 - b0) return false;
+            for (uint32_t i = 0; i < a1 - a0; i++)
+                if (memcmp(&h_ops[a0 + i - op0], &h_ops[b0 + i - op0], 12) != 0) return false;
+            return ((h_ops[a1 - op0].flags ^ h_ops[b1 - op0].flags) & CTTS_WE_TRIM) == 0;
+        };
         for (size_t ti = 0; ti < ht.size(); ti++) {
             const HostTask& h = ht[ti];
             if (h.bound > wcap || h.region_max > scr_samples) continue;
-            uint64_t cnt = 0, T = 0;
+            uint64_t cnt = 0, T = 0, hash = 1469598103934665603ull;
             bool ok = true, found = false;
-            sig.clear();
             uint32_t k = h.op_begin;
             for (; k < h.op_end && ok && !found; k++) {
                 const ctts_plan_op& op = h_ops[k - op0];
@@ -1121,19 +1126,34 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
                     default:                                                 // MARK before the first WORD_END
                         ok = false;
                 }
-                if (ok && !found) sig.append(reinterpret_cast<const char*>(&op), 12);   // kind, flags, a, b
+                if (ok && !found) {   // kind | flags, a, b
+                    const uint32_t* wds = reinterpret_cast<const uint32_t*>(&op);
+                    hash = (hash ^ wds[0]) * 1099511628211ull;
+                    hash = (hash ^ wds[1]) * 1099511628211ull;
+                    hash = (hash ^ wds[2]) * 1099511628211ull;
+                }
             }
             if (!ok || !found || cnt == 0 || T > 0x7fffffffull) continue;
             const uint32_t w = k - 1;
-            sig.push_back((char)(h_ops[w - op0].flags & CTTS_WE_TRIM));
-            auto it = seen.find(sig);
-            uint32_t gid;
-            if (it == seen.end()) {
-                gid = (uint32_t)groups.size();
-                seen.emplace(sig, gid);
-                groups.push_back(Group{(uint32_t)ti, 0u, ctts::NO_REGION});
-            } else {
-                gid = it->second;
+            hash = (hash ^ (h_ops[w - op0].flags & CTTS_WE_TRIM)) * 1099511628211ull;
+            hash ^= hash >> 29;
+            uint32_t gid = ctts::NO_REGION;
+            for (size_t sl = hash & (slots - 1);; sl = (sl + 1) & (slots - 1)) {
+                const uint32_t g2 = table[sl];
+                if (g2 == ctts::NO_REGION) {
+                    gid = (uint32_t)groups.size();
+                    table[sl] = gid;
+                    groups.push_back(Group{(uint32_t)ti, 0u, ctts::NO_REGION});
+                    group_hash.push_back(hash);
+                    break;
+                }
+                if (group_hash[g2] == hash) {
+                    const HostTask& f = ht[groups[g2].first_task];
+                    if (same_ops(f.op_begin, dd[groups[g2].first_task].w_op, h.op_begin, w)) {
+                        gid = g2;
+                        break;
+                    }
+                }
             }
             groups[gid].count++;
             dd[ti].w_op = w;
@@ -1551,11 +1571,14 @@ int submit_piece(ctts_gpu_session* s, const ctts_batch_plan* piece, const uint64
     ctts_gpu_ctx* ctx = s->ctx;
     const uint32_t n = piece->n_utts;
     ctts_gpu_ctx::Lane& l = ctx->lane[s->submitted % ctts_gpu_ctx::kLanes];
+    const auto tsub0 = std::chrono::steady_clock::now();
     if (s->submitted - s->harvested >= (uint32_t)ctts_gpu_ctx::kLanes) harvest_one(s);   // the lane's previous piece
     if (s->error) return s->error;
+    const auto tp0 = std::chrono::steady_clock::now();
     ctts_gpu_plan* p = nullptr;
     int rc = prepare_plan(ctx, piece, &s->prm, nullptr, &l.arena, &p);
     if (rc) return rc;
+    const auto tp1 = std::chrono::steady_clock::now();
     auto bail = [&](int code) {
         drain(ctx);
         ctts_gpu_plan_destroy(p);
@@ -1612,9 +1635,15 @@ int submit_piece(ctts_gpu_session* s, const ctts_batch_plan* piece, const uint64
     if (n) {
         rc = begin_run(ctx, p);
         if (!rc) rc = build_chunk(ctx, p, 0, ctx->stream);
+        const auto tp2 = std::chrono::steady_clock::now();
         if (!rc) rc = launch_chunk(ctx, p, 0, l.d_out, ctx->stream);
         if (!rc) rc = launch_stretch(ctx, p, 0, l.d_out, ctx->stream);
         if (rc) return bail(rc);
+        if (ctx->knobs.trace) {
+            auto msf = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "  submit %u utterances at %.1f ms: waited %.2f, prepare %.2f, build %.2f, launch %.2f ms\n", n, msf(s->t0, tp0),
+                    msf(tsub0, tp0), msf(tp0, tp1), msf(tp1, tp2), msf(tp2, std::chrono::steady_clock::now()));
+        }
         cudaError_t e = cudaSuccess;
         if (packed) {
             // device prefix sum of the counts -> packed positions -> gather; the scan kernel also stores counts

@@ -32,7 +32,41 @@ ENDINGS = [".", ".", ".", "?", "?", "!", ",", ";", ""]
 MID = [",", ",", ",", ";", ":", " -", ""]
 
 
-def sentence(rng: np.random.Generator, target_chars: int = 200) -> str:
+ONSETS = "b c d f g j l m n p r s t v z ch lh nh br cr dr fr gr pr tr bl cl fl pl qu gu".split() + [""]
+NUCLEI = "a e i o u á é í ó ú ã õ ai ei oi ui au eu ou ão".split()
+CODAS = ["", "", "", "", "s", "r", "m", "l", "n"]
+
+
+class Vocabulary:
+    """`size` word types with Zipf-Mandelbrot frequencies (p ~ 1 / (rank + 2.7)): the words above first (shuffled),
+    then pronounceable pseudo-words of 1-4 syllables.  For the vocabulary-size sensitivity of anything that gains
+    from repeated words (bench.py --vocab)."""
+
+    def __init__(self, size: int, seed: int = 4321):
+        rng = np.random.default_rng(seed)
+        seen = dict.fromkeys(WORDS)
+        words = list(seen)
+        rng.shuffle(words)
+        while len(words) < size:
+            w = ""
+            for _ in range(int(rng.integers(1, 5))):
+                w += ONSETS[int(rng.integers(len(ONSETS)))] + NUCLEI[int(rng.integers(len(NUCLEI)))]
+            w += CODAS[int(rng.integers(len(CODAS)))]
+            if w not in seen:
+                seen[w] = None
+                words.append(w)
+        self.words = words[:size]
+        p = 1.0 / (np.arange(len(self.words)) + 2.7)
+        self.cdf = np.cumsum(p / p.sum())
+
+    def draw(self, rng: np.random.Generator) -> str:
+        return self.words[min(int(np.searchsorted(self.cdf, rng.uniform())), len(self.words) - 1)]
+
+
+def sentence(rng: np.random.Generator, target_chars: int = 200, vocab: Vocabulary | None = None) -> str:
+    def word() -> str:
+        return vocab.draw(rng) if vocab is not None else WORDS[int(rng.integers(len(WORDS)))]
+
     parts: list[str] = []
     length = 0
     first = True
@@ -45,9 +79,9 @@ def sentence(rng: np.random.Generator, target_chars: int = 200) -> str:
         elif u < 0.11:
             w = ABBREV[int(rng.integers(len(ABBREV)))]
         elif u < 0.13:
-            w = WORDS[int(rng.integers(len(WORDS)))] + "-" + WORDS[int(rng.integers(len(WORDS)))]
+            w = word() + "-" + word()
         else:
-            w = WORDS[int(rng.integers(len(WORDS)))]
+            w = word()
         if first:
             w = w[0].upper() + w[1:]
             first = False
@@ -64,9 +98,9 @@ def sentence(rng: np.random.Generator, target_chars: int = 200) -> str:
     return text + ENDINGS[int(rng.integers(len(ENDINGS)))]
 
 
-def batch(n: int, seed: int = 1234, target_chars: int = 200) -> list[str]:
+def batch(n: int, seed: int = 1234, target_chars: int = 200, vocab: Vocabulary | None = None) -> list[str]:
     rng = np.random.default_rng(seed)
-    return [sentence(rng, target_chars) for _ in range(n)]
+    return [sentence(rng, target_chars, vocab) for _ in range(n)]
 
 
 def mixed_speeds(n: int, seed: int = 99) -> np.ndarray:

@@ -55,13 +55,17 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (BASELINE configs[3] sharded over the ranks)")
     ap.add_argument("--strong-utts", type=int, default=4096, help="utterances of the ONE batch the strong-scaling leg shards")
+    ap.add_argument("--vocab", type=int, default=0,
+                    help="draw the words from a Zipf vocabulary of this many types instead of the round-1 word list "
+                         "(sensitivity of the word-region deduplication; the default line reports one such point itself)")
     return ap.parse_args()
 
 
 def workload(args, rank: int):
     """Synthetic batch for one rank: texts, speeds."""
     pkg = importlib.import_module("2026-simple-c-tts_b200")
-    texts = pkg.corpus.batch(args.utts, seed=1234 + 7919 * rank, target_chars=215 if args.workload == "long" else 200)
+    vocab = pkg.corpus.Vocabulary(args.vocab) if args.vocab else None
+    texts = pkg.corpus.batch(args.utts, seed=1234 + 7919 * rank, target_chars=215 if args.workload == "long" else 200, vocab=vocab)
     if args.workload == "mixed":
         speeds = pkg.corpus.mixed_speeds(args.utts, seed=99 + rank)
     else:
@@ -70,6 +74,9 @@ def workload(args, rank: int):
 
 
 def workload_name(args) -> str:
+    if args.vocab:
+        return (f"NOT a BASELINE config: {args.utts} sentences (~200 chars) per GPU, words drawn from a Zipf vocabulary of "
+                f"{args.vocab} types, workload {args.workload}")
     if args.workload == "mixed":
         return f"BASELINE configs[3]: {args.utts} synthetic sentences (~200 chars) per GPU at mixed speeds 0.5-2.0 (WSOLA)"
     if args.workload == "long":
@@ -422,25 +429,48 @@ def main() -> int:
     # ---- the same resident plan with the word-region deduplication switched off (every region assembled): reported
     #      beside `value` so that the share of the speed-up that comes from repeated words in the batch is visible
     nodedup_ms = None
+    zipf = None
     if rank == 0 and info.n_canon_tasks:
         os.environ["CTTS_GPU_REGION_DEDUP"] = "0"       # knobs are read once, by ctts_gpu_init
         g0 = gpu.GpuSynth(db, local_rank)
         os.environ.pop("CTTS_GPU_REGION_DEDUP")
         g0.set_stream(stream.cuda_stream)
-        rp0 = g0.create_plan(plan, prm)
-        for _ in range(3):
-            rp0.run(d_out.data_ptr())
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0 = max(3, min(args.steps, 10))
-        with torch.cuda.stream(stream):
-            a0.record(stream)
-            for _ in range(k0):
-                rp0.run(d_out.data_ptr())
-            a1.record(stream)
-        torch.cuda.synchronize(local_rank)
-        nodedup_ms = a0.elapsed_time(a1) / k0
-        assert np.array_equal(rp0.counts(), counts)
-        rp0.close()
+
+        def resident_ms(ctx, pl, out=None):
+            r = ctx.create_plan(pl, prm)
+            if out is None:
+                out = torch.empty(max(r.out_samples, 8), dtype=torch.int16, device=f"cuda:{local_rank}")
+            for _ in range(3):
+                r.run(out.data_ptr())
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                a0.record(stream)
+                for _ in range(k0):
+                    r.run(out.data_ptr())
+                a1.record(stream)
+            torch.cuda.synchronize(local_rank)
+            c, i = r.counts(), r.info()
+            r.close()
+            return a0.elapsed_time(a1) / k0, c, i
+
+        nodedup_ms, c0, _ = resident_ms(g0, plan, d_out)
+        assert np.array_equal(c0, counts)
+        # ---- one more point on the same axis: the same sentence generator over a Zipf vocabulary of 20 000 word types
+        #      (rank r has probability ~ 1 / (r + 2.7)): about one token in ten occurs once in the batch
+        if args.workload == "speed1" and not args.vocab and args.utts >= 1024:
+            zt = pkg.corpus.batch(args.utts, seed=1234, target_chars=200, vocab=pkg.corpus.Vocabulary(20000))
+            zplan = fr.plan(zt, np.ones(args.utts, dtype=np.float32))
+            z_ms, zc, zi = resident_ms(g, zplan)
+            z0_ms, zc0, _ = resident_ms(g0, zplan)
+            assert np.array_equal(zc, zc0)
+            z_audio = float(zc.astype(np.int64).sum()) / SAMPLE_RATE
+            zipf = {"vocabulary": 20000, "utterances": args.utts, "audio_seconds": z_audio,
+                    "ms_per_step": z_ms, "value": z_audio / (z_ms / 1e3),
+                    "ms_per_step_without": z0_ms, "value_without_region_dedup": z_audio / (z0_ms / 1e3),
+                    "region_tasks": int(zi.n_tasks), "canonical_regions": int(zi.n_canon_tasks),
+                    "tasks_served_from_them": int(zi.n_dedup_tasks),
+                    "share_of_bound_samples": float(zi.dedup_bound_samples) / max(float(zi.bound_samples), 1.0)}
         g0.close()
 
     # ---- e2e, host buffers, copies inside the timed region: (1) plan -> PCM through the drop-in call
@@ -555,7 +585,8 @@ def main() -> int:
                     "value_without_region_dedup": (audio_s / (nodedup_ms / 1e3)) if nodedup_ms else None,
                     "corpus_note": "the benchmark corpus (round-1 generator, SURVEY 8d) draws its sentences from ~190 words plus numbers "
                                    "and abbreviations, so few distinct regions serve most tasks; a batch of all-distinct words costs what "
-                                   "value_without_region_dedup says"},
+                                   "value_without_region_dedup says; zipf_vocabulary is the same generator over 20 000 word types",
+                    "zipf_vocabulary": zipf},
                 "threads_per_cta": int(info.threads),
             },
             "gpu_launches": int(info.kernel_launches) * args.steps,

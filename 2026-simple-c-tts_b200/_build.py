@@ -76,7 +76,8 @@ def build_gpu(force: bool = False, verbose: bool = False) -> str:
         subprocess.run([cc, "-O2", "-std=c99", "-ffp-contract=off", "-fPIC", "-I", INCLUDE, "-c", s, "-o", o],
                        check=True)
         objs.append(o)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    # CTTS_NVCC_EXTRA: extra nvcc flags for development builds (e.g. -DCTTS_ASM_PROF=1 for CTTS_GPU_TASK_TIMES)
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("CTTS_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + \
         ["-I", INCLUDE, "-I", d, "-o", GPU_SO] + cus + objs + ["-lcudart"]
     subprocess.run(cmd, check=True)
     return GPU_SO

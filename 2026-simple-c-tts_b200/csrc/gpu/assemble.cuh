@@ -14,6 +14,7 @@ __device__ void op_fade_out(State& s, const Smem& sm, const AsmArgs& A, uint32_t
     if (a == 0) return;
     uint32_t f = a;
     if (s.cnt < a) {
+        if (threadIdx.x == 0) sm.bcast[3] = 1u;   // the result depends on more than this task's ops (TASK_SOURCE)
         need_base(s, sm, A);
         const unsigned long long count = (unsigned long long)s.base + s.cnt;
         if (count == 0) return;
@@ -45,9 +46,38 @@ __device__ void op_silence(State& s, uint32_t n) {
     __syncthreads();
 }
 
-__device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
+// The ticket thread 0 drew before this work item started: published in bcast[1] (read by everyone once the item is
+// done), its descriptor copied into `next_task` behind the scenes.
+__device__ __forceinline__ void fetch_next(const Smem& sm, const AsmArgs& A, RegionTask* next_task, uint32_t next_ticket) {
     const int tid = threadIdx.x;
-    const RegionTask task = A.tasks[ti];
+    if (tid < 32) {
+        const uint32_t n = __shfl_sync(0xffffffffu, next_ticket, 0);
+        if (tid == 0) sm.bcast[1] = n;
+        if (tid < 4 && n < A.n_tasks)
+            cp_async16(reinterpret_cast<char*>(next_task) + 16 * tid, reinterpret_cast<const char*>(A.tasks + n) + 16 * tid);
+    }
+}
+
+// CTTS_GPU_TASK_TIMES=1: CTA time per task class.  A development aid that costs 1.5 % when compiled in, so it is
+// compiled OUT by default: build with CTTS_NVCC_EXTRA=-DCTTS_ASM_PROF=1 (see _build.py) to use it.
+#ifndef CTTS_ASM_PROF
+#define CTTS_ASM_PROF 0
+#endif
+__device__ __forceinline__ void task_time(const Smem& sm, const AsmArgs& A, int cls) {
+    if (CTTS_ASM_PROF && A.prof && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicAdd(A.prof + 2 * cls, (unsigned long long)((uint32_t)t - sm.bcast[5]));
+        atomicAdd(A.prof + 2 * cls + 1, 1ull);
+    }
+}
+
+// `task` lives in shared memory (fields are read where they are used: no registers held over the op loop); `next_ticket`
+// is the ticket thread 0 drew before this task started: once the task's own first loads are on their way it is
+// published in bcast[1] and its descriptor is copied into `next_task` behind the scenes.
+__device__ __forceinline__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti, const RegionTask& task, RegionTask* next_task,
+                         uint32_t next_ticket) {
+    const int tid = threadIdx.x;
     State s;
     s.dst = ((task.flags & TASK_TO_PRE) ? A.dst_pre : A.dst_final) + task.dst_off;
     s.dst_cap = task.dst_cap;
@@ -58,6 +88,14 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
     s.have_base = task.pred < 0;
     s.base = 0;
     s.in_smem = true;
+    if (tid == 0) {
+        sm.bcast[3] = 0u;                         // reached-back flag, read after the op loop: barriers in between
+        if (CTTS_ASM_PROF && A.prof) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            sm.bcast[5] = (uint32_t)t;
+        }
+    }
     s.w = sm.win;
     s.cap = A.wcap;
     // ---- word-region deduplication.  What a word region holds right before its contour (units gathered, joined,
@@ -66,6 +104,14 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
     // region's start (the plan compiler proves that).  Equal regions of a batch are therefore computed ONCE per launch
     // -- the canonical tasks, first in ticket order, assembled as if the utterance were long -- and every other
     // occurrence copies the result and resumes at its own contour (whose factors differ from word to word).
+    // Second level: tasks that are equal as a whole (same canonical region, same WORD_END bit for bit, nothing but
+    // fade-outs / pauses / marks behind it).  The first of them in ticket order (TASK_SOURCE) stores what it flushes in
+    // the region store too, the others (TASK_REUSE) copy that and run nothing.
+    // the task's ops, asynchronously (an op fetched from HBM per step would stall the whole CTA)
+    {
+        const uint32_t n_pref = min(task.op_end - task.op_begin, TASK_OPS_SMEM);
+        if ((uint32_t)tid < 2 * n_pref) cp_async16(sm.ops + tid, reinterpret_cast<const int4*>(A.ops + task.op_begin) + tid);
+    }
     const bool canon = (task.flags & TASK_CANON) != 0;
     uint32_t k_first = task.op_begin;
     bool resumed = false;
@@ -74,29 +120,48 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
         s.have_base = true;
         s.base = CANON_BASE;
     } else if (task.region != NO_REGION) {
-        need_base(s, sm, A);
-        if (s.base >= task.thresh) {
-            if (tid == 0) {   // the canonical task has a smaller ticket: it is running or done
-                const unsigned long long* p = A.region_state + task.region;
-                unsigned long long v;
+        // One round trip for everything this task waits for: lane 0 the predecessor's chain word, lane 1 the
+        // canonical region's state, lane 2 the shared whole task's (their producers hold smaller tickets: running or
+        // done).  bcast[0] = base, bcast[2] / bcast[4] = lengths (NO_REGION: the producer gave up on it).
+        if (tid < 3) {
+            const unsigned long long* p = nullptr;
+            if (tid == 0 && !s.have_base) p = A.chain + s.pred;
+            if (tid == 1) p = A.region_state + task.region;
+            if (tid == 2 && (task.flags & TASK_REUSE)) p = A.region_state + task.whole;
+            unsigned long long v = NO_REGION;
+            if (p) {
                 unsigned ns = 20;
                 while ((uint32_t)((v = ld_acquire_u64(p)) >> 32) != A.epoch) {
                     __nanosleep(ns);
                     if (ns < 640) ns *= 2;
                 }
-                sm.bcast[2] = (uint32_t)v;
             }
-            __syncthreads();
-            const uint32_t len = sm.bcast[2];
-            __syncthreads();
-            if (len != NO_REGION && len <= s.cap) {
-                const int4* src = reinterpret_cast<const int4*>(A.region_store + __ldg(A.region_off + task.region));
-                int4* dstw = reinterpret_cast<int4*>(sm.win);
-                for (uint32_t v = tid; v < (len + 7) >> 3; v += ASM_THREADS) dstw[v] = __ldg(src + v);
-                s.cnt = len;
+            sm.bcast[2 * tid] = (uint32_t)v;
+        }
+        __syncthreads();
+        if (!s.have_base) {
+            s.base = sm.bcast[0];
+            s.have_base = true;
+        }
+        if (s.base >= task.thresh) {
+            const uint32_t len_whole = sm.bcast[4], len_region = sm.bcast[2];
+            uint32_t len = NO_REGION;
+            unsigned long long at = 0;
+            if (len_whole != NO_REGION && len_whole <= s.cap) {
+                len = len_whole;
+                at = 8ull * task.whole_at;
+                k_first = task.op_end;
+            } else if (len_region != NO_REGION && len_region <= s.cap) {
+                len = len_region;
+                at = 8ull * task.region_at;
                 k_first = task.w_op;
                 resumed = true;
-                __syncthreads();
+            }
+            if (len != NO_REGION) {   // region store -> window (written by another CTA during this launch: L2, not the read-only path)
+                const int4* src = reinterpret_cast<const int4*>(A.region_store + at);
+                int4* dstw = reinterpret_cast<int4*>(sm.win);
+                for (uint32_t v = tid; v < (len + 7) >> 3; v += ASM_THREADS) cp_async16(dstw + v, src + v);
+                s.cnt = len;
             }
         }
     }
@@ -107,15 +172,10 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
         s.w = s.dst + s.base;
         s.cap = s.dst_cap > s.base ? s.dst_cap - s.base : 0u;
         __threadfence();
-        __syncthreads();
     }
-
-    // the task's ops in one coalesced load (an op fetched from HBM per step would stall the whole CTA)
-    {
-        const uint32_t n_pref = min(task.op_end - task.op_begin, TASK_OPS_SMEM);
-        if ((uint32_t)tid < 2 * n_pref) sm.ops[tid] = __ldg(reinterpret_cast<const int4*>(A.ops + task.op_begin) + tid);
-        __syncthreads();
-    }
+    cp_async_wait_all();
+    __syncthreads();
+    fetch_next(sm, A, next_task, next_ticket);
     for (uint32_t k = k_first; k < task.op_end && !s.err; k++) {
         ctts_plan_op op;
         {
@@ -144,10 +204,20 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
             case CTTS_OP_FADE_OUT:
                 op_fade_out(s, sm, A, op.a);
                 break;
-            case CTTS_OP_WORD_END:
+            case CTTS_OP_WORD_END: {
+                unsigned long long t0 = 0;
+                const bool timed = CTTS_ASM_PROF && A.prof && !s.in_smem;
+                if (timed && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
                 if (canon) op_word_end(s, sm, A, task.big, op, true, false);              // stops in front of the contour
                 else op_word_end(s, sm, A, task.big, op, !(resumed && k == task.w_op), true);
+                if (timed && tid == 0) {
+                    unsigned long long t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    atomicAdd(A.prof + 10, t1 - t0);
+                    atomicAdd(A.prof + 11, 1ull);
+                }
                 break;
+            }
             case CTTS_OP_MARK:   // word_start_sample = buf.count, ctts.c:3723, :3765
                 s.word_start = s.cnt;
                 break;
@@ -165,10 +235,21 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
             int4* d = reinterpret_cast<int4*>(s.dst);
             for (uint32_t v = tid; v < (s.cnt + 7) >> 3; v += ASM_THREADS) d[v] = srcw[v];
         }
-        __threadfence();
         __syncthreads();
         if (tid == 0) st_release_u64(A.region_state + task.region, ((unsigned long long)A.epoch << 32) | (ok ? s.cnt : NO_REGION));
+        task_time(sm, A, 0);
         return;
+    }
+    if (task.flags & TASK_SOURCE) {
+        // ---- what this task appends goes to the region store as well, unless it depends on more than the task's ops
+        const bool ok = resumed && sm.bcast[3] == 0u && !s.err && s.in_smem && s.cnt <= task.bound;
+        if (ok) {
+            const int4* srcw = reinterpret_cast<const int4*>(sm.win);
+            int4* d = reinterpret_cast<int4*>(A.region_store + 8ull * task.whole_at);
+            for (uint32_t v = tid; v < (s.cnt + 7) >> 3; v += ASM_THREADS) d[v] = srcw[v];
+        }
+        __syncthreads();   // the CTA's stores happen before thread 0's release (barrier), the release is cumulative
+        if (tid == 0) st_release_u64(A.region_state + task.whole, ((unsigned long long)A.epoch << 32) | (ok ? s.cnt : NO_REGION));
     }
     // ---- publish: the region's final position is base, known from the predecessor
     need_base(s, sm, A);
@@ -177,7 +258,6 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
         if ((unsigned long long)s.base + s.cnt > s.dst_cap) s.err = s.err ? s.err : ERR_SLOT_OVERFLOW;
         else flush_window(s, sm, 0, s.cnt);
     }
-    __threadfence();
     __syncthreads();
     if (tid == 0) {
         const uint32_t total = s.base + s.cnt;
@@ -188,6 +268,7 @@ __device__ void run_task(const Smem& sm, const AsmArgs& A, uint32_t ti) {
         }
         st_release_u64(A.chain + ti, ((unsigned long long)A.epoch << 32) | total);
     }
+    task_time(sm, A, k_first == task.op_end && task.op_end != task.op_begin ? 1 : resumed ? 2 : (task.flags & TASK_GLOBAL) || !s.in_smem ? 4 : 3);
 }
 
 __global__ void __launch_bounds__(ASM_THREADS, 3) assemble_kernel(const AsmArgs A) {
@@ -210,14 +291,25 @@ __global__ void __launch_bounds__(ASM_THREADS, 3) assemble_kernel(const AsmArgs 
         sm.nrm2[i] = __ldg(A.tab.hann256 + i + PITCH_FRAME / 2) + __ldg(A.tab.hann256 + i);
     __syncthreads();
 
-    // persistent CTAs: tasks are taken in ticket order (see the header comment)
-    for (;;) {
-        if (tid == 0) sm.bcast[1] = atomicAdd(A.ticket, 1u);
+    // persistent CTAs: tasks are taken in ticket order (see the header comment), one ticket AHEAD: the atomic and the
+    // descriptor fetch of the next task overlap the running one.  (Still deadlock-free: the smallest unfinished
+    // ticket is always running -- its holder has no smaller ticket left.)
+    RegionTask* tbuf = reinterpret_cast<RegionTask*>(smem_raw + SMEM_TASK);
+    if (tid == 0) sm.bcast[1] = atomicAdd(A.ticket, 1u);
+    __syncthreads();
+    uint32_t ti = sm.bcast[1];
+    if (tid < 4 && ti < A.n_tasks)
+        cp_async16(reinterpret_cast<char*>(tbuf) + 16 * tid, reinterpret_cast<const char*>(A.tasks + ti) + 16 * tid);
+    uint32_t buf = 0;
+    while (ti < A.n_tasks) {
+        uint32_t next_ticket = 0;
+        if (tid == 0) next_ticket = atomicAdd(A.ticket, 1u);   // consumed inside run_task, a few loads later
+        cp_async_wait_all();
         __syncthreads();
-        const uint32_t ti = sm.bcast[1];
+        run_task(sm, A, ti, tbuf[buf], tbuf + (buf ^ 1u), next_ticket);
         __syncthreads();
-        if (ti >= A.n_tasks) break;
-        run_task(sm, A, ti);
+        ti = sm.bcast[1];
+        buf ^= 1u;
     }
 }
 

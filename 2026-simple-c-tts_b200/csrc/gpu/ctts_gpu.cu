@@ -52,7 +52,10 @@ struct Knobs {
     int ctas_per_sm = 3;              // CTTS_GPU_CTAS_PER_SM: occupancy the assembly window is sized for
     int window = 0;                   // CTTS_GPU_WINDOW: shared window in samples (tests: force the HBM-window path)
     uint64_t chunk_samples = 128ull << 20;   // CTTS_GPU_CHUNK_SAMPLES: output samples per launch of ctts_gpu_synth_batch
-    bool region_dedup = true;         // CTTS_GPU_REGION_DEDUP=0: assemble every word region of a batch, equal ones too
+    bool task_times = false;          // CTTS_GPU_TASK_TIMES=1: resident plans print the time their CTAs spent per task class
+                                      // (only in a library built with -DCTTS_ASM_PROF=1)
+    int region_dedup = 2;             // CTTS_GPU_REGION_DEDUP=0: assemble every word region of a batch, equal ones too;
+                                      // 1: share equal regions up to their contour; 2: equal whole tasks as well
     bool wsola_speculate = true;      // CTTS_GPU_WSOLA_SPECULATE=0: walk every WSOLA chain frame by frame
     uint32_t wsola_force_bad = 0;     // CTTS_GPU_WSOLA_FORCE_BAD=N: report every N-th frame as unverified (tests of the repair path)
 
@@ -67,7 +70,8 @@ struct Knobs {
         ctas_per_sm = (int)std::max(1ll, std::min(8ll, num("CTTS_GPU_CTAS_PER_SM", 3)));
         window = (int)std::max(0ll, num("CTTS_GPU_WINDOW", 0));
         chunk_samples = (uint64_t)std::max(1ll, num("CTTS_GPU_CHUNK_SAMPLES", 128ll << 20));
-        region_dedup = num("CTTS_GPU_REGION_DEDUP", 1) != 0;
+        region_dedup = (int)num("CTTS_GPU_REGION_DEDUP", 2);
+        task_times = num("CTTS_GPU_TASK_TIMES", 0) != 0;
         wsola_speculate = num("CTTS_GPU_WSOLA_SPECULATE", 1) != 0;
         wsola_force_bad = (uint32_t)std::max(0ll, num("CTTS_GPU_WSOLA_FORCE_BAD", 0));
     }
@@ -165,8 +169,8 @@ struct ctts_gpu_plan {
     ctts::RegionTask* d_tasks = nullptr;
     unsigned long long* d_chain = nullptr;
     uint32_t* d_ticket = nullptr;   // one per chunk
+    unsigned long long* d_prof = nullptr;   // CTTS_GPU_TASK_TIMES: per task class {ns, tasks}
     int16_t* d_region_store = nullptr;              // canonical word regions (see run_task in assemble.cuh)
-    unsigned long long* d_region_off = nullptr;
     unsigned long long* d_region_state = nullptr;
     size_t d_used = 0;              // arena mode: device bytes taken by prepare_plan (build_chunk continues from here)
     std::vector<PlanChunk> chunks;
@@ -545,6 +549,20 @@ void ctts_gpu_plan_destroy(ctts_gpu_plan* p) {
         cudaSetDevice(p->ctx->device);
         cudaStreamSynchronize(p->ctx->stream);
     }
+    if (p->d_prof) {
+        unsigned long long h[16];
+        if (cudaMemcpy(h, p->d_prof, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            static const char* const names[5] = {"canonical region", "copied whole", "resumed at the contour", "assembled in the window", "assembled in HBM"};
+            unsigned long long tot = 0;
+            for (int i = 0; i < 5; i++) tot += h[2 * i];
+            fprintf(stderr, "ctts_gpu: CTA time per task class, all launches of this plan (%.1f ms of CTA time)\n", tot * 1e-6);
+            for (int i = 0; i < 5; i++)
+                if (h[2 * i + 1])
+                    fprintf(stderr, "  %-26s %9llu tasks  %6.2f %% of the time  %7.2f us per task\n", names[i], h[2 * i + 1],
+                            100.0 * h[2 * i] / (tot ? tot : 1), h[2 * i] * 1e-3 / h[2 * i + 1]);
+            if (h[11]) fprintf(stderr, "  (WORD_END ops inside HBM tasks: %llu, %.2f us each, %.2f %% of the time)\n", h[11], h[10] * 1e-3 / h[11], 100.0 * h[10] / (tot ? tot : 1));
+        }
+    }
     for (void* d : p->owned) cudaFree(d);
     cudaFree(p->d_out_owned);
     delete p;
@@ -858,9 +876,10 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
     const size_t tasks_cap = (size_t)sc.n_regions + (size_t)sc.n_regions / 2 + 2;
     uint64_t pre_sum = 0;
     for (uint32_t u = 0; u < n; u++) pre_sum += pre[u];
-    // region store: the canonical regions' slots (<= half of all region samples) + their tables
-    const size_t region_bytes = PlanAlloc::up256((pre_sum / 2 + 16 * (sc.n_regions + 1)) * sizeof(int16_t)) +
-                                2 * PlanAlloc::up256((sc.n_regions / 2 + 2) * 8);
+    // region store: the canonical regions' slots and the shared whole tasks' (each <= half of all region samples,
+    // a slot per two tasks at most) + their tables
+    const size_t region_bytes = PlanAlloc::up256((pre_sum + 16 * (sc.n_regions + 2)) * sizeof(int16_t)) +
+                                2 * PlanAlloc::up256((sc.n_regions + 2) * 8);
     const size_t tasks_bytes = tasks_cap * sizeof(ctts::RegionTask);
     if (arena) {
         // device side: ops, tasks, chain, tickets, counts, pre_counts, err (+ the stretch buffers)
@@ -887,6 +906,10 @@ int prepare_plan(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, const ctts_asse
     p->d_tasks = al.dev<ctts::RegionTask>(tasks_cap);
     p->d_chain = al.dev<unsigned long long>(tasks_cap);
     p->d_ticket = al.dev<uint32_t>(n_chunks);
+    if (ctx->knobs.task_times && !arena) {
+        p->d_prof = al.dev<unsigned long long>(16);
+        if (p->d_prof) cudaMemset(p->d_prof, 0, 16 * 8);
+    }
     p->d_counts = al.dev<uint32_t>(n);
     p->d_pre_counts = al.dev<uint32_t>(n);
     p->d_err = al.dev<uint32_t>(n);
@@ -1071,7 +1094,7 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
     //     the device: the first region or two of an utterance usually assemble themselves).
     // Eligible tasks with equal ops (kind, flags, unit / samples, crossfade; the trim flag of the WORD_END) form a
     // group; a group of two or more gets a canonical task that computes the region once per launch.
-    struct Dedup { uint32_t w_op = 0, thresh = 0, group = ctts::NO_REGION; };
+    struct Dedup { uint32_t w_op = 0, thresh = 0, group = ctts::NO_REGION, whole = ctts::NO_REGION; };
     std::vector<Dedup> dd(ht.size());
     struct Group { uint32_t first_task, count, canon; };
     std::vector<Group> groups;
@@ -1087,9 +1110,10 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
                 if (memcmp(&h_ops[a0 + i - op0], &h_ops[b0 + i - op0], 12) != 0) return false;
             return ((h_ops[a1 - op0].flags ^ h_ops[b1 - op0].flags) & CTTS_WE_TRIM) == 0;
         };
+        uint64_t why[4] = {0, 0, 0, 0}, why_bound[4] = {0, 0, 0, 0};   // trace: too big, reaches back / no WORD_END, (unused), eligible
         for (size_t ti = 0; ti < ht.size(); ti++) {
             const HostTask& h = ht[ti];
-            if (h.bound > wcap || h.region_max > scr_samples) continue;
+            if (h.bound > wcap || h.region_max > scr_samples) { why[0]++; why_bound[0] += h.bound; continue; }
             uint64_t cnt = 0, T = 0, hash = 1469598103934665603ull;
             bool ok = true, found = false;
             uint32_t k = h.op_begin;
@@ -1133,7 +1157,9 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
                     hash = (hash ^ wds[2]) * 1099511628211ull;
                 }
             }
-            if (!ok || !found || cnt == 0 || T > 0x7fffffffull) continue;
+            if (!ok || !found || cnt == 0 || T > 0x7fffffffull) { why[1]++; why_bound[1] += h.bound; continue; }
+            why[3]++;
+            why_bound[3] += h.bound;
             const uint32_t w = k - 1;
             hash = (hash ^ (h_ops[w - op0].flags & CTTS_WE_TRIM)) * 1099511628211ull;
             hash ^= hash >> 29;
@@ -1160,6 +1186,20 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
             dd[ti].thresh = (uint32_t)T;
             dd[ti].group = gid;
         }
+        if (ctx->knobs.trace) {
+            uint64_t single = 0, single_bound = 0, first = 0, first_bound = 0;
+            for (uint32_t ui = 0; ui < u1 - u0; ui++)
+                for (uint32_t ti = ht_begin[ui]; ti < ht_begin[ui + 1]; ti++) {
+                    if (dd[ti].group == ctts::NO_REGION) continue;
+                    if (groups[dd[ti].group].count < 2) { single++; single_bound += ht[ti].bound; }
+                    else if (ti == ht_begin[ui] && dd[ti].thresh) { first++; first_bound += ht[ti].bound; }
+                }
+            fprintf(stderr, "ctts_gpu: region dedup, %zu tasks: too big %llu (%llu samples), not a function of their ops %llu (%llu), "
+                            "eligible %llu (%llu) of which unique %llu (%llu), first of an utterance with clamps %llu (%llu)\n",
+                    ht.size(), (unsigned long long)why[0], (unsigned long long)why_bound[0], (unsigned long long)why[1],
+                    (unsigned long long)why_bound[1], (unsigned long long)why[3], (unsigned long long)why_bound[3],
+                    (unsigned long long)single, (unsigned long long)single_bound, (unsigned long long)first, (unsigned long long)first_bound);
+        }
     }
     // canonical tasks: first in ticket order (an occurrence waits for a SMALLER ticket only), longest first
     std::vector<uint32_t> canon_groups;
@@ -1169,26 +1209,142 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
         const uint64_t ba = ht[groups[a].first_task].bound, bb = ht[groups[b].first_task].bound;
         return ba != bb ? ba > bb : a < b;
     });
-    std::vector<unsigned long long> region_off(canon_groups.size() + 1, 0);
-    for (uint32_t c = 0; c < canon_groups.size(); c++) {
-        groups[canon_groups[c]].canon = c;
-        region_off[c + 1] = region_off[c] + up8(ht[groups[canon_groups[c]].first_task].bound) + 8;
-    }
-    if (!canon_groups.empty()) {
-        PlanAlloc al{ctx, p};
-        al.d_used = p->d_used;
-        p->d_region_store = al.dev<int16_t>(region_off.back());
-        p->d_region_off = al.dev<unsigned long long>(canon_groups.size());
-        p->d_region_state = al.dev<unsigned long long>(canon_groups.size());
-        p->d_used = al.d_used;
-        if (al.err != cudaSuccess || (p->arena && p->d_used > p->arena->d_cap))
-            return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "region store");
-        CU(ctx, cudaMemsetAsync(p->d_region_state, 0, canon_groups.size() * 8, st));
+    const uint32_t n_canon = (uint32_t)canon_groups.size();
+    for (uint32_t c = 0; c < n_canon; c++) groups[canon_groups[c]].canon = c;
+
+    // ---- second level: WHOLE tasks that are equal.  A task that resumes from a canonical region and then runs only
+    // its WORD_END (trim flag, contour factors, energy ramp -- compared bit for bit) and fade-outs / pauses / marks
+    // produces samples that depend on its ops alone (a fade-out that finds fewer samples than it wants reaches back:
+    // seen on the device, the result is then not shared).  The first such task in ticket order -- the SOURCE -- also
+    // stores what it flushes into the region store; the others (REUSE) copy it from there and run nothing.
+    // Row 0 (the utterance is empty when the task starts) can only take part when thresh == 0.
+    struct Whole { uint32_t first_task, count, store, row; };
+    std::vector<Whole> wholes;
+    if (n_canon && ctx->knobs.region_dedup >= 2) {
+        size_t slots = 64;
+        while (slots < 2 * ht.size() + 16) slots *= 2;
+        std::vector<uint32_t> table(slots, ctts::NO_REGION);
+        std::vector<uint64_t> whole_hash;
+        auto same_tail = [&](size_t ta, size_t tb) {   // the WORD_END in full, the ops behind it like same_ops
+            const HostTask& a = ht[ta];
+            const HostTask& b = ht[tb];
+            if (a.op_end - dd[ta].w_op != b.op_end - dd[tb].w_op) return false;
+            if (memcmp(&h_ops[dd[ta].w_op - op0], &h_ops[dd[tb].w_op - op0], sizeof(ctts_plan_op)) != 0) return false;
+            for (uint32_t i = 1; i < a.op_end - dd[ta].w_op; i++)
+                if (memcmp(&h_ops[dd[ta].w_op + i - op0], &h_ops[dd[tb].w_op + i - op0], 12) != 0) return false;
+            return true;
+        };
+        for (uint32_t ui = 0; ui < u1 - u0; ui++) {
+            for (uint32_t ti = ht_begin[ui]; ti < ht_begin[ui + 1]; ti++) {
+                const Dedup& d = dd[ti];
+                if (d.group == ctts::NO_REGION || groups[d.group].canon == ctts::NO_REGION) continue;
+                if (ti == ht_begin[ui] && d.thresh != 0) continue;
+                const HostTask& h = ht[ti];
+                uint64_t hash = 1469598103934665603ull ^ d.group;
+                bool ok = true;
+                for (uint32_t k = d.w_op; k < h.op_end && ok; k++) {
+                    const ctts_plan_op& op = h_ops[k - op0];
+                    const uint32_t* wds = reinterpret_cast<const uint32_t*>(&op);
+                    if (k == d.w_op) {
+                        for (int i = 0; i < 8; i++) hash = (hash ^ wds[i]) * 1099511628211ull;
+                        continue;
+                    }
+                    if (op.kind != ctts::OP_NOP && op.kind != CTTS_OP_FADE_OUT && op.kind != CTTS_OP_SILENCE && op.kind != CTTS_OP_MARK) ok = false;
+                    for (int i = 0; i < 3; i++) hash = (hash ^ wds[i]) * 1099511628211ull;
+                }
+                if (!ok) continue;
+                hash ^= hash >> 29;
+                uint32_t wid = ctts::NO_REGION;
+                for (size_t sl = hash & (slots - 1);; sl = (sl + 1) & (slots - 1)) {
+                    const uint32_t w2 = table[sl];
+                    if (w2 == ctts::NO_REGION) {
+                        wid = (uint32_t)wholes.size();
+                        table[sl] = wid;
+                        wholes.push_back(Whole{ti, 0u, ctts::NO_REGION, 0u});
+                        whole_hash.push_back(hash);
+                        break;
+                    }
+                    if (whole_hash[w2] == hash && dd[wholes[w2].first_task].group == d.group && same_tail(wholes[w2].first_task, ti)) {
+                        wid = w2;
+                        break;
+                    }
+                }
+                wholes[wid].count++;
+                dd[ti].whole = wid;
+            }
+        }
     }
 
     // ticket order: canonical regions, then region-major (task k of every utterance before task k+1 of any),
     // inside a row longest first (it is the one a successor may have to wait for, and longest-first
-    // balances the tail of the launch)
+    // balances the tail of the launch); tasks that copy a whole task's samples are short and all latency: those whose
+    // source sits in an earlier row are spread evenly over the row (an SM then always has contours to issue while a
+    // copy waits for memory), those whose source is in the same row close it (and so run well after it)
+    std::vector<uint32_t> order;              // ht indices in ticket order
+    std::vector<uint32_t> ht_ui(ht.size());
+    for (uint32_t ui = 0; ui < u1 - u0; ui++)
+        for (uint32_t ti = ht_begin[ui]; ti < ht_begin[ui + 1]; ti++) ht_ui[ti] = ui;
+    order.reserve(ht.size());
+    std::vector<uint8_t> is_reuse(ht.size(), 0);
+    uint32_t n_sources = 0;
+    {
+        std::vector<uint32_t> row(u1 - u0), tail, kept, early;
+        for (uint32_t k = 0; k < max_rows; k++) {
+            uint32_t m = 0;
+            for (uint32_t i = 0; i < u1 - u0; i++)
+                if (k < ht_begin[i + 1] - ht_begin[i]) row[m++] = i;
+            std::sort(row.begin(), row.begin() + m, [&](uint32_t a, uint32_t b) {
+                const uint64_t ba = ht[ht_begin[a] + k].bound, bb = ht[ht_begin[b] + k].bound;
+                return ba != bb ? ba > bb : a < b;
+            });
+            tail.clear();
+            kept.clear();
+            early.clear();
+            for (uint32_t i = 0; i < m; i++) {
+                const uint32_t ti = ht_begin[row[i]] + k;
+                const uint32_t w = dd[ti].whole;
+                if (w != ctts::NO_REGION && wholes[w].count >= 2) {
+                    if (wholes[w].store == ctts::NO_REGION) {
+                        wholes[w].store = n_canon + n_sources++;
+                        wholes[w].first_task = ti;     // the source
+                        wholes[w].row = k;
+                    } else {
+                        is_reuse[ti] = 1;
+                        (wholes[w].row < k ? early : tail).push_back(row[i]);
+                        continue;
+                    }
+                }
+                kept.push_back(row[i]);
+            }
+            size_t ie = 0;
+            for (size_t i = 0; i < kept.size(); i++) {
+                order.push_back(ht_begin[kept[i]] + k);
+                for (const size_t want = (i + 1) * early.size() / kept.size(); ie < want; ie++) order.push_back(ht_begin[early[ie]] + k);
+            }
+            for (; ie < early.size(); ie++) order.push_back(ht_begin[early[ie]] + k);
+            for (uint32_t ui : tail) order.push_back(ht_begin[ui] + k);
+        }
+    }
+
+    const uint32_t n_store = n_canon + n_sources;
+    std::vector<unsigned long long> region_off(n_store + 1, 0);
+    for (uint32_t c = 0; c < n_canon; c++)
+        region_off[c + 1] = up8(ht[groups[canon_groups[c]].first_task].bound) + 8;
+    for (const Whole& w : wholes)
+        if (w.store != ctts::NO_REGION) region_off[w.store + 1] = up8(ht[w.first_task].bound) + 8;
+    for (uint32_t c = 0; c < n_store; c++) region_off[c + 1] += region_off[c];
+    if (region_off.back() >> 3 > 0xffffffffull) return fail(ctx, CTTS_GPU_ERR_INVALID_ARG, "region store larger than 2^35 samples");
+    if (n_store) {
+        PlanAlloc al{ctx, p};
+        al.d_used = p->d_used;
+        p->d_region_store = al.dev<int16_t>(region_off.back());
+        p->d_region_state = al.dev<unsigned long long>(n_store);
+        p->d_used = al.d_used;
+        if (al.err != cudaSuccess || (p->arena && p->d_used > p->arena->d_cap))
+            return fail(ctx, CTTS_GPU_ERR_OUT_OF_MEMORY, "region store");
+        CU(ctx, cudaMemsetAsync(p->d_region_state, 0, (size_t)n_store * 8, st));
+    }
+
     ch.task_begin = p->n_tasks;
     uint32_t nt = p->n_tasks;
     for (uint32_t c = 0; c < canon_groups.size(); c++) {
@@ -1204,54 +1360,65 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
         t.dst_off = region_off[c];
         t.big = 0xffffffffu;
         t.region = c;
+        t.whole = ctts::NO_REGION;
         t.w_op = dd[ti].w_op - op0;
         p->h_tasks[nt++] = t;
     }
     p->info.n_canon_tasks += (uint32_t)canon_groups.size();
     std::vector<int32_t> last_index(u1 - u0, -1);
-    std::vector<uint32_t> row(u1 - u0);
-    for (uint32_t k = 0; k < max_rows; k++) {
-        uint32_t m = 0;
-        for (uint32_t i = 0; i < u1 - u0; i++)
-            if (k < ht_begin[i + 1] - ht_begin[i]) row[m++] = i;
-        std::sort(row.begin(), row.begin() + m, [&](uint32_t a, uint32_t b) {
-            const uint64_t ba = ht[ht_begin[a] + k].bound, bb = ht[ht_begin[b] + k].bound;
-            return ba != bb ? ba > bb : a < b;
-        });
-        for (uint32_t i = 0; i < m; i++) {
-            const uint32_t ui = row[i], u = u0 + ui;
-            const HostTask& h = ht[ht_begin[ui] + k];
-            ctts::RegionTask t{};
-            t.utt = u;
-            t.op_begin = h.op_begin - op0;
-            t.op_end = h.op_end - op0;
-            t.bound = (uint32_t)std::min<uint64_t>(h.bound, 0xffffffffull);
-            t.pred = last_index[ui];
-            const bool stretched = p->pre_off[u] != ~0ull;
-            t.flags = (k + 1 == ht_begin[ui + 1] - ht_begin[ui] ? (uint32_t)ctts::TASK_LAST : 0u) | (stretched ? (uint32_t)ctts::TASK_TO_PRE : 0u);
-            if (h.bound > wcap) { t.flags |= ctts::TASK_GLOBAL; p->n_global_tasks++; }
-            t.dst_cap = stretched ? (uint32_t)p->pre_cap[u] : (uint32_t)(p->offsets[u + 1] - p->offsets[u]);
-            t.dst_off = stretched ? p->pre_off[u] : p->offsets[u];
-            t.big = 0xffffffffu;
-            if (h.region_max > scr_samples) {
-                if (p->n_big >= p->big_cap) return fail(ctx, CTTS_GPU_ERR_DEVICE, "internal: trim scratch slots");
-                t.big = p->n_big++;
-            }
-            t.region = ctts::NO_REGION;
-            {
-                const Dedup& d = dd[ht_begin[ui] + k];
-                if (d.group != ctts::NO_REGION && groups[d.group].canon != ctts::NO_REGION) {
-                    t.region = groups[d.group].canon;
-                    t.thresh = d.thresh;
-                    t.w_op = d.w_op - op0;
-                    p->info.n_dedup_tasks++;
-                    p->info.dedup_bound_samples += h.bound;
+    int build_rc = CTTS_GPU_OK;
+    auto make_task = [&](uint32_t hti) {
+        const uint32_t ui = ht_ui[hti], u = u0 + ui;
+        const uint32_t k = hti - ht_begin[ui];
+        const HostTask& h = ht[hti];
+        ctts::RegionTask t{};
+        t.utt = u;
+        t.op_begin = h.op_begin - op0;
+        t.op_end = h.op_end - op0;
+        t.bound = (uint32_t)std::min<uint64_t>(h.bound, 0xffffffffull);
+        t.pred = last_index[ui];
+        const bool stretched = p->pre_off[u] != ~0ull;
+        t.flags = (k + 1 == ht_begin[ui + 1] - ht_begin[ui] ? (uint32_t)ctts::TASK_LAST : 0u) | (stretched ? (uint32_t)ctts::TASK_TO_PRE : 0u);
+        if (h.bound > wcap) { t.flags |= ctts::TASK_GLOBAL; p->n_global_tasks++; }
+        t.dst_cap = stretched ? (uint32_t)p->pre_cap[u] : (uint32_t)(p->offsets[u + 1] - p->offsets[u]);
+        t.dst_off = stretched ? p->pre_off[u] : p->offsets[u];
+        t.big = 0xffffffffu;
+        if (h.region_max > scr_samples) {
+            if (p->n_big >= p->big_cap) build_rc = fail(ctx, CTTS_GPU_ERR_DEVICE, "internal: trim scratch slots");
+            else t.big = p->n_big++;
+        }
+        t.region = ctts::NO_REGION;
+        t.whole = ctts::NO_REGION;
+        const Dedup& d = dd[hti];
+        // (a first task whose clamps can bind never meets its threshold: it assembles itself)
+        if (d.group != ctts::NO_REGION && groups[d.group].canon != ctts::NO_REGION && (k > 0 || d.thresh == 0)) {
+            t.region = groups[d.group].canon;
+            t.region_at = (uint32_t)(region_off[t.region] >> 3);
+            t.thresh = d.thresh;
+            t.w_op = d.w_op - op0;
+            p->info.n_dedup_tasks++;
+            p->info.dedup_bound_samples += h.bound;
+            if (d.whole != ctts::NO_REGION && wholes[d.whole].store != ctts::NO_REGION) {
+                t.whole = wholes[d.whole].store;
+                t.whole_at = (uint32_t)(region_off[t.whole] >> 3);
+                if (is_reuse[hti]) {
+                    t.flags |= ctts::TASK_REUSE;
+                    p->info.n_reuse_tasks++;
+                    p->info.reuse_bound_samples += h.bound;
+                } else {
+                    t.flags |= ctts::TASK_SOURCE;
+                    p->info.n_source_tasks++;
                 }
             }
-            last_index[ui] = (int32_t)(nt - ch.task_begin);   // index inside this chunk's launch
-            p->h_tasks[nt++] = t;
         }
+        return t;
+    };
+    for (size_t oi = 0; oi < order.size(); oi++) {
+        p->h_tasks[nt] = make_task(order[oi]);
+        last_index[ht_ui[order[oi]]] = (int32_t)(nt - ch.task_begin);   // index inside this chunk's launch
+        nt++;
     }
+    if (build_rc) return build_rc;
     ch.n_tasks = nt - ch.task_begin;
     p->n_tasks = nt;
     ch.grid = (uint32_t)std::min<uint64_t>((uint64_t)p->occ * (uint64_t)ctx->sm_count, std::max<uint32_t>(ch.n_tasks, 1));
@@ -1262,10 +1429,6 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
     if (ch.n_tasks)
         CU(ctx, cudaMemcpyAsync(p->d_tasks + ch.task_begin, p->h_tasks + ch.task_begin, (size_t)ch.n_tasks * sizeof(ctts::RegionTask),
                                 cudaMemcpyHostToDevice, st));
-    if (!canon_groups.empty()) {
-        // (pageable source: the copy is staged before the call returns)
-        CU(ctx, cudaMemcpyAsync(p->d_region_off, region_off.data(), canon_groups.size() * 8, cudaMemcpyHostToDevice, st));
-    }
     p->built_chunks++;
     p->info.n_tasks = p->n_tasks;
     p->info.n_global_tasks = p->n_global_tasks;
@@ -1312,10 +1475,10 @@ int launch_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, int16_t* d_pcm
     a.trim_scratch = p->d_trim;
     a.trim_scratch_words = p->trim_words;
     a.region_store = p->d_region_store;
-    a.region_off = p->d_region_off;
     a.region_state = p->d_region_state;
     a.chain = p->d_chain + ch.task_begin;
     a.ticket = p->d_ticket + c;
+    a.prof = p->d_prof;
     a.epoch = p->epoch;
     a.prm = p->prm;
     a.wcap = p->wcap;

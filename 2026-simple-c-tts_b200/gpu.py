@@ -30,6 +30,7 @@ class RunInfo(C.Structure):
         ("n_tasks", C.c_uint32), ("n_global_tasks", C.c_uint32),
         ("ctas_per_sm", C.c_uint32), ("grid", C.c_uint32),
         ("n_canon_tasks", C.c_uint32), ("n_dedup_tasks", C.c_uint32), ("dedup_bound_samples", C.c_uint64),
+        ("n_source_tasks", C.c_uint32), ("n_reuse_tasks", C.c_uint32), ("reuse_bound_samples", C.c_uint64),
     ]
 
 

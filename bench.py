@@ -428,7 +428,7 @@ def main() -> int:
 
     # ---- the same resident plan with the word-region deduplication switched off (every region assembled): reported
     #      beside `value` so that the share of the speed-up that comes from repeated words in the batch is visible
-    nodedup_ms = None
+    nodedup_ms = level1_ms = None
     zipf = None
     if rank == 0 and info.n_canon_tasks:
         os.environ["CTTS_GPU_REGION_DEDUP"] = "0"       # knobs are read once, by ctts_gpu_init
@@ -456,6 +456,13 @@ def main() -> int:
 
         nodedup_ms, c0, _ = resident_ms(g0, plan, d_out)
         assert np.array_equal(c0, counts)
+        os.environ["CTTS_GPU_REGION_DEDUP"] = "1"       # regions up to their contour only
+        g1 = gpu.GpuSynth(db, local_rank)
+        os.environ.pop("CTTS_GPU_REGION_DEDUP")
+        g1.set_stream(stream.cuda_stream)
+        level1_ms, c1, _ = resident_ms(g1, plan, d_out)
+        assert np.array_equal(c1, counts)
+        g1.close()
         # ---- one more point on the same axis: the same sentence generator over a Zipf vocabulary of 20 000 word types
         #      (rank r has probability ~ 1 / (r + 2.7)): about one token in ten occurs once in the batch
         if args.workload == "speed1" and not args.vocab and args.utts >= 1024:
@@ -470,7 +477,9 @@ def main() -> int:
                     "ms_per_step_without": z0_ms, "value_without_region_dedup": z_audio / (z0_ms / 1e3),
                     "region_tasks": int(zi.n_tasks), "canonical_regions": int(zi.n_canon_tasks),
                     "tasks_served_from_them": int(zi.n_dedup_tasks),
-                    "share_of_bound_samples": float(zi.dedup_bound_samples) / max(float(zi.bound_samples), 1.0)}
+                    "share_of_bound_samples": float(zi.dedup_bound_samples) / max(float(zi.bound_samples), 1.0),
+                    "whole_task_sources": int(zi.n_source_tasks), "tasks_copied_whole": int(zi.n_reuse_tasks),
+                    "share_of_bound_samples_copied_whole": float(zi.reuse_bound_samples) / max(float(zi.bound_samples), 1.0)}
         g0.close()
 
     # ---- e2e, host buffers, copies inside the timed region: (1) plan -> PCM through the drop-in call
@@ -577,10 +586,14 @@ def main() -> int:
                 "persistent_ctas": int(info.grid), "ctas_per_sm": int(info.ctas_per_sm),
                 "region_dedup": {
                     "what": "equal word regions of the batch are assembled ONCE PER LAUNCH (canonical tasks, inside the timed step) and "
-                            "copied by their other occurrences, which run their own contour; nothing is kept from one step to the next; "
-                            "CTTS_GPU_REGION_DEDUP=0 switches it off (value_without_region_dedup)",
+                            "copied by their other occurrences, which run their own contour; tasks that are equal as a whole (same "
+                            "region, same contour factors, same pause) are run once and copied; nothing is kept from one step to the "
+                            "next; CTTS_GPU_REGION_DEDUP=0 switches it off (value_without_region_dedup), =1 keeps the first level only",
                     "canonical_regions": int(info.n_canon_tasks), "tasks_served_from_them": int(info.n_dedup_tasks),
                     "share_of_bound_samples": float(info.dedup_bound_samples) / max(float(info.bound_samples), 1.0),
+                    "whole_task_sources": int(info.n_source_tasks), "tasks_copied_whole": int(info.n_reuse_tasks),
+                    "share_of_bound_samples_copied_whole": float(info.reuse_bound_samples) / max(float(info.bound_samples), 1.0),
+                    "ms_per_step_regions_only": level1_ms,
                     "ms_per_step_without": nodedup_ms,
                     "value_without_region_dedup": (audio_s / (nodedup_ms / 1e3)) if nodedup_ms else None,
                     "corpus_note": "the benchmark corpus (round-1 generator, SURVEY 8d) draws its sentences from ~190 words plus numbers "

@@ -183,6 +183,10 @@ typedef struct ctts_gpu_run_info {
     uint32_t n_canon_tasks;      /* distinct regions computed once */
     uint32_t n_dedup_tasks;      /* region tasks that take their samples from one of those */
     uint64_t dedup_bound_samples;/* sum of their upper bounds */
+    /* ... second level: tasks that are equal as a whole (same region, same contour factors, same pause behind it) */
+    uint32_t n_source_tasks;     /* tasks whose samples are also kept for the others */
+    uint32_t n_reuse_tasks;      /* tasks that copy them and run nothing */
+    uint64_t reuse_bound_samples;/* sum of the upper bounds of those */
 } ctts_gpu_run_info;
 int ctts_gpu_plan_info(const ctts_gpu_plan* plan, ctts_gpu_run_info* info);
 

@@ -735,21 +735,27 @@ def test_region_dedup_on_and_off(H, gpu, small_db, oracle_small, front_small, mo
     rng = np.random.default_rng(12)
     texts = [" ".join(rng.choice(words, size=int(rng.integers(3, 14)))) + rng.choice([".", "?", "!", ",", ""]) for _ in range(40)]
     texts += ["casa, casa; casa: casa. casa! casa?", "a casa casa-casa casa", "12 casas e 12 casas", "...", "", "casa", "casa casa"]
+    texts += [texts[0], texts[0], texts[5], texts[11], "bom dia mundo", "bom dia mundo", "olá bom dia mundo"]   # equal whole tasks
     speeds = [1.0] * len(texts)
     speeds[3] = 1.5
     speeds[11] = 0.7
+    speeds[-4] = 0.7
     plan = front_small.plan(texts, speeds)
     want = [oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))[0] for u in range(plan.n_utts)]
     outs = {}
-    for mode in ("1", "0"):
+    for mode in ("2", "1", "0"):
         monkeypatch.setenv("CTTS_GPU_REGION_DEDUP", mode)
         g = gpu.GpuSynth(small_db, 0)
         rp = g.create_plan(plan, prm)
         info = rp.info()
-        if mode == "1":
+        if mode != "0":
             assert info.n_canon_tasks >= 5 and info.n_dedup_tasks > 4 * info.n_canon_tasks, (info.n_canon_tasks, info.n_dedup_tasks)
         else:
             assert info.n_canon_tasks == 0 and info.n_dedup_tasks == 0
+        if mode == "2":      # second level: whole tasks that are equal (same region, same contour, same pause)
+            assert info.n_source_tasks >= 10 and info.n_reuse_tasks >= info.n_source_tasks, (info.n_source_tasks, info.n_reuse_tasks)
+        else:
+            assert info.n_source_tasks == 0 and info.n_reuse_tasks == 0
         for _ in range(2):          # a second run of the same plan: a new epoch of the region states
             rp.run()
         outs[mode] = rp.utterances()

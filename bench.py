@@ -612,9 +612,10 @@ def main() -> int:
                 # the stage is instruction-issue bound, so the issue-slot utilisation is the fraction that
                 # says how far the kernel is from ITS ceiling (ncu, committed captures; FP32 pipe utilisation beside it)
                 "issue_active_pct": facts.get("issue_active_pct"), "fma_pipe_pct": facts.get("fma_pipe_pct"),
-                "ceiling": "at 100 % issue slots the measured instruction count of a 4096-utterance launch (6.67 G warp instructions with "
-                           "the word-region deduplication, 10.82 G without; what is left is fixed by bit-exactness: DESIGN.md 6) takes "
-                           "5.7 ms = 0.28 of the HBM peak (9.3 ms = 0.17 without); the north star's 0.60 is 1.6 ms",
+                "ceiling": "at 100 % issue slots the measured instruction count of a 4096-utterance launch (4.69 G warp instructions with "
+                           "both levels of the deduplication, 6.67 G with equal regions only, 10.82 G without; what is left is fixed by "
+                           "bit-exactness: DESIGN.md 6) takes 4.0 ms = 0.40 of the HBM peak (5.7 ms / 9.3 ms for the other two); the "
+                           "north star's 0.60 is 1.6 ms",
                 "kernels_ncu": {k: ncu_facts(k) for k in step_kernels},
                 "frac_of_nominal_8000_GBs": achieved / 8000.0,   # the north star quotes ~8 TB/s; SURVEY 8d asks for both
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,

@@ -721,6 +721,39 @@ def test_packed_batch_call(H, gpu, synth_small, oracle_small, front_small, monke
         g.synth_batch_packed(plan, prm, np.zeros(used - 8, dtype=np.int16))
 
 
+def test_whole_task_copies_when_a_fade_out_reaches_back(H, gpu, small_db, oracle_small):
+    """Second level of the deduplication with fade-outs longer than short words (fade_out_ms = 150: 3307 samples): a
+    source task whose fade-out reaches back into the previous word does not share its samples (its result depends on
+    more than its own ops) and the tasks that were to copy it fall back to their canonical region / assemble
+    themselves.  Long crossfades and no word pause move the thresholds as well.  Bit-exact against the oracle."""
+    for variant in range(2):
+        cfg = H.shipped_config()
+        cfg.fade_out_ms = 150.0
+        if variant == 1:
+            cfg.word_pause_ms = 0.0
+            cfg.crossfade_ms = 120.0
+            cfg.crossfade_vowel_ms = 160.0
+        fr = H.front.Front(small_db, cfg, H.NORM_CSV)
+        prm = fr.params()
+        base = ["a e o a e o casa a e o", "o a o a o a mundo o a", "e casa e casa e casa e casa", "a o e bom dia a o e bom dia"]
+        texts = base * 3 + ["casa " + base[0], base[1] + " dia"]
+        speeds = [1.0] * len(texts)
+        speeds[5] = 0.6
+        plan = fr.plan(texts, speeds)
+        g = gpu.GpuSynth(small_db, 0)
+        rp = g.create_plan(plan, prm)
+        info = rp.info()
+        assert info.n_source_tasks >= 4 and info.n_reuse_tasks >= 8, (info.n_source_tasks, info.n_reuse_tasks)
+        for _ in range(2):
+            rp.run()
+        outs = rp.utterances()
+        for u in range(plan.n_utts):
+            want, _ = oracle_small.synth(prm, plan.utt_ops(u), float(speeds[u]))
+            _assert_same(outs[u], want, f"variant {variant} utt {u} {texts[u]!r}")
+        rp.close()
+        g.close()
+
+
 def small_db_bytes(H):
     return H.small_db()
 

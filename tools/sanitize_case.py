@@ -12,8 +12,15 @@ prm = fr.params()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 texts = H.corpus.batch(n, seed=5, target_chars=60) + ["olá mundo", "a, b. c? d!"]
 speeds = [1.0] * n + [1.5, 1.0]
+# repeated words and sentences: canonical regions, tasks resumed at their contour, whole tasks copied
+texts += ["bom dia mundo casa", "bom dia mundo casa", "olá bom dia mundo casa", "casa casa casa casa"]
+speeds += [1.0, 1.0, 1.0, 0.8]
 plan = fr.plan(texts, speeds)
 g = gpu.GpuSynth(db, 0)
+rp = g.create_plan(plan, prm)
+info = rp.info()
+print("canonical", info.n_canon_tasks, "resumed or copied", info.n_dedup_tasks, "sources", info.n_source_tasks, "copied whole", info.n_reuse_tasks)
+rp.close()
 outs = g.synth_list(plan, prm)
 orc = H.Oracle(db)
 for u, got in enumerate(outs):

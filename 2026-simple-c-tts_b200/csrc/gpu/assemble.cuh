@@ -125,7 +125,7 @@ __device__ __forceinline__ void run_task(const Smem& sm, const AsmArgs& A, uint3
         // done).  bcast[0] = base, bcast[2] / bcast[4] = lengths (NO_REGION: the producer gave up on it).
         if (tid < 3) {
             const unsigned long long* p = nullptr;
-            if (tid == 0 && !s.have_base) p = A.chain + s.pred;
+            if (tid == 0 && !s.have_base && task.thresh != 0u) p = A.chain + s.pred;   // (threshold 0: the count is not needed yet)
             if (tid == 1) p = A.region_state + task.region;
             if (tid == 2 && (task.flags & TASK_REUSE)) p = A.region_state + task.whole;
             unsigned long long v = NO_REGION;
@@ -139,7 +139,7 @@ __device__ __forceinline__ void run_task(const Smem& sm, const AsmArgs& A, uint3
             sm.bcast[2 * tid] = (uint32_t)v;
         }
         __syncthreads();
-        if (!s.have_base) {
+        if (!s.have_base && task.thresh != 0u) {
             s.base = sm.bcast[0];
             s.have_base = true;
         }

@@ -997,7 +997,10 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
     // region that holds audio (trimming / the contour may move samples into the tail), resets it.
     // A region with no unit (a pause) or a tiny one is appended to the task before it while the
     // sum still fits the window.
-    struct HostTask { uint32_t op_begin, op_end; uint64_t bound; uint32_t region_max; };
+    // base_lb: a LOWER bound of the utterance's sample count when the task starts (trimming may take a whole region
+    // away, pauses and untrimmed regions stay): a task whose threshold it meets need not wait for its predecessor
+    // before it starts
+    struct HostTask { uint32_t op_begin, op_end; uint64_t bound; uint32_t region_max; uint64_t base_lb; };
     std::vector<HostTask> ht;
     std::vector<uint3> pitch_jobs;
     std::vector<uint32_t> pitch_job_units;   // unit of every new table entry (to take them back if the fill fails)
@@ -1006,6 +1009,7 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
     for (uint32_t u = u0; u < u1; u++) {
         ht_begin[u - u0] = (uint32_t)ht.size();
         uint64_t tz = 0, count_ub = 0, rb = 0, L = 0;
+        uint64_t count_lb = 0, word_lb = 0, region_lb = 0;   // lower bounds: of the count, at the last MARK, at the start of the open region
         uint32_t r_units = 0, r_begin = ub[u];
         bool audio = false;
         auto close_region = [&](uint32_t r_end) {
@@ -1016,8 +1020,9 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
                 ht.back().bound += rb;
                 ht.back().region_max = (uint32_t)std::max<uint64_t>(ht.back().region_max, rb);
             } else {
-                ht.push_back(HostTask{r_begin, r_end, rb, (uint32_t)std::min<uint64_t>(rb, 0xffffffffull)});
+                ht.push_back(HostTask{r_begin, r_end, rb, (uint32_t)std::min<uint64_t>(rb, 0xffffffffull), region_lb});
             }
+            region_lb = count_lb;
             r_begin = r_end;
             rb = 0;
             r_units = 0;
@@ -1045,6 +1050,7 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
                     }
                     memcpy(&op.f2, &slot1, 4);
                     count_ub += cn;
+                    count_lb += (op.flags & CTTS_UNIT_AFTER_BOUNDARY) ? cn : cn - std::min(op.b, cn);
                     p->gather += cn;
                     rb += unit_append_bound(op, cn, L);
                     r_units++;
@@ -1054,6 +1060,7 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
                 case CTTS_OP_SILENCE:
                     tz += op.a;
                     count_ub += op.a;
+                    count_lb += op.a;
                     rb += op.a;
                     L += op.a;
                     break;
@@ -1062,10 +1069,11 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
                     break;
                 case CTTS_OP_WORD_END:
                     if (audio) tz = 0;
-                    if (op.flags & CTTS_WE_TRIM) L = 0;
+                    if (op.flags & CTTS_WE_TRIM) { L = 0; count_lb = word_lb; }
                     break;
                 case CTTS_OP_MARK:
                     audio = false;
+                    word_lb = count_lb;
                     close_region(k + 1);
                     break;
             }
@@ -1394,7 +1402,7 @@ int build_chunk(ctts_gpu_ctx* ctx, ctts_gpu_plan* p, uint32_t c, cudaStream_t st
         if (d.group != ctts::NO_REGION && groups[d.group].canon != ctts::NO_REGION && (k > 0 || d.thresh == 0)) {
             t.region = groups[d.group].canon;
             t.region_at = (uint32_t)(region_off[t.region] >> 3);
-            t.thresh = d.thresh;
+            t.thresh = h.base_lb >= d.thresh ? 0u : d.thresh;   // 0: met whatever the predecessor's count turns out to be
             t.w_op = d.w_op - op0;
             p->info.n_dedup_tasks++;
             p->info.dedup_bound_samples += h.bound;

@@ -318,7 +318,7 @@ int ctts_b200_synth_texts(ctts_front* front, ctts_gpu_ctx* gpu, const char* cons
     P.speeds = speeds;
     P.stats = stats;
     P.n = n;
-    const uint32_t piece_utts = opt && opt->piece_utts ? opt->piece_utts : 128;
+    const uint32_t piece_utts = opt && opt->piece_utts ? opt->piece_utts : 192;
     const uint32_t group = piece_utts < GROUP_UTTS ? piece_utts : GROUP_UTTS;
     long cores = sysconf(_SC_NPROCESSORS_ONLN);
     uint32_t T = opt && opt->threads ? opt->threads : (uint32_t)(cores > 1 ? cores - 1 : 1);

@@ -51,7 +51,7 @@ struct Knobs {
     int pitch_slots = 0;              // CTTS_GPU_PITCH_SLOTS: capacity of the unit-head pitch table (tests: a table that fills up)
     int ctas_per_sm = 3;              // CTTS_GPU_CTAS_PER_SM: occupancy the assembly window is sized for
     int window = 0;                   // CTTS_GPU_WINDOW: shared window in samples (tests: force the HBM-window path)
-    uint64_t chunk_samples = 128ull << 20;   // CTTS_GPU_CHUNK_SAMPLES: output samples per launch of ctts_gpu_synth_batch
+    uint64_t chunk_samples = 192ull << 20;   // CTTS_GPU_CHUNK_SAMPLES: output samples per launch of ctts_gpu_synth_batch
     bool task_times = false;          // CTTS_GPU_TASK_TIMES=1: resident plans print the time their CTAs spent per task class
                                       // (only in a library built with -DCTTS_ASM_PROF=1)
     int region_dedup = 2;             // CTTS_GPU_REGION_DEDUP=0: assemble every word region of a batch, equal ones too;
@@ -69,7 +69,7 @@ struct Knobs {
         pitch_slots = (int)std::max(0ll, num("CTTS_GPU_PITCH_SLOTS", 0));
         ctas_per_sm = (int)std::max(1ll, std::min(8ll, num("CTTS_GPU_CTAS_PER_SM", 3)));
         window = (int)std::max(0ll, num("CTTS_GPU_WINDOW", 0));
-        chunk_samples = (uint64_t)std::max(1ll, num("CTTS_GPU_CHUNK_SAMPLES", 128ll << 20));
+        chunk_samples = (uint64_t)std::max(1ll, num("CTTS_GPU_CHUNK_SAMPLES", 192ll << 20));
         region_dedup = (int)num("CTTS_GPU_REGION_DEDUP", 2);
         task_times = num("CTTS_GPU_TASK_TIMES", 0) != 0;
         wsola_speculate = num("CTTS_GPU_WSOLA_SPECULATE", 1) != 0;
@@ -2013,7 +2013,8 @@ int ctts_gpu_synth_batch_packed(ctts_gpu_ctx* ctx, const ctts_batch_plan* plan, 
     int rc = ctts_gpu_session_begin(ctx, params, pcm_out, capacity, nullptr, nullptr, &s);
     if (rc) return rc;
     // pieces of about chunk_samples / 2400 utterances ... by ops: an op appends at most a few thousand samples, so
-    // cut by op count (no bounds are known before a piece is compiled): ~45 k ops ~ 128 sentences of 200 characters
+    // cut by op count (no bounds are known before a piece is compiled): ~70 k ops ~ 192 sentences of 200 characters (measured: text -> PCM of a mixed-speed batch 105 ms with pieces of
+    // 128, 97 with 192, 99 with 256; at speed 1.0 no difference)
     const uint64_t ops_per_piece = std::max<uint64_t>(ctx->knobs.chunk_samples / 2800, 64);
     for (uint32_t u0 = 0, u = 0; u < n && !rc; u++) {
         if (plan->utt_op_begin[u + 1] - plan->utt_op_begin[u0] >= ops_per_piece || u + 1 == n) {

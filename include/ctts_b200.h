@@ -31,7 +31,7 @@ void ctts_b200_plan_cache_stats(ctts_b200_plan_cache* cache, uint64_t* hits, uin
                                 uint64_t* bytes);
 
 typedef struct ctts_b200_options {
-    uint32_t piece_utts;     /* most utterances per device piece (0: 128); planner jobs are groups of 16 */
+    uint32_t piece_utts;     /* most utterances per device piece (0: 192); planner jobs are groups of 16 */
     uint32_t threads;        /* planner threads (0: host cores - 1, at least 1, at most 32) */
     ctts_gpu_chunk_fn on_piece;   /* may be NULL: called in order as utterance ranges arrive in pcm_out */
     void* user;

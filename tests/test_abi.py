@@ -55,6 +55,43 @@ def test_capacity_hint_covers_the_bounds(H, small_db, front_small):
     assert pipe.capacity_hint(front_small, pipe.TextBatch(texts, speeds)) >= need
 
 
+def test_ctypes_mirrors_match_the_headers(H, tmp_path):
+    """Every struct that crosses the C-ABI: sizeof and the offset of the last member as gcc sees them in include/*.h
+    against the ctypes mirrors the Python host side (and these tests) use."""
+    import subprocess
+    gpu = H.importlib.import_module("2026-simple-c-tts_b200.gpu")
+    pipe = H.importlib.import_module("2026-simple-c-tts_b200.pipeline")
+    pairs = [
+        ("ctts_gpu_run_info", "reuse_bound_samples", gpu.RunInfo),
+        ("ctts_gpu_wsola_stats", "walked_frames", gpu.WsolaStats),
+        ("ctts_b200_options", "cache", pipe.Options),
+        ("ctts_b200_timing", "reserved", pipe.Timing),
+        ("ctts_front_config", None, H.front.Config),
+        ("ctts_assembly_params", None, H.front.AssemblyParams),
+        ("ctts_batch_plan", "ops", H.front.CBatchPlan),
+        ("ctts_plan_op", "e1", None),
+    ]
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "ctts_plan.h"', '#include "ctts_front.h"',
+             '#include "ctts_gpu.h"', '#include "ctts_b200.h"', "int main(void) {"]
+    for name, last, _ in pairs:
+        off = f"offsetof({name}, {last})" if last else "0"
+        lines.append(f'  printf("{name} %zu %zu\\n", sizeof({name}), (size_t){off});')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "sizes.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(H.ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict((l.split()[0], (int(l.split()[1]), int(l.split()[2]))) for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, last, mirror in pairs:
+        size, off = out[name]
+        if mirror is None:
+            assert size == H.front.OP_DTYPE.itemsize and off == H.front.OP_DTYPE.fields[last][1], name
+            continue
+        assert C.sizeof(mirror) == size, (name, C.sizeof(mirror), size)
+        if last:
+            assert getattr(mirror, last).offset == off, (name, last)
+
+
 def test_plan_op_abi_is_32_bytes(H):
     assert H.front.OP_DTYPE.itemsize == 32
     assert C.sizeof(H.front.AssemblyParams) == 32

@@ -137,3 +137,20 @@ def test_threaded_planning_is_identical(H, front_small, monkeypatch):
         assert np.array_equal(a.utt_op_begin, b.utt_op_begin) and a.ops.tobytes() == b.ops.tobytes()
         assert np.array_equal(a.found, b.found) and np.array_equal(a.missing, b.missing)
         assert np.array_equal(a.speed, b.speed)
+
+
+def test_zipf_vocabulary_is_seeded_and_skewed(H):
+    """corpus.Vocabulary (the vocabulary-size sensitivity of bench.py): deterministic for a seed, the shipped word
+    list first, rank-frequency roughly 1 / (rank + 2.7); the default generator is untouched by it."""
+    import collections
+    c = H.corpus
+    v1, v2 = c.Vocabulary(5000, seed=7), c.Vocabulary(5000, seed=7)
+    assert v1.words == v2.words and len(set(v1.words)) == 5000
+    assert set(v1.words[:len(dict.fromkeys(c.WORDS))]) == set(c.WORDS)
+    a = c.batch(300, seed=3, vocab=v1)
+    assert a == c.batch(300, seed=3, vocab=v2) and a != c.batch(300, seed=4, vocab=v1)
+    counts = collections.Counter(w.strip(".,;:?!").lower() for t in a for w in t.split() if w.strip(".,;:?!-").isalpha())
+    top = counts.most_common(1)[0][1] / sum(counts.values())
+    assert 0.02 < top < 0.08                      # p(rank 0) = 1 / (2.7 * H) ~ 4 %
+    assert sum(1 for n in counts.values() if n == 1) > 0.25 * len(counts)   # a long tail of words seen once
+    assert c.batch(5, seed=1234)[0].startswith("Diferente trabalho")        # the benchmark corpus itself did not move
